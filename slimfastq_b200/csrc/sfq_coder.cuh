@@ -1,0 +1,323 @@
+// Range coder + the three adaptive frequency models, in the layouts the sm_100a kernels use.
+//
+// Behaviour follows the reference (coder.hpp, base2_ranger.hpp, log64_ranger.hpp,
+// power_ranger.hpp); the data layouts do not:
+//   * a 64/256-symbol model is NSYM packed 32-bit slots  [aux:8 | sym^index:8 | freq:16].
+//     Storing sym XOR slot-index makes all-zero memory the reference's start state (every
+//     unused slot k implicitly holds symbol k with freq 0, log64_ranger.hpp:103-105,126-127),
+//     and the aux bytes of slots 0..5 hold total (24 bit), count and iend, so the 16 bytes of
+//     slots 0..3 are the whole hot state of a context: one 16-byte load and one 16-byte store
+//     per coded symbol in the common case (hot symbols migrate to the front slots).
+//   * base contexts live in a per-chunk open-addressing hash table (or a direct table at
+//     level 1) because a chunk can touch at most `nbases` of the 2^22..2^26 contexts and an
+//     untouched context is by definition (3,3,3,3) (base2_ranger.hpp:69-72).
+#pragma once
+#include "sfq_common.cuh"
+
+#define SFQ_RC_TOP (1u << 24)
+
+// ------------------------------------------------------------------ byte sink / source
+struct SfqSink {
+    uint8_t *p;
+    uint32_t n, cap;
+    SFQ_HD void init(uint8_t *buf, uint32_t capacity) { p = buf; n = 0; cap = capacity; }
+    SFQ_HD void put(uint8_t c) {
+        if (n < cap) p[n] = c;
+        n++;                      // n > cap afterwards <=> overflow (reported as SFQ_E_CAP)
+    }
+    SFQ_HD bool overflow() const { return n > cap; }
+};
+
+// ------------------------------------------------------------------ encoder  (coder.hpp:34-39,52-81)
+struct SfqEnc {
+    uint64_t low;
+    uint32_t range;
+    SfqSink out;
+    bool live;
+    SFQ_HD void reset() { live = false; low = 0; range = 0xFFFFFFFFu; out.p = nullptr; out.n = 0; out.cap = 0; }
+    SFQ_HD void start(uint8_t *buf, uint32_t cap) { low = 0; range = 0xFFFFFFFFu; out.init(buf, cap); live = true; }
+    SFQ_HD void encode(uint32_t cum, uint32_t freq, uint32_t tot) {
+        range /= tot;
+        low += (uint32_t)(cum * range);
+        range *= freq;
+        while (range < SFQ_RC_TOP) {
+            if ((low ^ (low + range)) & (0xffULL << 56))
+                range = (((uint32_t)low) | (SFQ_RC_TOP - 1)) - (uint32_t)low;
+            out.put((uint8_t)(low >> 56));
+            range <<= 8;
+            low <<= 8;
+        }
+    }
+    SFQ_HD void finish() {
+        for (int i = 0; i < 8; i++) { out.put((uint8_t)(low >> 56)); low <<= 8; }
+    }
+};
+
+// ------------------------------------------------------------------ decoder  (coder.hpp:41-49,83-102)
+struct SfqDec {
+    uint64_t low, code;
+    uint32_t range;
+    const uint8_t *p;
+    uint32_t n, pos;
+    bool valid;
+    SFQ_HD uint8_t next() { return pos < n ? p[pos++] : (uint8_t)0; }   // EOF reads as 0, filer.hpp:94-97
+    SFQ_HD void start(const uint8_t *buf, uint32_t size) {
+        p = buf; n = size; pos = 0; low = 0; range = 0xFFFFFFFFu; code = 0;
+        valid = (buf != nullptr && size != 0);
+        for (int i = 0; i < 8; i++) code = (code << 8) | next();
+    }
+    SFQ_HD uint32_t get_freq(uint32_t tot) {
+        range /= tot;
+        // code < range * tot <= 2^32 holds for any stream an encoder can write; the 64-bit form is
+        // kept so that a corrupt stream behaves like the reference instead of trapping.
+        return (code >> 32) ? (uint32_t)(code / range) : ((uint32_t)code / range);
+    }
+    SFQ_HD void decode(uint32_t cum, uint32_t freq) {
+        uint32_t t = cum * range;
+        low += t;
+        code -= t;
+        range *= freq;
+        while (range < SFQ_RC_TOP) {
+            if ((low ^ (low + range)) & (0xffULL << 56))
+                range = (((uint32_t)low) | (SFQ_RC_TOP - 1)) - (uint32_t)low;
+            code = (code << 8) | next();
+            range <<= 8;
+            low <<= 8;
+        }
+    }
+};
+
+// ------------------------------------------------------------------ 4-symbol model (base2_ranger.hpp:35-105)
+// v holds freq[0..3] in bytes 0..3.
+SFQ_HD uint32_t sfq_b2_update(uint32_t v, uint32_t s) {
+    if (((v >> (8 * s)) & 0xffu) > 254u)
+        v = ((v & 0xFEFEFEFEu) >> 1) | (v & 0x01010101u);
+    return v + (1u << (8 * s));
+}
+SFQ_HD uint32_t sfq_b2_put(uint32_t v, SfqEnc &rc, uint32_t s) {
+    uint32_t f0 = v & 0xff, f1 = (v >> 8) & 0xff, f2 = (v >> 16) & 0xff, f3 = v >> 24;
+    uint32_t tot = f0 + f1 + f2 + f3;
+    uint32_t cum = (s > 0 ? f0 : 0) + (s > 1 ? f1 : 0) + (s > 2 ? f2 : 0);
+    uint32_t f = (v >> (8 * s)) & 0xff;
+    rc.encode(cum, f, tot);
+    return sfq_b2_update(v, s);
+}
+SFQ_HD uint32_t sfq_b2_get(uint32_t v, SfqDec &rc, uint32_t &sym) {
+    uint32_t f0 = v & 0xff, f1 = (v >> 8) & 0xff, f2 = (v >> 16) & 0xff, f3 = v >> 24;
+    uint32_t tot = f0 + f1 + f2 + f3;
+    uint32_t prob = rc.get_freq(tot);
+    uint32_t s, cum, f;
+    if (prob < f0) { s = 0; cum = 0; f = f0; }
+    else if (prob < f0 + f1) { s = 1; cum = f0; f = f1; }
+    else if (prob < f0 + f1 + f2) { s = 2; cum = f0 + f1; f = f2; }
+    else { s = 3; cum = f0 + f1 + f2; f = f3; }
+    rc.decode(cum, f);
+    sym = s;
+    return sfq_b2_update(v, s);
+}
+
+// Per-chunk base-context table.  `dense` (level 1: 2^18 contexts) stores freq ^ 0x03030303 so
+// zeroed memory is the start state; otherwise 64-bit slots (ctx+1)<<32 | freq with linear probing.
+struct SfqGenTable {
+    uint64_t *slots;       // hash slots, or the dense u32 table reinterpret-cast
+    uint32_t hbits;        // log2(#hash slots)
+    uint32_t used;         // occupied hash slots
+    uint32_t dense;
+    SFQ_HD void init(void *mem, uint32_t hash_bits, bool is_dense) {
+        slots = (uint64_t *)mem; hbits = hash_bits; used = 0; dense = is_dense;
+    }
+    // Returns the slot index of ctx (inserting the start state if absent) or 0xFFFFFFFF if full.
+    SFQ_HD uint32_t find(uint32_t ctx, uint32_t &v) {
+        if (dense) {
+            v = ((const uint32_t *)slots)[ctx] ^ 0x03030303u;
+            return ctx;
+        }
+        const uint32_t mask = (1u << hbits) - 1u;
+        uint32_t h = (ctx * 2654435761u) >> (32 - hbits);
+        const uint32_t key = ctx + 1u;
+        for (;;) {
+            uint64_t k = slots[h];
+            uint32_t kk = (uint32_t)(k >> 32);
+            if (kk == key) { v = (uint32_t)k; return h; }
+            if (kk == 0) {
+                if (used + 1u >= mask) return 0xFFFFFFFFu;
+                used++;
+                v = 0x03030303u;
+                return h;
+            }
+            h = (h + 1u) & mask;
+        }
+    }
+    SFQ_HD void store(uint32_t slot, uint32_t ctx, uint32_t v) {
+        if (dense) ((uint32_t *)slots)[slot] = v ^ 0x03030303u;
+        else slots[slot] = ((uint64_t)(ctx + 1u) << 32) | v;
+    }
+};
+
+// ------------------------------------------------------------------ 64 / 256-symbol models
+// log64_ranger.hpp:36-140 (NSYM 64, STEP 6, MAX_FREQ 65472, saturation slack 20) and
+// power_ranger.hpp:36-131 (256, 14, 32736, 256) are one scheme; see the layout note on top.
+template <int NSYM, int STEP, int MAXF, int SLACK>
+struct SfqAModel {
+    uint32_t *m;   // NSYM packed slots in global memory
+
+    SFQ_HD static uint32_t freq_of(uint32_t s) { return s & 0xffffu; }
+    SFQ_HD static uint32_t sym_of(uint32_t s, uint32_t i) { return ((s >> 16) & 0xffu) ^ (i & 0xffu); }
+    SFQ_HD static uint32_t aux_of(uint32_t s) { return s >> 24; }
+    SFQ_HD static uint32_t pack(uint32_t aux, uint32_t sym, uint32_t i, uint32_t f) {
+        return (aux << 24) | (((sym ^ i) & 0xffu) << 16) | f;
+    }
+    SFQ_HD uint32_t total() const { return aux_of(m[0]) | (aux_of(m[1]) << 8) | (aux_of(m[2]) << 16); }
+    SFQ_HD void set_total(uint32_t t) {
+        m[0] = (m[0] & 0x00ffffffu) | ((t & 0xffu) << 24);
+        m[1] = (m[1] & 0x00ffffffu) | (((t >> 8) & 0xffu) << 24);
+        m[2] = (m[2] & 0x00ffffffu) | (((t >> 16) & 0xffu) << 24);
+    }
+    SFQ_HD uint32_t iend() const { return aux_of(m[4]) | (aux_of(m[5]) << 8); }
+    SFQ_HD void set_iend(uint32_t e) {
+        m[4] = (m[4] & 0x00ffffffu) | ((e & 0xffu) << 24);
+        m[5] = (m[5] & 0x00ffffffu) | (((e >> 8) & 0xffu) << 24);
+    }
+
+    // update_freq (log64:69-87, power:68-86).  Returns the symbol that was in slot i.
+    SFQ_HD uint32_t update(uint32_t i, uint32_t tot) {
+        uint32_t s = m[i];
+        uint32_t f = freq_of(s);
+        const uint32_t sym = sym_of(s, i);
+        if (f > (uint32_t)(MAXF - STEP)) {
+            if (i == 0 && f + (uint32_t)SLACK > tot) return sym;
+            const uint32_t e = iend();
+            tot = 0;
+            for (uint32_t j = 0; j < e; j++) {       // normalize(): halve every live slot
+                uint32_t sj = m[j];
+                uint32_t fj = freq_of(sj) >> 1;
+                m[j] = (sj & 0xffff0000u) | fj;
+                tot += fj;
+            }
+            s = m[i];
+            f = freq_of(s);
+        }
+        f += STEP;
+        tot += STEP;
+        m[i] = (s & 0xffff0000u) | f;
+        set_total(tot);
+        if (i == 0) return sym;                      // `++count` is not evaluated for slot 0
+        uint32_t c3 = m[3];
+        uint32_t count = (aux_of(c3) + 1u) & 0xffu;
+        m[3] = (c3 & 0x00ffffffu) | (count << 24);
+        if ((count & 0xfu) == 0) {
+            uint32_t a = m[i], b = m[i - 1];
+            if (freq_of(a) > freq_of(b)) {           // down_level(): swap slots i and i-1
+                uint32_t sa = sym_of(a, i), sb = sym_of(b, i - 1);
+                m[i]     = pack(aux_of(a), sb, i,     freq_of(b));
+                m[i - 1] = pack(aux_of(b), sa, i - 1, freq_of(a));
+            }
+        }
+        return sym;
+    }
+
+    SFQ_HD void put(SfqEnc &rc, uint32_t sym) {      // log64:98-112, power:93-106
+        if (iend() <= sym) set_iend(sym + 1u);
+        uint32_t i = 0, sumf = 0, s;
+        for (;; i++) {
+            s = m[i];
+            if (sym_of(s, i) == sym) break;
+            sumf += freq_of(s);
+        }
+        const uint32_t tot = total();
+        rc.encode(sumf + i, freq_of(s) + 1u, tot + NSYM);
+        update(i, tot);
+    }
+
+    SFQ_HD uint32_t get(SfqDec &rc) {                // log64:114-138, power:108-130
+        const uint32_t tot = total();
+        const uint32_t prob = rc.get_freq(tot + NSYM);
+        uint32_t i = 0, sumf = 0, f = 0;
+        for (; i < NSYM; i++) {
+            f = freq_of(m[i]);
+            if (sumf + f + 1u <= prob) sumf += f + 1u; else break;
+        }
+        if (i >= NSYM) { i = NSYM - 1; f = freq_of(m[i]); }   // only a corrupt stream gets here
+        if (iend() <= i) set_iend(i + 1u);
+        rc.decode(sumf, f + 1u);
+        return update(i, tot);
+    }
+};
+typedef SfqAModel<64, 6, 65472, 20> SfqLog64;
+typedef SfqAModel<256, 14, 32736, 256> SfqPower;
+
+// PowerRangerU: variable-length u64 over 14 consecutive 256-symbol models (power_ranger.hpp:133-192)
+struct SfqPowerU {
+    uint32_t *m;   // 14 models, SFQ_PW_WORDS apart
+    SFQ_HD SfqPower at(int k) const { SfqPower p; p.m = m + (size_t)k * SFQ_PW_WORDS; return p; }
+    SFQ_HD void put(SfqEnc &rc, uint64_t num) {
+        if (num <= 0x7f) { at(0).put(rc, (uint32_t)num); return; }
+        if (num < 0x7ffe) {
+            at(0).put(rc, (uint32_t)(0xff & (0x80 | (num >> 8))));
+            at(1).put(rc, (uint32_t)(0xff & num));
+            return;
+        }
+        at(0).put(rc, 0xff);
+        if (num < (1ULL << 32)) {
+            at(1).put(rc, 0xfe);
+            for (int sh = 0, i = 2; sh < 32; sh += 8, i++) at(i).put(rc, (uint32_t)(0xff & (num >> sh)));
+        } else {
+            at(1).put(rc, 0xff);
+            for (int sh = 0, i = 6; sh < 64; sh += 8, i++) at(i).put(rc, (uint32_t)(0xff & (num >> sh)));
+        }
+    }
+    SFQ_HD uint64_t get(SfqDec &rc) {
+        uint64_t num = at(0).get(rc);
+        if (num > 0x7f) {
+            num = (num << 8) | at(1).get(rc);
+            if (num < 0xfffe) num &= 0x7fff;
+            else if (num == 0xfffe) {
+                num = 0;
+                for (int sh = 0, i = 2; sh < 32; sh += 8, i++) num |= (uint64_t)at(i).get(rc) << sh;
+            } else {
+                num = 0;
+                for (int sh = 0, i = 6; sh < 64; sh += 8, i++) num |= (uint64_t)at(i).get(rc) << sh;
+            }
+        }
+        return num;
+    }
+};
+
+// ------------------------------------------------------------------ exception-list streams (xfile.cpp:36-110)
+// Lazily created on the first put; closing writes put(0) and the coder flush.
+struct SfqXSave {
+    SfqEnc rc;
+    SfqPowerU num;
+    SfqPower str;
+    uint8_t *buf;
+    uint32_t cap;
+    SFQ_HD void init(uint32_t *pool, int xslot, uint8_t *out, uint32_t capacity) {
+        rc.reset();
+        num.m = pool + (size_t)(SFQ_PW_X_BASE + xslot * SFQ_PW_PER_X) * SFQ_PW_WORDS;
+        str.m = num.m + (size_t)14 * SFQ_PW_WORDS;
+        buf = out; cap = capacity;
+    }
+    SFQ_HD void open() { if (!rc.live) rc.start(buf, cap); }
+    SFQ_HD void put(uint64_t v) { open(); num.put(rc, v); }
+    SFQ_HD void put_chr(uint8_t c) { open(); str.put(rc, c); }
+    // returns stream size (0 = never created); sets ovf on arena overflow
+    SFQ_HD uint32_t close(bool &ovf) {
+        if (!rc.live) return 0;
+        put(0);
+        rc.finish();
+        if (rc.out.overflow()) ovf = true;
+        return rc.out.n;
+    }
+};
+struct SfqXLoad {
+    SfqDec rc;
+    SfqPowerU num;
+    SfqPower str;
+    SFQ_HD void init(uint32_t *pool, int xslot, const uint8_t *in, uint32_t size) {
+        num.m = pool + (size_t)(SFQ_PW_X_BASE + xslot * SFQ_PW_PER_X) * SFQ_PW_WORDS;
+        str.m = num.m + (size_t)14 * SFQ_PW_WORDS;
+        rc.start(in, size);
+    }
+    SFQ_HD uint64_t get() { return rc.valid ? num.get(rc) : 0; }   // absent stream reads 0 forever, xfile.cpp:90-93
+    SFQ_HD uint8_t get_chr() { return (uint8_t)str.get(rc); }
+};

@@ -1,0 +1,96 @@
+// Shared definitions for the sm_100a kernels of the slimfastq hot path.
+//
+// Every per-chunk coder routine is written as an SFQ_HD function over plain pointers so that
+// (a) the kernels are thin wrappers and (b) tests/emul can compile the very same routines with
+// g++ and single-step them on the CPU-only dev container.  The emulation build is test tooling:
+// the shipped library (sfq_abi.cu) only ever launches the __global__ wrappers and refuses to
+// work without a CUDA device.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define SFQ_HD __host__ __device__ __forceinline__
+#define SFQ_HDN static __host__ __device__
+#else
+#define SFQ_HD inline
+#define SFQ_HDN static
+#endif
+
+// Stream ids inside a chunk.  Names/ordering follow the reference's stream creation sites
+// (usrs.cpp:47-54,396-398; gens.cpp:68-69; recs.cpp:46).
+enum {
+    SFQ_S_REC = 0, SFQ_S_GEN, SFQ_S_QLT, SFQ_S_GEN_NS, SFQ_S_GEN_NN, SFQ_S_REC_X,
+    SFQ_S_USR_X, SFQ_S_USR_XQ, SFQ_S_USR_PFG, SFQ_S_USR_PFQ, SFQ_NSTREAMS
+};
+
+// Per-chunk status codes written by kernels; the host turns the first non-zero one into the
+// reference's croak text (config.cpp:54-68) and a non-zero return.
+enum {
+    SFQ_OK = 0,
+    SFQ_E_AT = 1,          // record does not start with '@'            usrs.cpp:158-163,200
+    SFQ_E_PLUS = 2,        // third line does not start with '+'        usrs.cpp:232,346
+    SFQ_E_TRUNC = 3,       // truncated record / missing final newline  usrs.cpp:165-168
+    SFQ_E_OVERSIZE = 4,    // id >= 8 KiB or line >= 64 KiB             usrs.hpp:34-36 (unsupported)
+    SFQ_E_BASE = 5,        // unexpected genome char                    gens.cpp:125-126
+    SFQ_E_NBYTE = 6,       // switched N byte                           gens.cpp:107-108
+    SFQ_E_SEPS = 7,        // > 64 separators in a header               recs.cpp:153-154
+    SFQ_E_CAP = 8,         // a stream outgrew its device arena (host retries with more room)
+    SFQ_E_TABLE = 9,       // base-context hash table full (host retries with a larger table)
+    SFQ_E_FIRSTHDR = 10,   // first header > 399 chars                  recs.cpp:31,69-70
+    SFQ_E_CORRUPT = 11,    // decoder: impossible value in a stream
+    SFQ_E_EMPTYSEQ = 12,   // first record of a chunk has an empty base line (usrs.cpp:216-231 cannot represent it)
+};
+
+// Sizes of the per-chunk model pools.
+#define SFQ_L64_WORDS   64u            // one quality context  = 64 packed slots = 256 B
+#define SFQ_PW_WORDS    256u           // one 256-symbol model = 256 packed slots = 1 KiB
+// 256-symbol model instances per chunk:
+//   header fields: 66 x (type, str, num[14])            recs.hpp:42-48
+//   7 exception streams x (num[14], str)                xfile.hpp:41-42
+//   1 quality escape model                              qlts.hpp:44
+#define SFQ_PW_REC_BASE   0u
+#define SFQ_PW_PER_FIELD  16u
+#define SFQ_PW_X_BASE     (66u * 16u)
+#define SFQ_PW_PER_X      15u
+#define SFQ_PW_QEX        (SFQ_PW_X_BASE + 7u * SFQ_PW_PER_X)
+#define SFQ_PW_PER_CHUNK  (SFQ_PW_QEX + 1u)      // 1162 models = 1.13 MiB per resident chunk
+// exception-stream slot -> stream id
+#define SFQ_X_NS 0
+#define SFQ_X_NN 1
+#define SFQ_X_REC 2
+#define SFQ_X_LLEN 3
+#define SFQ_X_QLEN 4
+#define SFQ_X_SGEN 5
+#define SFQ_X_SQLT 6
+
+#define SFQ_MAX_ID_LLEN 0x2000
+#define SFQ_MAX_GN_LLEN 0x10000
+
+// What the host learns about a chunk from the planning kernel, and what every coder needs.
+struct SfqChunkMeta {
+    uint64_t text_off;      // byte offset of the chunk's first record in the FASTQ buffer
+    uint64_t text_len;      // bytes of FASTQ text in the chunk
+    uint64_t out_len;       // bytes the decoder will print for it (== text_len unless the input
+                            // has one of the reference's lossy cases, e.g. a 2nd id that differs)
+    uint64_t line0;         // index of the chunk's first line in the line-start table
+    uint32_t nrec;          // records in the chunk (num_records, usrs.cpp:405)
+    uint32_t nbases;        // sum of coded base-line lengths
+    uint32_t nquals;        // sum of coded quality-line lengths
+    uint32_t hdr_bytes;     // sum of header lengths (without '@' and '\n')
+    int32_t  llen;          // `llen` info key: first record's base-line length (usrs.cpp:265)
+    uint8_t  solid;         // usr.solid  (usrs.cpp:242-263)
+    uint8_t  two_id;        // usr.2id    (usrs.cpp:235-239,266)
+    uint8_t  n_byte;        // gen.N_byte (gens.cpp:100-105); 0 = key absent
+    uint8_t  pad;
+    uint32_t extra_hi;      // qlt.extra.hi (qlts.cpp:57-60)
+    uint32_t status;        // SFQ_OK or first error
+    uint32_t status_arg;    // record number / offending byte for the message
+};
+
+// Output arena of one resident chunk: SFQ_NSTREAMS sub-ranges.
+struct SfqArena {
+    uint64_t off[SFQ_NSTREAMS];    // byte offset of each stream's region in the arena buffer
+    uint32_t cap[SFQ_NSTREAMS];
+    uint32_t size[SFQ_NSTREAMS];   // filled by the coders (0 = stream never created)
+};

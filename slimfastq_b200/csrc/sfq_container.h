@@ -1,0 +1,62 @@
+// The chunked .sfq container that replaces the reference's 8 KiB-page WORM file (filer.cpp) on this
+// path.  Host-only definitions shared by the C-ABI library, the CLI and the test emulation.
+//
+//   file   = SfqFileHeader | blob[0] | blob[1] | ... | u64 blob_offset[nchunks] (index)
+//   blob   = SfqBlobHeader | rec_first bytes | stream bytes in SFQ_S_* order, unpadded
+//
+// A blob carries exactly what the reference keeps for a standalone file: the semantic keys of its
+// info stream (config.level, llen, usr.solid, usr.2id, gen.N_byte, num_records, rec.first,
+// qlt.extra.hi) and the named range-coded streams, byte-identical to the reference's.
+// The first 16 bytes are the stamp the reference sniffs (config.cpp:295-304); the next 16 tell the
+// two container kinds apart.  All integers little-endian.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "sfq_common.cuh"
+
+#define SFQ_STAMP      "whoami=slimfastq"           /* 16 bytes */
+#define SFQ_KIND       "\nformat=b200.c1\n"         /* 16 bytes */
+#define SFQ_BLOB_MAGIC 0x43514653u                  /* "SFQC" */
+#define SFQ_INTERNAL_VERSION 6                      /* config.cpp:44 */
+
+#pragma pack(push, 1)
+struct SfqFileHeader {
+    char     stamp[16];
+    char     kind[16];
+    uint32_t version;        // SFQ_INTERNAL_VERSION
+    uint32_t level;          // config.level
+    uint64_t orig_size;      // orig.size
+    uint64_t nchunks;
+    uint64_t chunk_bytes;
+    uint64_t index_off;      // file offset of the blob-offset index
+};                           // 72 bytes
+struct SfqBlobHeader {
+    uint32_t magic;
+    uint32_t level;
+    uint64_t text_len;       // FASTQ bytes of the chunk in the original input
+    uint64_t out_len;        // FASTQ bytes the chunk decodes to (UsrLoad::save, usrs.cpp:512-529)
+    uint32_t nrec;           // num_records
+    uint32_t nbases, nquals, hdr_bytes;
+    int32_t  llen;           // llen
+    uint8_t  solid, two_id, n_byte, pad;
+    uint32_t extra_hi;       // qlt.extra.hi
+    uint32_t rec_first_len;  // rec.first follows the header
+    uint32_t ssize[SFQ_NSTREAMS];
+};                           // 96 bytes
+#pragma pack(pop)
+
+static inline void sfq_file_header_init(SfqFileHeader *h, int level, uint64_t orig, uint64_t nchunks,
+                                        uint64_t chunk_bytes, uint64_t index_off) {
+    memcpy(h->stamp, SFQ_STAMP, 16);
+    memcpy(h->kind, SFQ_KIND, 16);
+    h->version = SFQ_INTERNAL_VERSION; h->level = (uint32_t)level; h->orig_size = orig;
+    h->nchunks = nchunks; h->chunk_bytes = chunk_bytes; h->index_off = index_off;
+}
+static inline bool sfq_is_chunked_container(const uint8_t *p, size_t n) {
+    return n >= sizeof(SfqFileHeader) && !memcmp(p, SFQ_STAMP, 16) && !memcmp(p + 16, SFQ_KIND, 16);
+}
+static inline uint64_t sfq_blob_size(const SfqBlobHeader *b) {
+    uint64_t s = sizeof(SfqBlobHeader) + b->rec_first_len;
+    for (int k = 0; k < SFQ_NSTREAMS; k++) s += b->ssize[k];
+    return s;
+}

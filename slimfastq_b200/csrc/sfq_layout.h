@@ -1,0 +1,47 @@
+// Host-side sizing policy for the per-chunk device workspace (shared by the library and the test
+// emulation so both exercise the same table geometry).
+#pragma once
+#include <stdint.h>
+#include "sfq_common.cuh"
+
+static inline uint32_t sfq_ceil_log2(uint64_t v) { uint32_t b = 0; while ((1ull << b) < v) b++; return b; }
+
+// Quality-context table: 4096 contexts at level 1, 65536 otherwise (qlts.cpp:34-39), 256 B each.
+static inline uint64_t sfq_qtable_bytes(int level) { return (level <= 1 ? 4096ull : 65536ull) * SFQ_L64_WORDS * 4; }
+// Base-context table.  Level 1: direct 2^18 x u32.  Levels 2-4: open-addressing hash of 64-bit
+// slots sized for a load factor <= 0.5 at `max_bases` insertions, never larger than the dense table
+// of the level would be.
+static inline uint32_t sfq_gen_hbits(int level, uint64_t max_bases, uint32_t grow) {
+    if (level <= 1) return 18;
+    uint32_t b = sfq_ceil_log2(max_bases * 2 + 16) + grow;
+    return b < 10 ? 10 : b > 27 ? 27 : b;
+}
+static inline uint64_t sfq_gtable_bytes(int level, uint32_t hbits) {
+    return level <= 1 ? (1ull << 18) * 4 : (1ull << hbits) * 8;
+}
+static inline uint64_t sfq_pwpool_bytes() { return (uint64_t)SFQ_PW_PER_CHUNK * SFQ_PW_WORDS * 4; }
+
+// Output arena capacities.  Generous versus the typical 2 bit/base and 2-5 bit/quality; a stream
+// that still overflows is reported (SFQ_E_CAP) and the host retries the wave with `grow` doubled.
+static inline void sfq_arena_layout(const SfqChunkMeta *m, uint32_t grow, uint64_t base, SfqArena *a, uint64_t *end) {
+    const uint64_t g = 1ull << grow;
+    uint64_t cap[SFQ_NSTREAMS];
+    cap[SFQ_S_REC] = (uint64_t)m->hdr_bytes * g + 16ull * m->nrec + 256;
+    cap[SFQ_S_GEN] = ((uint64_t)m->nbases * g) / 2 + 256;
+    cap[SFQ_S_QLT] = (uint64_t)m->nquals * g + 256;
+    cap[SFQ_S_GEN_NS] = ((uint64_t)m->nbases * g) / 8 + 256;
+    cap[SFQ_S_GEN_NN] = ((uint64_t)m->nbases * g) / 8 + 256;
+    cap[SFQ_S_REC_X] = (uint64_t)m->hdr_bytes * g + 16ull * m->nrec + 256;
+    cap[SFQ_S_USR_X] = 8ull * m->nrec * g + 256;
+    cap[SFQ_S_USR_XQ] = 8ull * m->nrec * g + 256;
+    cap[SFQ_S_USR_PFG] = 4ull * m->nrec * g + 256;
+    cap[SFQ_S_USR_PFQ] = 4ull * m->nrec * g + 256;
+    uint64_t o = base;
+    for (int k = 0; k < SFQ_NSTREAMS; k++) {
+        a->off[k] = o;
+        a->cap[k] = (uint32_t)(cap[k] > 0xFFFFFF00ull ? 0xFFFFFF00ull : cap[k]);
+        a->size[k] = 0;
+        o += (a->cap[k] + 15ull) & ~15ull;
+    }
+    *end = o;
+}

@@ -1,0 +1,74 @@
+// Chunk planning: what UsrSave::determine_record (usrs.cpp:186-267) and the structural checks of
+// UsrSave::get_record (usrs.cpp:303-390) establish for a standalone file, computed per chunk from
+// the line-start table.  One thread per chunk.
+#pragma once
+#include "sfq_common.cuh"
+
+// Smallest record index whose first byte is at or after `target` (records = groups of 4 lines).
+SFQ_HD uint64_t sfq_first_record_at(const uint64_t *ls, uint64_t nrec_total, uint64_t target) {
+    uint64_t lo = 0, hi = nrec_total;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (ls[4 * mid] < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Fills `m` for the chunk made of records [r0, r1).  nrec == 0 chunks are left empty (text_len 0).
+SFQ_HDN void sfq_plan_chunk(const uint8_t *text, const uint64_t *ls, uint64_t r0, uint64_t r1, SfqChunkMeta *m) {
+    m->line0 = 4 * r0;
+    m->text_off = ls[4 * r0];
+    m->text_len = ls[4 * r1] - ls[4 * r0];
+    m->out_len = 0;
+    m->nrec = (uint32_t)(r1 - r0);
+    m->nbases = m->nquals = m->hdr_bytes = 0;
+    m->llen = 0; m->solid = 0; m->two_id = 0; m->n_byte = 0; m->pad = 0;
+    m->extra_hi = 0; m->status = SFQ_OK; m->status_arg = 0;
+    if (r1 == r0) return;
+
+    uint32_t status = SFQ_OK, arg = 0;
+    // ---- first record decides llen / SOLiD / 2nd-id for the whole chunk (usrs.cpp:216-266)
+    {
+        const uint64_t *l = ls + 4 * r0;
+        const uint32_t sl = (uint32_t)(l[2] - l[1] - 1);
+        if (sl == 0) { status = SFQ_E_EMPTYSEQ; }
+        const uint8_t *seq = text + l[1];
+        bool solid = false, d_solid = false;
+        for (uint32_t i = 1; i < sl && !d_solid && !solid; i++) {
+            switch (seq[i] | 0x20) {
+            case '0': case '1': case '2': case '3': solid = true; break;
+            case 'a': case 'c': case 'g': case 't': d_solid = true; break;
+            default: break;
+            }
+        }
+        const uint8_t *plus = text + l[2];
+        const uint32_t pl = (uint32_t)(l[3] - l[2] - 1);
+        bool two = false;
+        for (uint32_t i = 1; i < pl; i++) if (plus[i] != ' ') two = true;
+        m->solid = solid;
+        m->two_id = two;
+        m->llen = (int32_t)sl - (solid ? 1 : 0);
+    }
+    const uint32_t solid = m->solid;
+    uint64_t nb = 0, nq = 0, nh = 0;
+    for (uint64_t r = r0; r < r1 && status == SFQ_OK; r++) {
+        const uint64_t *l = ls + 4 * r;
+        const uint64_t hl = l[1] - l[0] - 1, sl = l[2] - l[1] - 1, pl = l[3] - l[2] - 1, ql = l[4] - l[3] - 1;
+        const uint32_t recno = (uint32_t)(r - r0 + 1);
+        if (hl == 0 || text[l[0]] != '@') { status = SFQ_E_AT; arg = recno; break; }
+        if (pl == 0 || text[l[2]] != '+') { status = SFQ_E_PLUS; arg = recno; break; }
+        // `sanity` loops of usrs.cpp:314,334,350,367: an id line of 8191+ chars or a base/quality line
+        // of 65535+ chars takes the oversized-record path, which this build does not code.
+        if (solid && (sl == 0 || ql == 0)) { status = SFQ_E_TRUNC; arg = recno; break; }
+        if (hl - 1 >= SFQ_MAX_ID_LLEN - 1 || pl - 1 >= SFQ_MAX_ID_LLEN - 1 ||
+            sl - solid >= SFQ_MAX_GN_LLEN - 1 || ql - solid >= SFQ_MAX_GN_LLEN - 1) { status = SFQ_E_OVERSIZE; arg = recno; break; }
+        nh += hl - 1;
+        nb += sl - solid;
+        nq += ql - solid;
+    }
+    m->nbases = (uint32_t)nb; m->nquals = (uint32_t)nq; m->hdr_bytes = (uint32_t)nh;
+    // UsrLoad::save (usrs.cpp:512-529): '@'hdr\n [pf]bases\n '+'[hdr]\n [pf]quals\n
+    m->out_len = nh + 2ull * m->nrec + nb + (uint64_t)(solid + 1) * m->nrec + 2ull * m->nrec +
+                 (m->two_id ? nh : 0) + nq + (uint64_t)(solid + 1) * m->nrec;
+    m->status = status; m->status_arg = arg;
+}

@@ -1,0 +1,555 @@
+// Per-chunk coders: one routine per (chunk, main stream).  Each routine is the whole serial
+// dependency chain of one adaptive range-coded stream; the kernels in sfq_kernels.cu run one
+// such routine per thread (thousands of chunk-streams resident at once).
+//
+// A chunk is coded exactly as the reference would code it as a standalone file:
+//   gen  + gen.Ns + gen.Nn              GenSave::save / GenLoad::load      gens.cpp:91-159, 200-249
+//   qlt                                 QltSave::save_1/2/3 / load_1/2/3   qlts.cpp:74-136, 163-234
+//   rec  + rec.x + usr.x/.x.q/.pfg/.pfq RecSave::save / RecLoad::load      recs.cpp:277-461
+//                                       UsrSave::get_record/update         usrs.cpp:124-156, 303-390
+#pragma once
+#include "sfq_coder.cuh"
+
+// Geometry of record r of a chunk, read from the line-start table built by the scan kernel.
+// line_start[L] = offset of the first byte of line L; line_start[nlines] = end of text.
+struct SfqRecView {
+    const uint8_t *hdr;  uint32_t hlen;     // header without '@' and '\n'
+    const uint8_t *seq;  uint32_t llen;     // coded bases (SOLiD prefix stripped)
+    const uint8_t *qual; uint32_t qlen;     // coded qualities (SOLiD prefix stripped)
+    uint32_t plus_len;                      // '+' line length including the '+'
+    uint8_t pf_gen, pf_qlt;                 // SOLiD prefix chars (usrs.cpp:324-329,358-363)
+};
+SFQ_HD SfqRecView sfq_rec_view(const uint8_t *text, const uint64_t *ls, uint64_t line0, uint32_t r, uint32_t solid) {
+    const uint64_t *l = ls + line0 + 4ull * r;
+    SfqRecView v;
+    v.hdr = text + l[0] + 1;  v.hlen = (uint32_t)(l[1] - l[0] - 2);
+    uint32_t sl = (uint32_t)(l[2] - l[1] - 1), ql = (uint32_t)(l[4] - l[3] - 1);
+    v.plus_len = (uint32_t)(l[3] - l[2] - 1);
+    v.seq = text + l[1];  v.qual = text + l[3];
+    v.pf_gen = 0; v.pf_qlt = 0;
+    if (solid) {
+        // usrs.cpp:324-329: the prefix byte is consumed unconditionally, then the line is scanned.
+        v.pf_gen = v.seq[0]; v.pf_qlt = v.qual[0];
+        v.seq++; v.qual++;
+        sl = sl ? sl - 1 : 0; ql = ql ? ql - 1 : 0;
+    }
+    v.llen = sl; v.qlen = ql;
+    return v;
+}
+
+SFQ_HD uint32_t sfq_gencode(uint8_t c) {            // gencodes[], gens.cpp:72-77
+    switch (c) {
+    case '0': case 'A': case 'a': return 0;
+    case '1': case 'C': case 'c': return 1;
+    case '2': case 'G': case 'g': return 2;
+    case '3': case 'T': case 't': return 3;
+    case '.': case 'N': case 'n': return 4;
+    default: return 0x10;
+    }
+}
+SFQ_HD uint32_t sfq_gen_mask(int level) {           // gens.hpp:43-53,74-82
+    return level <= 1 ? (1u << 18) - 1 : level == 2 ? (1u << 22) - 1 : level == 3 ? (1u << 24) - 1 : (1u << 26) - 1;
+}
+
+// ============================================================================ gen: encode
+SFQ_HDN void sfq_gen_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *meta, int level,
+                                  void *table_mem, uint32_t hbits, uint32_t *pwpool,
+                                  uint8_t *arena, SfqArena *ar) {
+    SfqEnc rc;
+    rc.start(arena + ar->off[SFQ_S_GEN], ar->cap[SFQ_S_GEN]);
+    SfqXSave xns, xnn;
+    xns.init(pwpool, SFQ_X_NS, arena + ar->off[SFQ_S_GEN_NS], ar->cap[SFQ_S_GEN_NS]);
+    xnn.init(pwpool, SFQ_X_NN, arena + ar->off[SFQ_S_GEN_NN], ar->cap[SFQ_S_GEN_NN]);
+    SfqGenTable tab;
+    tab.init(table_mem, hbits, level <= 1);
+    const uint32_t mask = sfq_gen_mask(level);
+    const uint32_t solid = meta->solid;
+    uint64_t genofs = 0, ns_index = 0, nn_index = 0;     // g_genofs_count, m_last.*  (gens.hpp:56-60)
+    uint8_t n_byte = 0;
+    uint32_t status = SFQ_OK, status_arg = 0;
+
+    for (uint32_t r = 0; r < meta->nrec && status == SFQ_OK; r++) {
+        const SfqRecView v = sfq_rec_view(text, ls, meta->line0, r, solid);
+        uint32_t last = 0x007616c7u;                                           // gens.cpp:139
+        for (uint32_t i = 0; i < v.llen; i++) {
+            const uint8_t g = v.seq[i];
+            const uint8_t q = i < v.qlen ? v.qual[i] : (uint8_t)40;            // gens.cpp:153
+            uint32_t n = sfq_gencode(g);
+            const bool bad_q = (q == '!');
+            bool bad_n = false;
+            if (n > 3) {
+                if (n > 4) { status = SFQ_E_BASE; status_arg = g; break; }
+                bad_n = true; n = 0;
+            }
+            genofs++;
+            if (bad_n || bad_q) {                                              // gens.cpp:91-114
+                if (!bad_n) { xnn.put(genofs - nn_index); nn_index = genofs; }
+                else {
+                    if (!n_byte) n_byte = g;
+                    if (g != n_byte) { status = SFQ_E_NBYTE; status_arg = g; break; }
+                    if (!bad_q) { xns.put(genofs - ns_index); ns_index = genofs; }
+                }
+            }
+            last &= mask;
+            uint32_t fv;
+            const uint32_t slot = tab.find(last, fv);
+            if (slot == 0xFFFFFFFFu) { status = SFQ_E_TABLE; break; }
+            tab.store(slot, last, sfq_b2_put(fv, rc, n));
+            last = (last << 2) | n;
+        }
+    }
+    rc.finish();
+    bool ovf = rc.out.overflow();
+    ar->size[SFQ_S_GEN] = rc.out.n;
+    ar->size[SFQ_S_GEN_NS] = xns.close(ovf);
+    ar->size[SFQ_S_GEN_NN] = xnn.close(ovf);
+    if (status == SFQ_OK && ovf) status = SFQ_E_CAP;
+    meta->n_byte = (n_byte && n_byte != 'N') ? n_byte : 0;                     // gens.cpp:103-104
+    if (status != SFQ_OK && meta->status == SFQ_OK) { meta->status = status; meta->status_arg = status_arg; }
+}
+
+// ============================================================================ gen: decode
+// Writes the base line of every record into `bases` (record r at boff[r], llen[r] bytes).  The
+// "quality '!' means N" rule (GenLoad::normalize_gen, gens.cpp:200-213) needs the record's decoded
+// qualities, which another thread is producing concurrently, so it is applied afterwards by the
+// assemble kernel: positions taken from gen.Nn (a real base under a '!' quality) are flagged with
+// bit 7 here so the rule skips them; gen.Ns positions get the N byte right away.
+SFQ_HDN void sfq_gen_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
+                                  SfqChunkMeta *meta, int level, void *table_mem, uint32_t hbits,
+                                  uint32_t *pwpool, const uint32_t *llen_tab, const uint64_t *boff_tab,
+                                  uint8_t *bases) {
+    SfqDec rc;
+    rc.start(in + soff[SFQ_S_GEN], ssize[SFQ_S_GEN]);
+    SfqXLoad xns, xnn;
+    xns.init(pwpool, SFQ_X_NS, in + soff[SFQ_S_GEN_NS], ssize[SFQ_S_GEN_NS]);
+    xnn.init(pwpool, SFQ_X_NN, in + soff[SFQ_S_GEN_NN], ssize[SFQ_S_GEN_NN]);
+    SfqGenTable tab;
+    tab.init(table_mem, hbits, level <= 1);
+    const uint32_t mask = sfq_gen_mask(level);
+    const uint8_t n_byte = meta->n_byte ? meta->n_byte : (uint8_t)'N';          // gens.cpp:169
+    const uint8_t a0 = meta->solid ? '0' : 'A', a1 = meta->solid ? '1' : 'C',
+                  a2 = meta->solid ? '2' : 'G', a3 = meta->solid ? '3' : 'T';   // gens.cpp:173-178
+    uint64_t genofs = 0;
+    uint64_t ns_index = xns.get(), nn_index = xnn.get();                        // gens.cpp:188-189
+    uint32_t status = SFQ_OK;
+    for (uint32_t r = 0; r < meta->nrec && status == SFQ_OK; r++) {
+        const uint32_t llen = llen_tab[r];
+        uint8_t *g = bases + boff_tab[r];
+        uint32_t last = 0x007616c7u;
+        for (uint32_t i = 0; i < llen; i++) {
+            last &= mask;
+            uint32_t fv, b;
+            const uint32_t slot = tab.find(last, fv);
+            if (slot == 0xFFFFFFFFu) { status = SFQ_E_TABLE; break; }
+            tab.store(slot, last, sfq_b2_get(fv, rc, b));
+            last = (last << 2) + b;
+            uint8_t c = b == 0 ? a0 : b == 1 ? a1 : b == 2 ? a2 : a3;
+            genofs++;
+            if (nn_index == genofs) { nn_index += xnn.get(); c |= 0x80; }
+            else if (ns_index == genofs) { ns_index += xns.get(); c = n_byte; }
+            g[i] = c;
+        }
+    }
+    if (status != SFQ_OK && meta->status == SFQ_OK) meta->status = status;
+}
+
+// ============================================================================ qlt
+struct SfqQCtx {                                      // qlts.cpp:109-112
+    uint32_t last, delta, di;
+    uint8_t q1, q2;
+    SFQ_HD void reset() { last = 0; delta = 5; di = 0; q1 = 0; q2 = 0; }
+};
+SFQ_HD uint32_t sfq_q_delta_ctx(uint32_t &delta, uint8_t q, uint8_t q1, uint8_t q2) {   // qlts.hpp:62-74
+    if (q1 > q) delta += (uint32_t)(q1 - q);
+    const uint32_t d = delta >> 3;
+    return ((uint32_t)q | ((uint32_t)(q1 < q2 ? q2 : q1) << 6) | ((uint32_t)(q1 == q2) << 12)
+            | ((d < 7u ? d : 7u) << 13)) & 0xFFFFu;
+}
+SFQ_HD void sfq_q_next(SfqQCtx &c, int level, uint8_t b) {
+    if (level <= 1) { c.last = ((uint32_t)b | (c.last << 6)) & 0xFFFu; return; }        // qlts.hpp:52-54
+    if (level == 2) { c.last = ((uint32_t)b | (c.last << 6)) & 0xFFFFu; return; }       // qlts.hpp:55-57
+    if (++c.di & 1u) { c.last = sfq_q_delta_ctx(c.delta, b, c.q1, c.q2); c.q2 = b; }    // qlts.cpp:127-134
+    else             { c.last = sfq_q_delta_ctx(c.delta, b, c.q2, c.q1); c.q1 = b; }
+}
+
+SFQ_HDN void sfq_qlt_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *meta, int level,
+                                  uint32_t *qtable, uint32_t *pwpool, uint8_t *arena, SfqArena *ar) {
+    SfqEnc rc;
+    rc.start(arena + ar->off[SFQ_S_QLT], ar->cap[SFQ_S_QLT]);
+    SfqPower ex; ex.m = pwpool + (size_t)SFQ_PW_QEX * SFQ_PW_WORDS;
+    const uint32_t solid = meta->solid;
+    uint32_t extra_hi = 0;
+    for (uint32_t r = 0; r < meta->nrec; r++) {
+        const SfqRecView v = sfq_rec_view(text, ls, meta->line0, r, solid);
+        SfqQCtx c; c.reset();
+        for (uint32_t i = 0; i < v.qlen; i++) {
+            const uint8_t b = (uint8_t)(v.qual[i] - '!');
+            SfqLog64 m; m.m = qtable + (size_t)c.last * SFQ_L64_WORDS;
+            if (b < 63) m.put(rc, b);
+            else { m.put(rc, 63); ex.put(rc, b); extra_hi++; }                  // qlts.cpp:120-125
+            sfq_q_next(c, level, b);
+        }
+    }
+    rc.finish();
+    ar->size[SFQ_S_QLT] = rc.out.n;
+    meta->extra_hi = extra_hi;
+    if (rc.out.overflow() && meta->status == SFQ_OK) meta->status = SFQ_E_CAP;
+}
+
+SFQ_HDN void sfq_qlt_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
+                                  SfqChunkMeta *meta, int level, uint32_t *qtable, uint32_t *pwpool,
+                                  const uint32_t *qlen_tab, const uint64_t *qoff_tab, uint8_t *quals) {
+    SfqDec rc;
+    rc.start(in + soff[SFQ_S_QLT], ssize[SFQ_S_QLT]);
+    SfqPower ex; ex.m = pwpool + (size_t)SFQ_PW_QEX * SFQ_PW_WORDS;
+    for (uint32_t r = 0; r < meta->nrec; r++) {
+        const uint32_t qlen = qlen_tab[r];
+        uint8_t *q = quals + qoff_tab[r];
+        SfqQCtx c; c.reset();
+        for (uint32_t i = 0; i < qlen; i++) {
+            SfqLog64 m; m.m = qtable + (size_t)c.last * SFQ_L64_WORDS;
+            uint32_t b = m.get(rc);
+            if (b == 63) b = ex.get(rc);                                        // qlts.cpp:206-208
+            q[i] = (uint8_t)('!' + b);
+            sfq_q_next(c, level, (uint8_t)b);
+        }
+    }
+}
+
+// ============================================================================ rec (+ usr framing)
+enum { SFQ_ST_DGT = 0, SFQ_ST_DLT, SFQ_ST_STR, SFQ_ST_HGT, SFQ_ST_HLT, SFQ_ST_HGT_Z, SFQ_ST_HLT_Z,
+       SFQ_ST_HGTC, SFQ_ST_HLTC, SFQ_ST_HGTC_Z, SFQ_ST_HLTC_Z, SFQ_ST_DGT_Z, SFQ_ST_DLT_Z };   // recs.cpp:160-189
+
+struct SfqSpaceMap {                                  // recs.hpp:69-74
+    uint16_t off[66], wln[66];
+    uint8_t str[66];
+    uint32_t len;
+};
+SFQ_HD bool sfq_is_dig(uint8_t c) { return c >= '0' && c <= '9'; }
+SFQ_HD bool sfq_is_word(uint8_t c) {                  // isdigit||isalpha in the C locale, recs.cpp:139
+    return sfq_is_dig(c) || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z');
+}
+// map_space (recs.cpp:140-157); returns false on > 64 separators.
+SFQ_HD bool sfq_map_space(SfqSpaceMap &m, const uint8_t *p) {
+    m.len = 0;
+    m.off[0] = 0;
+    for (uint32_t i = 0;; i++) {
+        const uint8_t c = p[i];
+        if (!sfq_is_word(c)) {
+            m.wln[m.len] = (uint16_t)(i - m.off[m.len]);
+            m.str[m.len++] = c;
+            m.off[m.len] = (uint16_t)(i + 1);
+            if (c == 0 || c == '\n') return true;
+            if (m.len > 64) return false;
+        }
+    }
+}
+// numberwang (recs.cpp:192-262)
+SFQ_HD uint32_t sfq_numberwang(const uint8_t *p, uint32_t len, uint64_t &num, uint8_t pctype) {
+    uint32_t i = 0;
+    const bool has_z = p[0] == '0';
+    if (has_z && p[++i] == '0') return SFQ_ST_STR;
+    uint32_t caps = 0;
+    num = 0;
+    while (pctype != 2) {
+        if (i >= len) return has_z ? SFQ_ST_DGT_Z : SFQ_ST_DGT;
+        const uint8_t c = p[i];
+        if (sfq_is_dig(c)) {
+            const uint64_t t = (num << 3) + (num << 1) + c - '0';
+            i++;
+            if (t < num) return SFQ_ST_STR;
+            num = t;
+            continue;
+        }
+        if ((c | 0x20) < 'a' || (c | 0x20) > 'f') return SFQ_ST_STR;
+        caps = 1u + (c < 'a');
+        i = has_z;
+        num = 0;
+        break;
+    }
+    if (len > 16) return SFQ_ST_STR;
+    for (; i < len; i++) {
+        const uint8_t c = p[i];
+        uint32_t nib;
+        if (sfq_is_dig(c)) nib = c - '0';
+        else if (c >= 'a' && c <= 'f') { if (caps == 2) return SFQ_ST_STR; caps = 1; nib = 10u + c - 'a'; }
+        else if (c >= 'A' && c <= 'F') { if (caps == 1) return SFQ_ST_STR; caps = 2; nib = 10u + c - 'A'; }
+        else return SFQ_ST_STR;
+        num = (num << 4) + nib;
+    }
+    return caps == 2 ? (has_z ? SFQ_ST_HGTC_Z : SFQ_ST_HGTC) : (has_z ? SFQ_ST_HGT_Z : SFQ_ST_HGT);
+}
+
+struct SfqFieldRangers {                              // RecBase::ranger_t, recs.hpp:42-46
+    SfqPower type, str;
+    SfqPowerU num;
+    SFQ_HD void bind(uint32_t *pool, uint32_t field) {
+        uint32_t *b = pool + (size_t)(SFQ_PW_REC_BASE + field * SFQ_PW_PER_FIELD) * SFQ_PW_WORDS;
+        type.m = b; str.m = b + SFQ_PW_WORDS; num.m = b + 2 * SFQ_PW_WORDS;
+    }
+};
+
+SFQ_HDN void sfq_rec_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *meta,
+                                  uint32_t *pwpool, uint8_t *arena, SfqArena *ar) {
+    SfqEnc rc;
+    rc.start(arena + ar->off[SFQ_S_REC], ar->cap[SFQ_S_REC]);
+    SfqXSave x_rec, x_llen, x_qlen, x_sgen, x_sqlt;
+    x_rec.init(pwpool, SFQ_X_REC, arena + ar->off[SFQ_S_REC_X], ar->cap[SFQ_S_REC_X]);
+    x_llen.init(pwpool, SFQ_X_LLEN, arena + ar->off[SFQ_S_USR_X], ar->cap[SFQ_S_USR_X]);
+    x_qlen.init(pwpool, SFQ_X_QLEN, arena + ar->off[SFQ_S_USR_XQ], ar->cap[SFQ_S_USR_XQ]);
+    x_sgen.init(pwpool, SFQ_X_SGEN, arena + ar->off[SFQ_S_USR_PFG], ar->cap[SFQ_S_USR_PFG]);
+    x_sqlt.init(pwpool, SFQ_X_SQLT, arena + ar->off[SFQ_S_USR_PFQ], ar->cap[SFQ_S_USR_PFQ]);
+
+    SfqSpaceMap smap[2];
+    uint8_t ctype[2][65];
+    uint64_t cnumb[2][65];
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 65; b++) { ctype[a][b] = 0; cnumb[a][b] = 0; }
+    smap[0].len = smap[1].len = 0;
+    uint32_t imap = 0;
+    uint64_t x_index = 0;                              // RecBase::m_last.index
+    const uint32_t solid = meta->solid;
+    uint32_t m_llen = (uint32_t)meta->llen;            // UsrSave::m_llen (sticky), usrs.cpp:126-131
+    uint64_t i_llen = 0, i_qlen = 0, i_sgen = 0, i_sqlt = 0;
+    uint8_t pf_gen = 0, pf_qlt = 0;
+    const uint8_t *prev = nullptr;
+    uint32_t status = SFQ_OK, status_arg = 0;
+
+    for (uint32_t r = 0; r < meta->nrec; r++) {
+        const uint64_t recno = (uint64_t)r + 1;        // g_record_count
+        const SfqRecView v = sfq_rec_view(text, ls, meta->line0, r, solid);
+        // ---- framing exceptions, in get_record order (usrs.cpp:320-372)
+        if (solid && pf_gen != v.pf_gen && v.pf_gen) {
+            x_sgen.put(recno - i_sgen); x_sgen.put_chr(v.pf_gen); i_sgen = recno; pf_gen = v.pf_gen;
+        }
+        if (m_llen != v.llen) {
+            x_llen.put(recno - i_llen); x_llen.put((uint16_t)v.llen); i_llen = recno; m_llen = (uint16_t)v.llen;
+        }
+        if (solid && pf_qlt != v.pf_qlt) {
+            x_sqlt.put(recno - i_sqlt); x_sqlt.put_chr(v.pf_qlt); i_sqlt = recno; pf_qlt = v.pf_qlt;
+        }
+        if (v.qlen != m_llen) { x_qlen.put(recno - i_qlen); x_qlen.put((uint16_t)v.qlen); i_qlen = recno; }
+
+        // ---- header model (recs.cpp:277-372)
+        const uint8_t *buf = v.hdr;
+        if (r == 0) {
+            // first header travels in clear as the `rec.first` info key (recs.cpp:68-75)
+            if (v.hlen > 399) { status = SFQ_E_FIRSTHDR; break; }
+            imap = 0;
+            if (!sfq_map_space(smap[0], buf)) { status = SFQ_E_SEPS; status_arg = 1; break; }
+            prev = buf;
+            continue;
+        }
+        const uint32_t pm = imap, im = imap ^ 1u;
+        imap = im;
+        SfqSpaceMap &S = smap[im];
+        const SfqSpaceMap &P = smap[pm];
+        if (!sfq_map_space(S, buf)) { status = SFQ_E_SEPS; status_arg = (uint32_t)recno; break; }
+        bool same = S.len == P.len;
+        for (uint32_t k = 0; same && k < S.len; k++) same = S.str[k] == P.str[k];
+        if (!same) {                                                            // recs.cpp:291-304
+            x_rec.put(recno - x_index);
+            x_index = recno;
+            x_rec.put(v.hlen);
+            for (uint32_t j = 0; j < v.hlen; j++) x_rec.put_chr(buf[j]);
+            for (int b = 0; b < 65; b++) ctype[im][b] = 0;
+            prev = buf;
+            continue;
+        }
+        uint64_t map = 0;
+        for (uint32_t i = 0; i < S.len; i++) {
+            bool diff = S.wln[i] != P.wln[i];
+            const uint8_t *a = buf + S.off[i], *b = prev + P.off[i];
+            for (uint32_t k = 0; !diff && k < S.wln[i]; k++) diff = a[k] != b[k];
+            if (diff) map |= 1ULL << (i & 63u);        // x86 shift-count masking of DO_SET at i == 64
+        }
+        SfqFieldRangers R0; R0.bind(pwpool, 0);
+        R0.num.put(rc, map);                                                    // recs.cpp:312
+        for (uint32_t i = 0; i < S.len; i++) {
+            if (!(map & (1ULL << (i & 63u)))) {
+                ctype[im][i] = ctype[pm][i];
+                cnumb[im][i] = cnumb[pm][i];
+                continue;
+            }
+            const uint8_t *b = buf + S.off[i];
+            uint64_t bnum;
+            uint32_t type = sfq_numberwang(b, S.wln[i], bnum, ctype[pm][i]);
+            SfqFieldRangers R; R.bind(pwpool, i + 1);
+            if (type == SFQ_ST_STR) {
+                R.type.put(rc, type);
+                R.num.put(rc, S.wln[i]);
+                for (uint32_t j = 0; j < S.wln[i]; j++) R.str.put(rc, b[j]);
+                ctype[im][i] = 0;
+                continue;
+            }
+            const uint64_t pnum = ctype[pm][i] ? cnumb[pm][i] : 0;
+            uint64_t gap;
+            ctype[im][i] = (type < SFQ_ST_STR || type >= SFQ_ST_DGT_Z) ? 1 : 2;
+            cnumb[im][i] = bnum;
+            if (bnum < pnum) { gap = pnum - bnum; type++; } else gap = bnum - pnum;
+            R.type.put(rc, type);
+            R.num.put(rc, gap);
+        }
+        prev = buf;
+    }
+    rc.finish();
+    bool ovf = rc.out.overflow();
+    ar->size[SFQ_S_REC] = rc.out.n;
+    ar->size[SFQ_S_REC_X] = x_rec.close(ovf);
+    ar->size[SFQ_S_USR_X] = x_llen.close(ovf);
+    ar->size[SFQ_S_USR_XQ] = x_qlen.close(ovf);
+    ar->size[SFQ_S_USR_PFG] = x_sgen.close(ovf);
+    ar->size[SFQ_S_USR_PFQ] = x_sqlt.close(ovf);
+    if (status == SFQ_OK && ovf) status = SFQ_E_CAP;
+    if (status != SFQ_OK && meta->status == SFQ_OK) { meta->status = status; meta->status_arg = status_arg; }
+}
+
+// ---------------------------------------------------------------------------- usr decode
+// UsrLoad::update (usrs.cpp:471-510): replays usr.x / usr.x.q / usr.pfg / usr.pfq into per-record
+// tables so that the qlt, gen and rec decoders of the chunk can run concurrently afterwards.
+SFQ_HDN void sfq_usr_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
+                                  SfqChunkMeta *meta, uint32_t *pwpool,
+                                  uint32_t *llen_tab, uint32_t *qlen_tab, uint8_t *pfg_tab, uint8_t *pfq_tab) {
+    SfqXLoad x_llen, x_qlen, x_sgen, x_sqlt;
+    x_llen.init(pwpool, SFQ_X_LLEN, in + soff[SFQ_S_USR_X], ssize[SFQ_S_USR_X]);
+    x_qlen.init(pwpool, SFQ_X_QLEN, in + soff[SFQ_S_USR_XQ], ssize[SFQ_S_USR_XQ]);
+    x_sgen.init(pwpool, SFQ_X_SGEN, in + soff[SFQ_S_USR_PFG], ssize[SFQ_S_USR_PFG]);
+    x_sqlt.init(pwpool, SFQ_X_SQLT, in + soff[SFQ_S_USR_PFQ], ssize[SFQ_S_USR_PFQ]);
+    const bool solid = meta->solid != 0;
+    uint64_t m_llen = (uint64_t)(uint32_t)meta->llen, m_qlen = m_llen;
+    uint64_t i_llen = x_llen.get(), i_qlen = x_qlen.get(), i_sgen = x_sgen.get(), i_sqlt = x_sqlt.get();
+    uint8_t pf_gen = 0, pf_qlt = 0;
+    uint64_t nb = 0, nq = 0;
+    uint32_t status = SFQ_OK;
+    for (uint32_t r = 0; r < meta->nrec; r++) {
+        const uint64_t recno = (uint64_t)r + 1;
+        if (i_llen == recno) { m_llen = x_llen.get(); m_qlen = m_llen; i_llen += x_llen.get(); }
+        if (i_qlen == recno) { m_qlen = x_qlen.get(); i_qlen += x_qlen.get(); }
+        else if (m_qlen != m_llen) m_qlen = m_llen;
+        if (solid && i_sgen == recno) { pf_gen = x_sgen.get_chr(); i_sgen += x_sgen.get(); }
+        if (solid && i_sqlt == recno) { pf_qlt = x_sqlt.get_chr(); i_sqlt += x_sqlt.get(); }
+        if (m_llen >= SFQ_MAX_GN_LLEN || m_qlen >= SFQ_MAX_GN_LLEN) { status = SFQ_E_CORRUPT; m_llen = m_qlen = 0; }
+        llen_tab[r] = (uint32_t)m_llen;
+        qlen_tab[r] = (uint32_t)m_qlen;
+        pfg_tab[r] = pf_gen;
+        pfq_tab[r] = pf_qlt;
+        nb += m_llen; nq += m_qlen;
+    }
+    if (nb != meta->nbases || nq != meta->nquals) status = SFQ_E_CORRUPT;
+    if (status != SFQ_OK && meta->status == SFQ_OK) meta->status = status;
+}
+
+// ---------------------------------------------------------------------------- rec decode
+SFQ_HD uint32_t sfq_fmt_u64(uint8_t *b, uint64_t v, uint32_t base, bool upper, bool is_signed) {
+    // what sprintf("%lld" / "%llx" / "%llX") prints for a non-zero value (recs.cpp:436-456)
+    uint8_t tmp[24];
+    uint32_t n = 0, o = 0;
+    if (is_signed && (int64_t)v < 0) { b[o++] = '-'; v = 0ull - v; }
+    while (v) {
+        const uint32_t d = (uint32_t)(v % base);
+        tmp[n++] = (uint8_t)(d < 10 ? '0' + d : (upper ? 'A' : 'a') + d - 10);
+        v /= base;
+    }
+    while (n) b[o++] = tmp[--n];
+    return o;
+}
+
+// Decodes all headers of a chunk into `hdrs` (each followed by '\n'; record r at hoff_tab[r],
+// length hlen_tab[r]).  `hcap` = bytes available in the plane; the caller gives meta->hdr_bytes +
+// nrec + 64 so the conservative room checks below never reject a valid container.
+SFQ_HDN void sfq_rec_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
+                                  SfqChunkMeta *meta, uint32_t *pwpool, const uint8_t *rec_first,
+                                  uint32_t rec_first_len, uint8_t *hdrs, uint64_t hcap,
+                                  uint32_t *hlen_tab, uint64_t *hoff_tab) {
+    SfqDec rc;
+    rc.start(in + soff[SFQ_S_REC], ssize[SFQ_S_REC]);
+    SfqXLoad x_rec;
+    x_rec.init(pwpool, SFQ_X_REC, in + soff[SFQ_S_REC_X], ssize[SFQ_S_REC_X]);
+    SfqSpaceMap S;
+    uint8_t ctype[2][65];
+    uint64_t cnumb[2][65];
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 65; b++) { ctype[a][b] = 0; cnumb[a][b] = 0; }
+    uint32_t imap = 0;
+    uint64_t x_index = x_rec.get();                                             // recs.cpp:104-105
+    uint64_t pos = 0;
+    const uint8_t *prev = nullptr;
+    uint32_t status = SFQ_OK;
+
+    for (uint32_t r = 0; r < meta->nrec; r++) {
+        const uint64_t recno = (uint64_t)r + 1;
+        uint8_t *buf = hdrs + pos;
+        // every branch below checks room before it writes; a valid container never trips it
+        uint64_t room = hcap - pos;
+        uint32_t n = 0;
+        if (r == 0) {                                                           // recs.cpp:375-381
+            if (rec_first_len + 1ull > room) { status = SFQ_E_CORRUPT; break; }
+            for (uint32_t k = 0; k < rec_first_len; k++) buf[k] = rec_first[k];
+            n = rec_first_len;
+            imap = 0;
+        } else {
+            const uint32_t pm = imap, im = imap ^ 1u;
+            imap = im;
+            if (x_index == recno) {                                             // recs.cpp:386-393
+                const uint64_t len = x_rec.get();
+                if (len + 1ull > room) { status = SFQ_E_CORRUPT; break; }
+                for (uint32_t j = 0; j < (uint32_t)len; j++) buf[j] = x_rec.get_chr();
+                x_index += x_rec.get();
+                for (int b = 0; b < 65; b++) ctype[im][b] = 0;
+                n = (uint32_t)len;
+            } else {
+                if (!sfq_map_space(S, prev)) { status = SFQ_E_CORRUPT; break; }
+                SfqFieldRangers R0; R0.bind(pwpool, 0);
+                const uint64_t map = R0.num.get(rc);
+                uint8_t *b = buf;
+                bool bad = false;
+                for (uint32_t i = 0; i < S.len; i++) {
+                    if ((uint64_t)(b - buf) + S.wln[i] + 44ull > room) { bad = true; break; }
+                    if (!(map & (1ULL << (i & 63u)))) {
+                        const uint8_t *src = prev + S.off[i];
+                        for (uint32_t k = 0; k < S.wln[i]; k++) *b++ = src[k];
+                        *b++ = S.str[i];
+                        ctype[im][i] = ctype[pm][i];
+                        cnumb[im][i] = cnumb[pm][i];
+                        continue;
+                    }
+                    SfqFieldRangers R; R.bind(pwpool, i + 1);
+                    const uint32_t type = R.type.get(rc);
+                    if (type == SFQ_ST_STR) {
+                        const uint64_t len = R.num.get(rc);
+                        if ((uint64_t)(b - buf) + len + 2ull > room) { bad = true; break; }
+                        for (uint32_t j = 0; j < (uint32_t)len; j++) *b++ = (uint8_t)R.str.get(rc);
+                        ctype[im][i] = 0;
+                        *b++ = S.str[i];
+                        continue;
+                    }
+                    if (type > SFQ_ST_DLT_Z) { bad = true; break; }
+                    const uint64_t pval = ctype[pm][i] == 0 ? 0 : cnumb[pm][i];
+                    const uint64_t gap = R.num.get(rc);
+                    const bool less = type == SFQ_ST_DLT || type == SFQ_ST_HLT || type == SFQ_ST_HLT_Z ||
+                                      type == SFQ_ST_HLTC || type == SFQ_ST_HLTC_Z || type == SFQ_ST_DLT_Z;
+                    const uint64_t val = less ? pval - gap : pval + gap;
+                    ctype[im][i] = (type < SFQ_ST_STR || type >= SFQ_ST_DGT_Z) ? 1 : 2;
+                    cnumb[im][i] = val;
+                    if (val == 0) *b++ = '0';                                   // recs.cpp:453-454
+                    else {
+                        const bool dec = type <= SFQ_ST_DLT || type >= SFQ_ST_DGT_Z;
+                        const bool zed = type == SFQ_ST_HGT_Z || type == SFQ_ST_HLT_Z || type == SFQ_ST_HGTC_Z ||
+                                         type == SFQ_ST_HLTC_Z || type == SFQ_ST_DGT_Z || type == SFQ_ST_DLT_Z;
+                        const bool upper = type >= SFQ_ST_HGTC && type <= SFQ_ST_HLTC_Z;
+                        if (zed) *b++ = '0';
+                        b += sfq_fmt_u64(b, val, dec ? 10u : 16u, upper, dec);
+                    }
+                    *b++ = S.str[i];
+                }
+                if (bad) { status = SFQ_E_CORRUPT; break; }
+                n = (uint32_t)(b - buf) - 1u;                                   // recs.cpp:460
+            }
+        }
+        buf[n] = '\n';       // terminator the next record's tokeniser stops at (UsrLoad::putline)
+        hlen_tab[r] = n;
+        hoff_tab[r] = pos;
+        prev = buf;
+        pos += (uint64_t)n + 1;
+    }
+    if (status == SFQ_OK && pos != (uint64_t)meta->hdr_bytes + meta->nrec) status = SFQ_E_CORRUPT;
+    if (status != SFQ_OK && meta->status == SFQ_OK) meta->status = status;
+}

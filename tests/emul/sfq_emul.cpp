@@ -1,0 +1,133 @@
+// TEST TOOLING ONLY: compiles the per-chunk coder routines of slimfastq_b200/csrc (the bodies of the
+// CUDA kernels) with g++ and runs them one chunk-stream at a time on the CPU, so their logic can be
+// checked against the oracle in the GPU-less dev container.  Never linked into the product library.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../slimfastq_b200/csrc/sfq_streams.cuh"
+#include "../../slimfastq_b200/csrc/sfq_plan.cuh"
+#include "../../slimfastq_b200/csrc/sfq_container.h"
+#include "../../slimfastq_b200/csrc/sfq_layout.h"
+
+static void put_bytes(std::vector<uint8_t> &o, const void *p, size_t n) {
+    const uint8_t *b = (const uint8_t *)p; o.insert(o.end(), b, b + n);
+}
+
+extern "C" int sfq_emul_compress(const uint8_t *text, size_t n, int level, uint64_t chunk_bytes,
+                                 uint8_t **out, size_t *out_n, uint32_t *status_out) {
+    level = level > 4 ? 4 : level < 1 ? 1 : level;
+    *status_out = 0;
+    std::vector<uint64_t> ls;
+    ls.push_back(0);
+    for (size_t i = 0; i < n; i++) if (text[i] == '\n') ls.push_back(i + 1);
+    if (n == 0 || text[n - 1] != '\n' || (ls.size() - 1) % 4) { *status_out = SFQ_E_TRUNC; return 1; }
+    const uint64_t nrec = (ls.size() - 1) / 4;
+    const uint64_t nslots = (n + chunk_bytes - 1) / chunk_bytes;
+    std::vector<uint8_t> file(sizeof(SfqFileHeader));
+    std::vector<uint64_t> index;
+    for (uint64_t c = 0; c < nslots; c++) {
+        uint64_t r0 = sfq_first_record_at(ls.data(), nrec, c * chunk_bytes);
+        uint64_t r1 = c + 1 == nslots ? nrec : sfq_first_record_at(ls.data(), nrec, (c + 1) * chunk_bytes);
+        if (r0 == r1) continue;
+        SfqChunkMeta m;
+        sfq_plan_chunk(text, ls.data(), r0, r1, &m);
+        if (m.status) { *status_out = m.status; return 1; }
+        for (uint32_t grow = 0;; grow++) {
+            SfqArena ar; uint64_t end;
+            sfq_arena_layout(&m, grow, 0, &ar, &end);
+            std::vector<uint8_t> arena(end);
+            uint32_t hbits = sfq_gen_hbits(level, m.nbases, grow);
+            void *gt = calloc(1, sfq_gtable_bytes(level, hbits));
+            uint32_t *qt = (uint32_t *)calloc(1, sfq_qtable_bytes(level));
+            uint32_t *pw = (uint32_t *)calloc(1, sfq_pwpool_bytes());
+            m.status = 0;
+            sfq_gen_encode_chunk(text, ls.data(), &m, level, gt, hbits, pw, arena.data(), &ar);
+            sfq_qlt_encode_chunk(text, ls.data(), &m, level, qt, pw, arena.data(), &ar);
+            sfq_rec_encode_chunk(text, ls.data(), &m, pw, arena.data(), &ar);
+            free(gt); free(qt); free(pw);
+            if ((m.status == SFQ_E_CAP || m.status == SFQ_E_TABLE) && grow < 6) continue;
+            if (m.status) { *status_out = m.status; return 1; }
+            SfqBlobHeader b; memset(&b, 0, sizeof b);
+            b.magic = SFQ_BLOB_MAGIC; b.level = level; b.text_len = m.text_len; b.out_len = m.out_len; b.nrec = m.nrec;
+            b.nbases = m.nbases; b.nquals = m.nquals; b.hdr_bytes = m.hdr_bytes; b.llen = m.llen;
+            b.solid = m.solid; b.two_id = m.two_id; b.n_byte = m.n_byte; b.extra_hi = m.extra_hi;
+            b.rec_first_len = (uint32_t)(ls[m.line0 + 1] - ls[m.line0] - 2);
+            for (int k = 0; k < SFQ_NSTREAMS; k++) b.ssize[k] = ar.size[k];
+            index.push_back(file.size());
+            put_bytes(file, &b, sizeof b);
+            put_bytes(file, text + ls[m.line0] + 1, b.rec_first_len);
+            for (int k = 0; k < SFQ_NSTREAMS; k++) put_bytes(file, arena.data() + ar.off[k], ar.size[k]);
+            break;
+        }
+    }
+    SfqFileHeader h;
+    sfq_file_header_init(&h, level, n, index.size(), chunk_bytes, file.size());
+    memcpy(file.data(), &h, sizeof h);
+    put_bytes(file, index.data(), index.size() * 8);
+    *out = (uint8_t *)malloc(file.size());
+    memcpy(*out, file.data(), file.size());
+    *out_n = file.size();
+    return 0;
+}
+
+extern "C" int sfq_emul_decompress(const uint8_t *sfq, size_t n, uint8_t **out, size_t *out_n, uint32_t *status_out) {
+    *status_out = 0;
+    if (!sfq_is_chunked_container(sfq, n)) { *status_out = SFQ_E_CORRUPT; return 1; }
+    SfqFileHeader h; memcpy(&h, sfq, sizeof h);
+    std::vector<uint8_t> text;
+    for (uint64_t c = 0; c < h.nchunks; c++) {
+        uint64_t off; memcpy(&off, sfq + h.index_off + 8 * c, 8);
+        SfqBlobHeader b; memcpy(&b, sfq + off, sizeof b);
+        if (b.magic != SFQ_BLOB_MAGIC) { *status_out = SFQ_E_CORRUPT; return 1; }
+        SfqChunkMeta m; memset(&m, 0, sizeof m);
+        m.nrec = b.nrec; m.nbases = b.nbases; m.nquals = b.nquals; m.hdr_bytes = b.hdr_bytes; m.llen = b.llen;
+        m.solid = b.solid; m.two_id = b.two_id; m.n_byte = b.n_byte; m.text_len = b.text_len; m.out_len = b.out_len;
+        const int level = (int)b.level;
+        uint64_t soff[SFQ_NSTREAMS]; uint32_t ssize[SFQ_NSTREAMS];
+        uint64_t o = off + sizeof b + b.rec_first_len;
+        for (int k = 0; k < SFQ_NSTREAMS; k++) { soff[k] = o; ssize[k] = b.ssize[k]; o += b.ssize[k]; }
+        uint32_t hbits = sfq_gen_hbits(level, m.nbases, 0);
+        void *gt = calloc(1, sfq_gtable_bytes(level, hbits));
+        uint32_t *qt = (uint32_t *)calloc(1, sfq_qtable_bytes(level));
+        uint32_t *pw = (uint32_t *)calloc(1, sfq_pwpool_bytes());
+        std::vector<uint32_t> llen(m.nrec), qlen(m.nrec), hlen(m.nrec);
+        std::vector<uint8_t> pfg(m.nrec), pfq(m.nrec);
+        std::vector<uint64_t> boff(m.nrec), qoff(m.nrec), hoff(m.nrec);
+        sfq_usr_decode_chunk(sfq, ssize, soff, &m, pw, llen.data(), qlen.data(), pfg.data(), pfq.data());
+        if (m.status) { *status_out = m.status; return 1; }
+        uint64_t nb = 0, nq = 0;
+        for (uint32_t r = 0; r < m.nrec; r++) { boff[r] = nb; qoff[r] = nq; nb += llen[r]; nq += qlen[r]; }
+        std::vector<uint8_t> bases(nb + 1), quals(nq + 1), hdrs((size_t)m.hdr_bytes + m.nrec + 64);
+        sfq_gen_decode_chunk(sfq, ssize, soff, &m, level, gt, hbits, pw, llen.data(), boff.data(), bases.data());
+        sfq_qlt_decode_chunk(sfq, ssize, soff, &m, level, qt, pw, qlen.data(), qoff.data(), quals.data());
+        sfq_rec_decode_chunk(sfq, ssize, soff, &m, pw, sfq + off + sizeof b, b.rec_first_len, hdrs.data(),
+                             hdrs.size(), hlen.data(), hoff.data());
+        free(gt); free(qt); free(pw);
+        if (m.status) { *status_out = m.status; return 1; }
+        const uint8_t nbyte = m.n_byte ? m.n_byte : 'N';
+        size_t before = text.size();
+        for (uint32_t r = 0; r < m.nrec; r++) {       // UsrLoad::save, usrs.cpp:512-529 (the assemble kernel)
+            text.push_back('@'); put_bytes(text, hdrs.data() + hoff[r], hlen[r]); text.push_back('\n');
+            if (m.solid) text.push_back(pfg[r]);
+            for (uint32_t i = 0; i < llen[r]; i++) {
+                uint8_t cch = bases[boff[r] + i];
+                uint8_t q = i < qlen[r] ? quals[qoff[r] + i] : 40;
+                if (cch & 0x80) cch &= 0x7f; else if (q == '!') cch = nbyte;
+                text.push_back(cch);
+            }
+            text.push_back('\n'); text.push_back('+');
+            if (m.two_id) put_bytes(text, hdrs.data() + hoff[r], hlen[r]);
+            text.push_back('\n');
+            if (m.solid) text.push_back(pfq[r]);
+            put_bytes(text, quals.data() + qoff[r], qlen[r]);
+            text.push_back('\n');
+        }
+        if (text.size() - before != b.out_len) { *status_out = SFQ_E_CORRUPT; return 1; }
+    }
+    *out = (uint8_t *)malloc(text.size() + 1);
+    memcpy(*out, text.data(), text.size());
+    *out_n = text.size();
+    return 0;
+}
+extern "C" void sfq_emul_free(void *p) { free(p); }
