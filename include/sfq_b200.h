@@ -1,0 +1,104 @@
+/* sfq_b200.h - C ABI of the B200-native slimfastq hot path (libsfq_b200.so).
+ *
+ * The reference has no FFI; its hot path sits behind C++ objects that are driven once per record
+ * from exactly two loops.  The entry points below replace those loops wholesale (a batch of
+ * records in, all streams out), so a host program - the reference's own main(), or the CLI in
+ * slimfastq_b200/csrc/sfq_cli.cpp - binds them where it used to run:
+ *
+ *   sfq_compress / sfq_compress_device     <- UsrSave::encode()              usrs.cpp:392-407
+ *        RecSave::save  recs.cpp:277-372 | GenSave::save  gens.hpp:89-93, gens.cpp:138-159
+ *        QltSave::save  qlts.hpp:82-90, qlts.cpp:74-136 | UsrSave::get_record usrs.cpp:303-390
+ *        XFileSave::put/put_chr/put_str xfile.cpp:66-99 | RCoder::Encode/done coder.hpp:52-81
+ *   sfq_decompress / sfq_decompress_device <- UsrLoad::decode()              usrs.cpp:539-574
+ *        RecLoad::load  recs.cpp:374-461 | GenLoad::load  gens.hpp:110-114, gens.cpp:215-249
+ *        QltLoad::load  qlts.hpp:108-116, qlts.cpp:163-234 | UsrLoad::update/save usrs.cpp:471-529
+ *        XFileLoad::get/get_chr/get_str xfile.cpp:76-109 | RCoder::GetFreq/Decode coder.hpp:83-102
+ *   sfq_last_error + non-zero return       <- croak() + exit(1)              config.cpp:54-68
+ *   the container written/read             <- FilerSave::put / FilerLoad::get filer.hpp:70-97
+ *
+ * Every chunk of the container holds the byte streams the reference would write for that chunk as
+ * a standalone file at the same level (rec, gen, qlt, gen.Ns, gen.Nn, rec.x, usr.x, usr.x.q,
+ * usr.pfg, usr.pfq) plus the semantic keys of its info stream; see sfq_container.h.
+ *
+ * Plain pointers and sizes only.  All entry points return 0 on success; on failure they return a
+ * non-zero SFQ_ERR_* code and sfq_last_error() gives the message (the reference's croak text where
+ * one exists).  There is no CPU fallback: without a usable CUDA device sfq_create() fails.
+ * A context is not thread-safe; use one per host thread / per GPU.
+ */
+#ifndef SFQ_B200_H
+#define SFQ_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sfq_ctx sfq_ctx;
+
+enum {
+    SFQ_ERR_NONE = 0,
+    SFQ_ERR_CUDA = 1,        /* no device / CUDA runtime failure                               */
+    SFQ_ERR_ARG = 2,         /* bad argument                                                   */
+    SFQ_ERR_FASTQ = 3,       /* input is not FASTQ the reference would accept (croak text)      */
+    SFQ_ERR_UNSUPPORTED = 4, /* oversized records (usrs.hpp:34-36) are not coded by this build  */
+    SFQ_ERR_FORMAT = 5,      /* not a b200 chunked .sfq container / corrupt container           */
+    SFQ_ERR_NOMEM = 6,       /* host or device memory                                          */
+    SFQ_ERR_SPACE = 7        /* caller-provided output buffer too small                        */
+};
+
+/* Per-call measurements (device times from CUDA events on the library's stream). */
+typedef struct sfq_stats {
+    uint64_t in_bytes, out_bytes;
+    uint64_t nchunks, nrecords, nbases, nquals;
+    uint64_t stream_bytes;        /* sum of all range-coded stream bytes                      */
+    uint32_t waves;               /* coder launches (resident-chunk waves)                    */
+    uint32_t resident_chunks;     /* chunks resident per wave                                 */
+    uint32_t kernel_launches;     /* kernels launched by the call                             */
+    uint32_t retries;             /* reruns after a stream arena / hash table had to grow     */
+    float ms_total;               /* whole call on the device timeline                        */
+    float ms_h2d, ms_d2h;         /* host<->device copies (host-buffer entry points only)     */
+    float ms_scan;                /* newline scan: count + prefix + fill                      */
+    float ms_plan;                /* chunk bounds + per-chunk framing facts                   */
+    float ms_clear;               /* zeroing the model tables                                 */
+    float ms_code;                /* k_encode / k_decode (sum over waves)                     */
+    float ms_pack;                /* k_blob_offsets + k_pack  |  k_out_offsets + k_assemble   */
+    uint64_t workspace_bytes;     /* model tables resident per wave                           */
+} sfq_stats;
+
+/* Create a context on CUDA device `device` (-1 = current).  Fails if no device is usable. */
+int  sfq_create(sfq_ctx **ctx, int device);
+void sfq_destroy(sfq_ctx *ctx);
+const char *sfq_last_error(const sfq_ctx *ctx);
+const char *sfq_version(void);          /* "2.04/6 b200" - user version / internal format, config.cpp:44-45 */
+
+/* Upper bound on resident chunks per coder wave (0 = as many as device memory allows). */
+int sfq_set_max_resident(sfq_ctx *ctx, uint32_t chunks);
+
+/* Pinned host staging buffers (optional, but pageable memory halves the PCIe rate). */
+void *sfq_host_alloc(size_t bytes);
+void  sfq_host_free(void *p);
+
+/* Compress a whole FASTQ buffer held in HOST memory.  level 1..4 (clamped like config.cpp:231-236),
+ * chunk_bytes = target chunk size (0 = 1 MiB).  *out points to a context-owned pinned buffer that
+ * stays valid until the next call on this context. */
+int sfq_compress(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes,
+                 const uint8_t **out, size_t *out_n);
+/* Same with input and output resident in DEVICE memory (16-byte aligned). */
+int sfq_compress_device(sfq_ctx *ctx, const void *d_fastq, size_t n, int level, uint64_t chunk_bytes,
+                        void *d_out, size_t out_cap, size_t *out_n);
+/* Worst-case container size sfq_compress_device may need for n input bytes. */
+size_t sfq_compress_bound(size_t n, uint64_t chunk_bytes);
+
+/* Decompress a chunked .sfq container. */
+int sfq_decompress(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **out, size_t *out_n);
+int sfq_decompress_device(sfq_ctx *ctx, const void *d_sfq, size_t n, void *d_out, size_t out_cap, size_t *out_n);
+/* Size of the FASTQ text a container (host pointer; only the 72-byte header is read) decodes to. */
+int sfq_decompressed_size(const uint8_t *sfq, size_t n, uint64_t *out_n, int *level);
+
+int sfq_get_stats(const sfq_ctx *ctx, sfq_stats *st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,9 @@
+"""slimfastq_b200: B200-native implementation of slimfastq's entropy-coding hot path.
+
+`Codec` (api.py) is the host-side mirror of the reference's encode/decode loops over the C ABI in
+include/sfq_b200.h; `container` reads the chunked .sfq container; `synth` generates the benchmark
+inputs.  All coding runs in libsfq_b200.so's sm_100a kernels - there is no CPU path.
+"""
+from .api import Codec, SfqError, decompressed_size, merge_containers, split_records  # noqa: F401
+
+__all__ = ["Codec", "SfqError", "decompressed_size", "merge_containers", "split_records"]

@@ -11,7 +11,7 @@ from dataclasses import dataclass, field
 STAMP = b"whoami=slimfastq"
 KIND = b"\nformat=b200.c1\n"
 STREAM_NAMES = ["rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq"]
-FILE_HDR = struct.Struct("<16s16sIIQQQQ")
+FILE_HDR = struct.Struct("<16s16sIIQQQQQ")
 BLOB_HDR = struct.Struct("<IIQQIIIIiBBBBII10I")
 BLOB_MAGIC = 0x43514653
 
@@ -44,6 +44,7 @@ class Container:
     orig_size: int
     chunk_bytes: int
     chunks: list[Chunk]
+    out_size: int = 0
 
     @property
     def stream_bytes(self) -> int:
@@ -57,7 +58,7 @@ def is_container(blob: bytes) -> bool:
 def parse(blob: bytes) -> Container:
     if not is_container(blob):
         raise ValueError("not a b200 chunked .sfq container")
-    _, _, version, level, orig, nchunks, chunk_bytes, index_off = FILE_HDR.unpack_from(blob, 0)
+    _, _, version, level, orig, nchunks, chunk_bytes, index_off, out_size = FILE_HDR.unpack_from(blob, 0)
     offs = struct.unpack_from(f"<{nchunks}Q", blob, index_off)
     chunks = []
     for off in offs:
@@ -76,4 +77,4 @@ def parse(blob: bytes) -> Container:
             p += sz
         chunks.append(Chunk(lvl, text_len, out_len, nrec, nb, nq, hb, llen, solid, two_id, n_byte,
                             extra_hi, rec_first, streams, p - off))
-    return Container(level, orig, chunk_bytes, chunks)
+    return Container(level, orig, chunk_bytes, chunks, out_size)

@@ -1,0 +1,604 @@
+// C-ABI library (include/sfq_b200.h): host orchestration of the sm_100a kernels.
+// No CPU coding path exists in this file: every stream byte is produced by a kernel launch.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sfq_b200.h"
+#include "sfq_kernels.cuh"
+#include "sfq_layout.h"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum { EV_START = 0, EV_H2D, EV_SCAN, EV_PLAN, EV_CODE_END, EV_D2H, EV_COUNT };
+
+}  // namespace
+
+struct sfq_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    sfq_stats st{};
+    uint32_t max_resident = 0;
+    cudaEvent_t ev[EV_COUNT]{};
+    std::vector<cudaEvent_t> wave_ev;       // 4 per wave: clear start, code start, code end, pack end
+    // device buffers (grow-only, reused across calls)
+    DevBuf text, out, tiles, tile_prefix, lines, scalars, rec_begin, r0, r1, metas, arenas, arena_buf,
+           blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
+           t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff;
+    HostBuf h_out, h_small;
+    void release_all() {
+        DevBuf *all[] = {&text, &out, &tiles, &tile_prefix, &lines, &scalars, &rec_begin, &r0, &r1, &metas,
+                         &arenas, &arena_buf, &blob_off, &gtab, &qtab, &pw, &dchunks, &bhdrs, &bases, &quals,
+                         &hdrs, &rec_chunk, &t_llen, &t_qlen, &t_hlen, &t_pfg, &t_pfq, &t_boff, &t_qoff,
+                         &t_hoff, &t_ooff};
+        for (DevBuf *b : all) b->release();
+        h_out.release(); h_small.release();
+    }
+};
+
+namespace {
+
+int fail(sfq_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    c->err = buf;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? SFQ_ERR_NOMEM : SFQ_ERR_CUDA,        \
+                        "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__);      \
+    } while (0)
+#define LAUNCHED() (ctx->st.kernel_launches++)
+
+// The reference's croak texts (config.cpp:54-68 prefix omitted), keyed by kernel status.
+int status_to_error(sfq_ctx *ctx, const SfqChunkMeta &m, uint64_t chunk, uint64_t rec_base) {
+    const unsigned long long rec = rec_base + m.status_arg;
+    switch (m.status) {
+    case SFQ_E_AT: return fail(ctx, SFQ_ERR_FASTQ, "fastq file: expecting '@' at record %llu (chunk %llu)", rec, (unsigned long long)chunk);
+    case SFQ_E_PLUS: return fail(ctx, SFQ_ERR_FASTQ, "fastq file: expecting '+' at record %llu (chunk %llu)", rec, (unsigned long long)chunk);
+    case SFQ_E_TRUNC: return fail(ctx, SFQ_ERR_FASTQ, "fastq file: record seems truncated  after record %llu", rec);
+    case SFQ_E_OVERSIZE: return fail(ctx, SFQ_ERR_UNSUPPORTED, "record %llu: oversized record (id >= 8 KiB or line >= 64 KiB) is not supported", rec);
+    case SFQ_E_BASE: return fail(ctx, SFQ_ERR_FASTQ, "unexpected genome char: %c", (int)m.status_arg);
+    case SFQ_E_NBYTE: return fail(ctx, SFQ_ERR_FASTQ, "switched N_byte: %c", (int)m.status_arg);
+    case SFQ_E_SEPS: return fail(ctx, SFQ_ERR_FASTQ, "ERROR: irregulal record (over 64 non alpha non digit). Is it a valid fastq file?");
+    case SFQ_E_FIRSTHDR: return fail(ctx, SFQ_ERR_UNSUPPORTED, "chunk %llu: first header longer than 399 chars", (unsigned long long)chunk);
+    case SFQ_E_EMPTYSEQ: return fail(ctx, SFQ_ERR_UNSUPPORTED, "chunk %llu: first record has an empty base line", (unsigned long long)chunk);
+    case SFQ_E_CORRUPT: return fail(ctx, SFQ_ERR_FORMAT, "chunk %llu: corrupt stream", (unsigned long long)chunk);
+    default: return fail(ctx, SFQ_ERR_CUDA, "chunk %llu: internal status %u", (unsigned long long)chunk, m.status);
+    }
+}
+
+// How many chunks can have their model tables resident at once.
+uint32_t pick_resident(sfq_ctx *ctx, uint64_t nchunks, uint64_t per_chunk, uint64_t already_have) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    uint64_t budget = (uint64_t)((double)(free_b + already_have) * 0.90);
+    uint64_t r = budget / per_chunk;
+    if (r < 1) r = 1;
+    if (ctx->max_resident && r > ctx->max_resident) r = ctx->max_resident;
+    const char *env = getenv("SFQ_MAX_RESIDENT");
+    if (env && atoll(env) > 0 && r > (uint64_t)atoll(env)) r = (uint64_t)atoll(env);
+    if (r > nchunks) r = nchunks;
+    // even waves: ceil(nchunks / nwaves)
+    uint64_t nw = (nchunks + r - 1) / r;
+    r = (nchunks + nw - 1) / nw;
+    return (uint32_t)r;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+int ensure_wave_events(sfq_ctx *ctx, size_t waves) {
+    while (ctx->wave_ev.size() < waves * 4) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->wave_ev.push_back(e);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ compress
+int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level, uint64_t chunk_bytes,
+                       uint8_t *d_out, size_t out_cap, size_t *out_n) {
+    cudaStream_t s = ctx->stream;
+    sfq_stats &st = ctx->st;
+    level = level > 4 ? 4 : level < 1 ? 1 : level;                    // range_level, config.cpp:231-236
+    if (!chunk_bytes) chunk_bytes = 1ull << 20;
+    if (chunk_bytes < 4096) chunk_bytes = 4096;
+    if (n == 0) return fail(ctx, SFQ_ERR_FASTQ, "no records were found");
+    if (((uintptr_t)d_text & 15) || ((uintptr_t)d_out & 15)) return fail(ctx, SFQ_ERR_ARG, "device buffers must be 16-byte aligned");
+    if (out_cap < sizeof(SfqFileHeader)) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small");
+
+    // ---- scan: newline index
+    const uint64_t ntiles = (n + SFQ_SCAN_TILE - 1) / SFQ_SCAN_TILE;
+    CK(ctx->tiles.ensure(ntiles * 4));
+    CK(ctx->tile_prefix.ensure(ntiles * 8));
+    CK(ctx->scalars.ensure(256));
+    CK(ctx->h_small.ensure(4096));
+    uint64_t *d_scal = ctx->scalars.as<uint64_t>();     // [0] newline total, [1] blob cursor, [2] pack overflow
+    k_count_newlines<<<(unsigned)ntiles, SFQ_SCAN_THREADS, 0, s>>>(d_text, n, ctx->tiles.as<uint32_t>()); LAUNCHED();
+    k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tiles.as<uint32_t>(), ctx->tile_prefix.as<uint64_t>(), ntiles, d_scal); LAUNCHED();
+    uint64_t *h_small = ctx->h_small.as<uint64_t>();
+    CK(cudaMemcpyAsync(h_small, d_scal, 8, cudaMemcpyDeviceToHost, s));
+    uint8_t last_byte = 0;
+    CK(cudaMemcpyAsync(&h_small[1], d_text + n - 1, 1, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t nlines = h_small[0];
+    last_byte = *reinterpret_cast<uint8_t *>(&h_small[1]);
+    if (last_byte != '\n' || nlines % 4 || nlines == 0)
+        return fail(ctx, SFQ_ERR_FASTQ, "fastq file: record seems truncated  after record %llu", (unsigned long long)(nlines / 4));
+    const uint64_t nrec_total = nlines / 4;
+    CK(ctx->lines.ensure((nlines + 1) * 8));
+    const uint64_t *d_ls = ctx->lines.as<uint64_t>();
+    k_fill_lines<<<(unsigned)ntiles, SFQ_SCAN_THREADS, 0, s>>>(d_text, n, ctx->tile_prefix.as<uint64_t>(), ctx->lines.as<uint64_t>()); LAUNCHED();
+    CK(cudaEventRecord(ctx->ev[EV_SCAN], s));
+
+    // ---- plan: chunk boundaries, then per-chunk framing facts
+    const uint64_t nslots = (n + chunk_bytes - 1) / chunk_bytes;
+    CK(ctx->rec_begin.ensure((nslots + 1) * 8));
+    k_chunk_bounds<<<(unsigned)((nslots + 1 + 127) / 128), 128, 0, s>>>(d_ls, nrec_total, chunk_bytes, nslots, ctx->rec_begin.as<uint64_t>()); LAUNCHED();
+    std::vector<uint64_t> rb(nslots + 1);
+    CK(cudaMemcpyAsync(rb.data(), ctx->rec_begin.p, (nslots + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<uint64_t> r0, r1;
+    for (uint64_t c = 0; c < nslots; c++)
+        if (rb[c + 1] > rb[c]) { r0.push_back(rb[c]); r1.push_back(rb[c + 1]); }
+    const uint32_t nchunks = (uint32_t)r0.size();
+    CK(ctx->r0.ensure(nchunks * 8ull)); CK(ctx->r1.ensure(nchunks * 8ull));
+    CK(ctx->metas.ensure(nchunks * sizeof(SfqChunkMeta)));
+    CK(cudaMemcpyAsync(ctx->r0.p, r0.data(), nchunks * 8ull, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->r1.p, r1.data(), nchunks * 8ull, cudaMemcpyHostToDevice, s));
+    SfqChunkMeta *d_metas = ctx->metas.as<SfqChunkMeta>();
+    k_chunk_plan<<<(nchunks + 63) / 64, 64, 0, s>>>(d_text, d_ls, ctx->r0.as<uint64_t>(), ctx->r1.as<uint64_t>(), d_metas, nchunks); LAUNCHED();
+    std::vector<SfqChunkMeta> metas(nchunks);
+    CK(cudaMemcpyAsync(metas.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[EV_PLAN], s));
+    CK(cudaStreamSynchronize(s));
+    uint64_t max_bases = 0, out_total = 0;
+    st.nchunks = nchunks; st.nrecords = nrec_total; st.nbases = st.nquals = 0;
+    for (uint32_t c = 0; c < nchunks; c++) {
+        if (metas[c].status) return status_to_error(ctx, metas[c], c, r0[c]);
+        max_bases = std::max<uint64_t>(max_bases, metas[c].nbases);
+        st.nbases += metas[c].nbases; st.nquals += metas[c].nquals;
+        out_total += metas[c].out_len;
+    }
+
+    // ---- code + pack, in waves of resident chunks; rerun with more room if a stream or table overflowed
+    CK(ctx->arenas.ensure(nchunks * sizeof(SfqArena)));
+    CK(ctx->blob_off.ensure(nchunks * 8ull));
+    SfqArena *d_arenas = ctx->arenas.as<SfqArena>();
+    uint64_t *d_blob_off = ctx->blob_off.as<uint64_t>();
+    std::vector<SfqArena> arenas(nchunks);
+    std::vector<uint64_t> blob_off(nchunks);
+    uint64_t end_cursor = 0;
+    st.retries = 0;
+    for (uint32_t grow = 0;; grow++) {
+        const uint32_t hbits = sfq_gen_hbits(level, max_bases, grow);
+        const uint64_t gstride = sfq_gtable_bytes(level, hbits), qbytes = sfq_qtable_bytes(level), pbytes = sfq_pwpool_bytes();
+        uint64_t max_arena = 0;
+        for (uint32_t c = 0; c < nchunks; c++) {
+            uint64_t end; SfqArena a;
+            sfq_arena_layout(&metas[c], grow, 0, &a, &end);
+            max_arena = std::max(max_arena, end);
+        }
+        const uint64_t per_chunk = gstride + qbytes + pbytes + max_arena + 4096;
+        const uint32_t R = pick_resident(ctx, nchunks, per_chunk, ctx->gtab.cap + ctx->qtab.cap + ctx->pw.cap + ctx->arena_buf.cap);
+        CK(ctx->gtab.ensure(R * gstride)); CK(ctx->qtab.ensure(R * qbytes)); CK(ctx->pw.ensure(R * pbytes));
+        const uint32_t nwaves = (nchunks + R - 1) / R;
+        if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
+        st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * (gstride + qbytes + pbytes);
+        // arena layout: offsets restart at 0 for every wave
+        uint64_t wave_arena_max = 0;
+        for (uint32_t w = 0; w < nwaves; w++) {
+            uint64_t o = 0;
+            for (uint32_t c = w * R; c < std::min(nchunks, (w + 1) * R); c++) sfq_arena_layout(&metas[c], grow, o, &arenas[c], &o);
+            wave_arena_max = std::max(wave_arena_max, o);
+        }
+        CK(ctx->arena_buf.ensure(wave_arena_max + 64));
+        CK(cudaMemcpyAsync(d_arenas, arenas.data(), nchunks * sizeof(SfqArena), cudaMemcpyHostToDevice, s));
+        h_small[0] = 0; h_small[1] = sizeof(SfqFileHeader); h_small[2] = 0;
+        CK(cudaMemcpyAsync(d_scal, h_small, 24, cudaMemcpyHostToDevice, s));
+        SfqWorkspace ws;
+        ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
+        ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.pw = ctx->pw.as<uint32_t>();
+        for (uint32_t w = 0; w < nwaves; w++) {
+            const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
+            CK(cudaEventRecord(ctx->wave_ev[4 * w + 0], s));
+            CK(cudaMemsetAsync(ctx->gtab.p, 0, nc * gstride, s));
+            CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
+            CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
+            CK(cudaEventRecord(ctx->wave_ev[4 * w + 1], s));
+            k_encode<<<dim3((nc + 31) / 32, 3), 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), ws, level, nc); LAUNCHED();
+            CK(cudaEventRecord(ctx->wave_ev[4 * w + 2], s));
+            k_blob_offsets<<<1, 1024, 0, s>>>(d_metas + c0, d_arenas + c0, d_ls, nc, d_blob_off + c0, d_scal + 1); LAUNCHED();
+            k_pack<<<nc, 256, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), d_blob_off + c0, level,
+                                      d_out, out_cap, reinterpret_cast<uint32_t *>(d_scal + 2)); LAUNCHED();
+            CK(cudaEventRecord(ctx->wave_ev[4 * w + 3], s));
+        }
+        CK(cudaMemcpyAsync(metas.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(arenas.data(), d_arenas, nchunks * sizeof(SfqArena), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(blob_off.data(), d_blob_off, nchunks * 8ull, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_small, d_scal, 24, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        bool again = false;
+        for (uint32_t c = 0; c < nchunks; c++) {
+            if (metas[c].status == SFQ_E_CAP || metas[c].status == SFQ_E_TABLE) again = true;
+            else if (metas[c].status) return status_to_error(ctx, metas[c], c, r0[c]);
+        }
+        st.ms_clear = st.ms_code = st.ms_pack = 0;
+        for (uint32_t w = 0; w < nwaves; w++) {
+            st.ms_clear += ev_ms(ctx->wave_ev[4 * w], ctx->wave_ev[4 * w + 1]);
+            st.ms_code += ev_ms(ctx->wave_ev[4 * w + 1], ctx->wave_ev[4 * w + 2]);
+            st.ms_pack += ev_ms(ctx->wave_ev[4 * w + 2], ctx->wave_ev[4 * w + 3]);
+        }
+        if (!again) { end_cursor = h_small[1]; if (*reinterpret_cast<uint32_t *>(&h_small[2])) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need more than %llu bytes)", (unsigned long long)out_cap); break; }
+        if (grow >= 6) return fail(ctx, SFQ_ERR_CUDA, "stream arena still too small after 6 doublings");
+        st.retries++;
+        for (uint32_t c = 0; c < nchunks; c++) metas[c].status = SFQ_OK;
+        CK(cudaMemcpyAsync(d_metas, metas.data(), nchunks * sizeof(SfqChunkMeta), cudaMemcpyHostToDevice, s));
+    }
+
+    // ---- file header + index ("host-side exchange of compressed-size offsets")
+    const uint64_t index_off = end_cursor;
+    if (index_off + nchunks * 8ull > out_cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)(index_off + nchunks * 8ull));
+    SfqFileHeader fh;
+    sfq_file_header_init(&fh, level, n, nchunks, chunk_bytes, index_off, out_total);
+    CK(cudaMemcpyAsync(d_out, &fh, sizeof fh, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_out + index_off, blob_off.data(), nchunks * 8ull, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->ev[EV_CODE_END], s));
+    CK(cudaStreamSynchronize(s));
+    *out_n = index_off + nchunks * 8ull;
+    st.stream_bytes = 0;
+    for (uint32_t c = 0; c < nchunks; c++) for (int k = 0; k < SFQ_NSTREAMS; k++) st.stream_bytes += arenas[c].size[k];
+    st.in_bytes = n; st.out_bytes = *out_n;
+    st.ms_scan = ev_ms(ctx->ev[EV_H2D], ctx->ev[EV_SCAN]);
+    st.ms_plan = ev_ms(ctx->ev[EV_SCAN], ctx->ev[EV_PLAN]);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ decompress
+// `h_hdr`/`h_index`/`h_blobs` are host copies of the file header, the blob-offset index and the blob headers.
+int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqFileHeader &fh,
+                         const std::vector<uint64_t> &index, const std::vector<SfqBlobHeader> &blobs,
+                         uint8_t *d_out, size_t out_cap, size_t *out_n) {
+    cudaStream_t s = ctx->stream;
+    sfq_stats &st = ctx->st;
+    const uint32_t nchunks = (uint32_t)fh.nchunks;
+    std::vector<SfqChunkMeta> metas(nchunks);
+    std::vector<SfqDecChunk> dcs(nchunks);
+    uint64_t nrec = 0, nb = 0, nq = 0, nh = 0, no = 0, max_bases = 0;
+    int max_level = 1;
+    st.stream_bytes = 0;
+    for (uint32_t c = 0; c < nchunks; c++) {
+        const SfqBlobHeader &b = blobs[c];
+        const uint64_t off = index[c];
+        if (b.magic != SFQ_BLOB_MAGIC || off + sfq_blob_size(&b) > n || b.level < 1 || b.level > 4 ||
+            b.nrec == 0 || b.rec_first_len > 399)
+            return fail(ctx, SFQ_ERR_FORMAT, "chunk %u: bad blob header", c);
+        SfqChunkMeta &m = metas[c];
+        memset(&m, 0, sizeof m);
+        m.text_len = b.text_len; m.out_len = b.out_len; m.nrec = b.nrec; m.nbases = b.nbases; m.nquals = b.nquals;
+        m.hdr_bytes = b.hdr_bytes; m.llen = b.llen; m.solid = b.solid; m.two_id = b.two_id; m.n_byte = b.n_byte;
+        SfqDecChunk &d = dcs[c];
+        uint64_t o = off + sizeof(SfqBlobHeader);
+        d.rec_first_off = o; d.rec_first_len = b.rec_first_len; o += b.rec_first_len;
+        for (int k = 0; k < SFQ_NSTREAMS; k++) { d.soff[k] = o; d.ssize[k] = b.ssize[k]; o += b.ssize[k]; st.stream_bytes += b.ssize[k]; }
+        d.level = (int32_t)b.level;
+        d.rec_base = nrec; d.base_plane = nb; d.qual_plane = nq; d.hdr_plane = nh;
+        nrec += b.nrec; nb += b.nbases; nq += b.nquals; nh += SFQ_HDR_PLANE(&m); no += b.out_len;
+        max_bases = std::max<uint64_t>(max_bases, b.nbases);
+        max_level = std::max(max_level, (int)b.level);
+        // a record prints at least "@h\nb\n+\nq\n": reject headers whose counts cannot match their out_len
+        if (b.out_len < 6ull * b.nrec || (uint64_t)b.nbases + b.nquals + b.hdr_bytes > b.out_len)
+            return fail(ctx, SFQ_ERR_FORMAT, "chunk %u: inconsistent blob header", c);
+    }
+    if (no > out_cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)no);
+    CK(ctx->blob_off.ensure(nchunks * 8ull));          // reused as per-chunk output sizes / offsets
+    CK(ctx->scalars.ensure(256));
+    CK(ctx->h_small.ensure(4096));
+    st.nchunks = nchunks; st.nrecords = nrec; st.nbases = nb; st.nquals = nq;
+
+    CK(ctx->metas.ensure(nchunks * sizeof(SfqChunkMeta)));
+    CK(ctx->dchunks.ensure(nchunks * sizeof(SfqDecChunk)));
+    CK(ctx->bases.ensure(nb + 16)); CK(ctx->quals.ensure(nq + 16)); CK(ctx->hdrs.ensure(nh + 16));
+    CK(ctx->rec_chunk.ensure(nrec * 4));
+    CK(ctx->t_llen.ensure(nrec * 4)); CK(ctx->t_qlen.ensure(nrec * 4)); CK(ctx->t_hlen.ensure(nrec * 4));
+    CK(ctx->t_pfg.ensure(nrec)); CK(ctx->t_pfq.ensure(nrec));
+    CK(ctx->t_boff.ensure(nrec * 8)); CK(ctx->t_qoff.ensure(nrec * 8)); CK(ctx->t_hoff.ensure(nrec * 8)); CK(ctx->t_ooff.ensure(nrec * 8));
+    std::vector<uint32_t> rec_chunk(nrec);
+    for (uint32_t c = 0; c < nchunks; c++) std::fill(rec_chunk.begin() + dcs[c].rec_base, rec_chunk.begin() + dcs[c].rec_base + metas[c].nrec, c);
+    SfqChunkMeta *d_metas = ctx->metas.as<SfqChunkMeta>();
+    SfqDecChunk *d_dcs = ctx->dchunks.as<SfqDecChunk>();
+    CK(cudaMemcpyAsync(d_metas, metas.data(), nchunks * sizeof(SfqChunkMeta), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_dcs, dcs.data(), nchunks * sizeof(SfqDecChunk), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->rec_chunk.p, rec_chunk.data(), nrec * 4, cudaMemcpyHostToDevice, s));
+    SfqRecTables t;
+    t.llen = ctx->t_llen.as<uint32_t>(); t.qlen = ctx->t_qlen.as<uint32_t>(); t.hlen = ctx->t_hlen.as<uint32_t>();
+    t.pfg = ctx->t_pfg.as<uint8_t>(); t.pfq = ctx->t_pfq.as<uint8_t>();
+    t.boff = ctx->t_boff.as<uint64_t>(); t.qoff = ctx->t_qoff.as<uint64_t>(); t.hoff = ctx->t_hoff.as<uint64_t>(); t.ooff = ctx->t_ooff.as<uint64_t>();
+    CK(cudaEventRecord(ctx->ev[EV_PLAN], s));
+
+    // all chunks of a container share one table geometry (sized for the largest level / chunk)
+    const uint32_t hbits = sfq_gen_hbits(max_level, max_bases, 0);
+    const uint64_t gstride = std::max(sfq_gtable_bytes(max_level, hbits), sfq_gtable_bytes(1, 18));
+    const uint64_t qbytes = sfq_qtable_bytes(max_level), pbytes = sfq_pwpool_bytes();
+    const uint32_t R = pick_resident(ctx, nchunks, gstride + qbytes + pbytes + 4096, ctx->gtab.cap + ctx->qtab.cap + ctx->pw.cap);
+    CK(ctx->gtab.ensure(R * gstride)); CK(ctx->qtab.ensure(R * qbytes)); CK(ctx->pw.ensure(R * pbytes));
+    const uint32_t nwaves = (nchunks + R - 1) / R;
+    if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
+    st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * (gstride + qbytes + pbytes);
+    SfqWorkspace ws;
+    ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
+    ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.pw = ctx->pw.as<uint32_t>();
+    for (uint32_t w = 0; w < nwaves; w++) {
+        const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
+        CK(cudaEventRecord(ctx->wave_ev[4 * w + 0], s));
+        CK(cudaMemsetAsync(ctx->gtab.p, 0, nc * gstride, s));
+        CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
+        CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
+        CK(cudaEventRecord(ctx->wave_ev[4 * w + 1], s));
+        k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, nc); LAUNCHED();
+        k_decode<<<dim3((nc + 31) / 32, 3), 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, ctx->bases.as<uint8_t>(),
+                                                     ctx->quals.as<uint8_t>(), ctx->hdrs.as<uint8_t>(), nc); LAUNCHED();
+        CK(cudaEventRecord(ctx->wave_ev[4 * w + 2], s));
+        CK(cudaEventRecord(ctx->wave_ev[4 * w + 3], s));
+    }
+    cudaEvent_t asm0 = ctx->ev[EV_SCAN];    // reused as "assemble start" on the decode timeline
+    CK(cudaEventRecord(asm0, s));
+    // output layout from the decoded lengths; equals the recorded out_len except where the reference
+    // itself prints a header differently from how it read it
+    uint64_t *d_cout = ctx->blob_off.as<uint64_t>();
+    k_out_sizes<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks); LAUNCHED();
+    k_scan_u64<<<1, 1024, 0, s>>>(d_cout, nchunks, ctx->scalars.as<uint64_t>()); LAUNCHED();
+    k_out_offsets<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks); LAUNCHED();
+    uint64_t *h_total = ctx->h_small.as<uint64_t>();
+    CK(cudaMemcpyAsync(h_total, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(metas.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint32_t c = 0; c < nchunks; c++)
+        if (metas[c].status) return status_to_error(ctx, metas[c], c, dcs[c].rec_base);
+    no = *h_total;
+    if (no > out_cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)no);
+    k_assemble<<<(unsigned)((nrec * 32 + 255) / 256), 256, 0, s>>>(d_dcs, d_metas, t, ctx->rec_chunk.as<uint32_t>(), ctx->bases.as<uint8_t>(),
+                                                                   ctx->quals.as<uint8_t>(), ctx->hdrs.as<uint8_t>(), d_out, nrec); LAUNCHED();
+    CK(cudaEventRecord(ctx->ev[EV_CODE_END], s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    st.ms_clear = st.ms_code = st.ms_pack = 0;
+    for (uint32_t w = 0; w < nwaves; w++) {
+        st.ms_clear += ev_ms(ctx->wave_ev[4 * w], ctx->wave_ev[4 * w + 1]);
+        st.ms_code += ev_ms(ctx->wave_ev[4 * w + 1], ctx->wave_ev[4 * w + 2]);
+        st.ms_pack += ev_ms(ctx->wave_ev[4 * w + 2], ctx->wave_ev[4 * w + 3]);
+    }
+    st.ms_pack += ev_ms(asm0, ctx->ev[EV_CODE_END]);
+    st.ms_scan = 0;
+    st.ms_plan = ev_ms(ctx->ev[EV_H2D], ctx->ev[EV_PLAN]);
+    st.in_bytes = n; st.out_bytes = no;
+    *out_n = no;
+    return 0;
+}
+
+int parse_host_container(sfq_ctx *ctx, const uint8_t *sfq, size_t n, SfqFileHeader &fh,
+                         std::vector<uint64_t> &index, std::vector<SfqBlobHeader> &blobs) {
+    if (!sfq_is_chunked_container(sfq, n)) return fail(ctx, SFQ_ERR_FORMAT, "not a b200 chunked .sfq container");
+    memcpy(&fh, sfq, sizeof fh);
+    if (fh.version > SFQ_INTERNAL_VERSION)     // config.cpp:373-377
+        return fail(ctx, SFQ_ERR_FORMAT, "compressed with slimfastq version %u. My version is %d. Please upgrade me before decoing", fh.version, SFQ_INTERNAL_VERSION);
+    if (fh.nchunks == 0 || fh.nchunks > 0x7fffffffull || fh.index_off > n || n - fh.index_off < fh.nchunks * 8)
+        return fail(ctx, SFQ_ERR_FORMAT, "corrupt container index");
+    index.resize(fh.nchunks); blobs.resize(fh.nchunks);
+    memcpy(index.data(), sfq + fh.index_off, fh.nchunks * 8);
+    for (uint64_t c = 0; c < fh.nchunks; c++) {
+        if (index[c] > n || n - index[c] < sizeof(SfqBlobHeader)) return fail(ctx, SFQ_ERR_FORMAT, "corrupt container index");
+        memcpy(&blobs[c], sfq + index[c], sizeof(SfqBlobHeader));
+    }
+    return 0;
+}
+
+void begin_call(sfq_ctx *ctx) {
+    cudaSetDevice(ctx->device);
+    ctx->err.clear();
+    memset(&ctx->st, 0, sizeof ctx->st);
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+const char *sfq_version(void) { return "2.04/6 b200"; }
+
+int sfq_create(sfq_ctx **out, int device) {
+    if (!out) return SFQ_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SFQ_ERR_CUDA;   // no CPU fallback
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return SFQ_ERR_CUDA;
+    if (device >= ndev) return SFQ_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return SFQ_ERR_CUDA;
+    sfq_ctx *ctx = new sfq_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    *out = ctx;
+    return 0;
+}
+
+void sfq_destroy(sfq_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->release_all();
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->wave_ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *sfq_last_error(const sfq_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context (is a CUDA device present?)"; }
+int sfq_set_max_resident(sfq_ctx *ctx, uint32_t chunks) { if (!ctx) return SFQ_ERR_ARG; ctx->max_resident = chunks; return 0; }
+int sfq_get_stats(const sfq_ctx *ctx, sfq_stats *st) { if (!ctx || !st) return SFQ_ERR_ARG; *st = ctx->st; return 0; }
+
+void *sfq_host_alloc(size_t bytes) { void *p = nullptr; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+void sfq_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+size_t sfq_compress_bound(size_t n, uint64_t chunk_bytes) {
+    if (!chunk_bytes) chunk_bytes = 1ull << 20;
+    const uint64_t slots = n / chunk_bytes + 2;
+    return (size_t)(n + n / 4 + slots * (sizeof(SfqBlobHeader) + 512 + 12 * SFQ_NSTREAMS + 8) + sizeof(SfqFileHeader) + 4096);
+}
+
+int sfq_compress_device(sfq_ctx *ctx, const void *d_fastq, size_t n, int level, uint64_t chunk_bytes,
+                        void *d_out, size_t out_cap, size_t *out_n) {
+    if (!ctx || !d_fastq || !d_out || !out_n) return SFQ_ERR_ARG;
+    begin_call(ctx);
+    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+    int rc = compress_on_device(ctx, (const uint8_t *)d_fastq, n, level, chunk_bytes, (uint8_t *)d_out, out_cap, out_n);
+    if (rc) return rc;
+    ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_CODE_END]);
+    return 0;
+}
+
+int sfq_compress(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes,
+                 const uint8_t **out, size_t *out_n) {
+    if (!ctx || !fastq || !out || !out_n) return SFQ_ERR_ARG;
+    begin_call(ctx);
+    if (n == 0) return fail(ctx, SFQ_ERR_FASTQ, "no records were found");
+    const size_t cap = sfq_compress_bound(n, chunk_bytes);
+    CK(ctx->text.ensure(n + 16));
+    CK(ctx->out.ensure(cap));
+    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->text.p, fastq, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+    size_t on = 0;
+    int rc = compress_on_device(ctx, ctx->text.as<uint8_t>(), n, level, chunk_bytes, ctx->out.as<uint8_t>(), cap, &on);
+    if (rc) return rc;
+    CK(ctx->h_out.ensure(on));
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->out.p, on, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->st.ms_h2d = ev_ms(ctx->ev[EV_START], ctx->ev[EV_H2D]);
+    ctx->st.ms_d2h = ev_ms(ctx->ev[EV_CODE_END], ctx->ev[EV_D2H]);
+    ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_D2H]);
+    *out = ctx->h_out.as<uint8_t>();
+    *out_n = on;
+    return 0;
+}
+
+int sfq_decompressed_size(const uint8_t *sfq, size_t n, uint64_t *out_n, int *level) {
+    if (!sfq || !sfq_is_chunked_container(sfq, n)) return SFQ_ERR_FORMAT;
+    SfqFileHeader fh;
+    memcpy(&fh, sfq, sizeof fh);
+    if (out_n) *out_n = fh.out_size;
+    if (level) *level = (int)fh.level;
+    return 0;
+}
+
+int sfq_decompress(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **out, size_t *out_n) {
+    if (!ctx || !sfq || !out || !out_n) return SFQ_ERR_ARG;
+    begin_call(ctx);
+    SfqFileHeader fh;
+    std::vector<uint64_t> index;
+    std::vector<SfqBlobHeader> blobs;
+    int rc = parse_host_container(ctx, sfq, n, fh, index, blobs);
+    if (rc) return rc;
+    uint64_t total = 4096;
+    for (auto &b : blobs) total += b.out_len + 8ull * b.nrec;      // slack: see SFQ_HDR_PLANE
+    CK(ctx->text.ensure(n + 16));          // container bytes
+    CK(ctx->out.ensure(total + 16));
+    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->text.p, sfq, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+    size_t on = 0;
+    rc = decompress_on_device(ctx, ctx->text.as<uint8_t>(), n, fh, index, blobs, ctx->out.as<uint8_t>(), total, &on);
+    if (rc) return rc;
+    CK(ctx->h_out.ensure(on + 1));
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->out.p, on, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->st.ms_h2d = ev_ms(ctx->ev[EV_START], ctx->ev[EV_H2D]);
+    ctx->st.ms_d2h = ev_ms(ctx->ev[EV_CODE_END], ctx->ev[EV_D2H]);
+    ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_D2H]);
+    *out = ctx->h_out.as<uint8_t>();
+    *out_n = on;
+    return 0;
+}
+
+int sfq_decompress_device(sfq_ctx *ctx, const void *d_sfq, size_t n, void *d_out, size_t out_cap, size_t *out_n) {
+    if (!ctx || !d_sfq || !d_out || !out_n) return SFQ_ERR_ARG;
+    begin_call(ctx);
+    cudaStream_t s = ctx->stream;
+    if (n < sizeof(SfqFileHeader)) return fail(ctx, SFQ_ERR_FORMAT, "not a b200 chunked .sfq container");
+    CK(cudaEventRecord(ctx->ev[EV_START], s));
+    CK(cudaEventRecord(ctx->ev[EV_H2D], s));
+    SfqFileHeader fh;
+    CK(cudaMemcpyAsync(&fh, d_sfq, sizeof fh, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (!sfq_is_chunked_container(reinterpret_cast<const uint8_t *>(&fh), sizeof fh)) return fail(ctx, SFQ_ERR_FORMAT, "not a b200 chunked .sfq container");
+    if (fh.nchunks == 0 || fh.nchunks > 0x7fffffffull || fh.index_off > n || n - fh.index_off < fh.nchunks * 8)
+        return fail(ctx, SFQ_ERR_FORMAT, "corrupt container index");
+    std::vector<uint64_t> index(fh.nchunks);
+    std::vector<SfqBlobHeader> blobs(fh.nchunks);
+    CK(ctx->bhdrs.ensure(fh.nchunks * sizeof(SfqBlobHeader)));
+    const uint64_t *d_index = reinterpret_cast<const uint64_t *>((const uint8_t *)d_sfq + fh.index_off);
+    if (fh.index_off & 7) {     // unaligned index: stage it through the blob_off buffer
+        CK(ctx->blob_off.ensure(fh.nchunks * 8));
+        CK(cudaMemcpyAsync(ctx->blob_off.p, (const uint8_t *)d_sfq + fh.index_off, fh.nchunks * 8, cudaMemcpyDeviceToDevice, s));
+        d_index = ctx->blob_off.as<uint64_t>();
+    }
+    k_gather_blob_headers<<<(unsigned)((fh.nchunks + 127) / 128), 128, 0, s>>>((const uint8_t *)d_sfq, d_index, ctx->bhdrs.as<SfqBlobHeader>(), fh.nchunks, n); LAUNCHED();
+    CK(cudaMemcpyAsync(index.data(), d_index, fh.nchunks * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(blobs.data(), ctx->bhdrs.p, fh.nchunks * sizeof(SfqBlobHeader), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint64_t c = 0; c < fh.nchunks; c++)
+        if (index[c] > n || n - index[c] < sizeof(SfqBlobHeader)) return fail(ctx, SFQ_ERR_FORMAT, "corrupt container index");
+    int rc = decompress_on_device(ctx, (const uint8_t *)d_sfq, n, fh, index, blobs, (uint8_t *)d_out, out_cap, out_n);
+    if (rc) return rc;
+    ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_CODE_END]);
+    return 0;
+}
+
+}  // extern "C"

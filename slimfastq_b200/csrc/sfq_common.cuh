@@ -88,6 +88,10 @@ struct SfqChunkMeta {
     uint32_t status_arg;    // record number / offending byte for the message
 };
 
+// Bytes reserved for a chunk's decoded headers (each followed by '\n').  The slack covers the few
+// cases where the reference prints a header field longer than it was (sign of a "%lld" value).
+#define SFQ_HDR_PLANE(m) ((uint64_t)(m)->hdr_bytes + 9ull * (m)->nrec + 64ull)
+
 // Output arena of one resident chunk: SFQ_NSTREAMS sub-ranges.
 struct SfqArena {
     uint64_t off[SFQ_NSTREAMS];    // byte offset of each stream's region in the arena buffer

@@ -29,7 +29,8 @@ struct SfqFileHeader {
     uint64_t nchunks;
     uint64_t chunk_bytes;
     uint64_t index_off;      // file offset of the blob-offset index
-};                           // 72 bytes
+    uint64_t out_size;       // bytes the container decodes to (sum of the blobs' out_len)
+};                           // 80 bytes
 struct SfqBlobHeader {
     uint32_t magic;
     uint32_t level;
@@ -46,11 +47,11 @@ struct SfqBlobHeader {
 #pragma pack(pop)
 
 static inline void sfq_file_header_init(SfqFileHeader *h, int level, uint64_t orig, uint64_t nchunks,
-                                        uint64_t chunk_bytes, uint64_t index_off) {
+                                        uint64_t chunk_bytes, uint64_t index_off, uint64_t out_size) {
     memcpy(h->stamp, SFQ_STAMP, 16);
     memcpy(h->kind, SFQ_KIND, 16);
     h->version = SFQ_INTERNAL_VERSION; h->level = (uint32_t)level; h->orig_size = orig;
-    h->nchunks = nchunks; h->chunk_bytes = chunk_bytes; h->index_off = index_off;
+    h->nchunks = nchunks; h->chunk_bytes = chunk_bytes; h->index_off = index_off; h->out_size = out_size;
 }
 static inline bool sfq_is_chunked_container(const uint8_t *p, size_t n) {
     return n >= sizeof(SfqFileHeader) && !memcmp(p, SFQ_STAMP, 16) && !memcmp(p + 16, SFQ_KIND, 16);

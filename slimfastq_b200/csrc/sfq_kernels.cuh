@@ -1,0 +1,368 @@
+// __global__ kernels for sm_100a.  Included once, by sfq_abi.cu.
+//
+//   scan   k_count_newlines / k_scan_tiles / k_fill_lines   HBM-bound: 16-byte vector loads,
+//          byte-compare SIMD (__vcmpeq4), warp-shuffle + shared-memory prefix sums
+//   plan   k_chunk_bounds / k_chunk_plan                    binary search + per-chunk framing facts
+//   code   k_encode / k_decode (role per blockIdx.y)        one adaptive-coder chain per thread
+//   pack   k_blob_sizes / k_pack                            prefix-sum of stream sizes, gather to container
+//   build  k_decode_usr / k_out_offsets / k_assemble        planes -> FASTQ text
+#pragma once
+#include <cuda_runtime.h>
+#include "sfq_streams.cuh"
+#include "sfq_plan.cuh"
+#include "sfq_container.h"
+
+#define SFQ_SCAN_THREADS 256
+#define SFQ_SCAN_ITERS   4
+#define SFQ_SCAN_TILE    (SFQ_SCAN_THREADS * SFQ_SCAN_ITERS * 16)     // 16 KiB of text per CTA
+
+// 16 bytes of text starting at `idx` (vectorised when wholly inside the buffer; the buffer base is
+// 16-byte aligned, checked by the host).  Bytes past n read as 0.
+__device__ __forceinline__ uint4 sfq_load16(const uint8_t *text, uint64_t idx, uint64_t n) {
+    if (idx + 16 <= n) return __ldg(reinterpret_cast<const uint4 *>(text + idx));
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 16; b++)
+        if (idx + b < n) w[b >> 2] |= (uint32_t)text[idx + b] << (8 * (b & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// per-byte 0x80 flags of the newline positions in a 32-bit word
+__device__ __forceinline__ uint32_t sfq_nl_flags(uint32_t w) { return __vcmpeq4(w, 0x0a0a0a0au) & 0x80808080u; }
+__device__ __forceinline__ uint32_t sfq_nl_count16(uint4 v) {
+    return __popc(sfq_nl_flags(v.x)) + __popc(sfq_nl_flags(v.y)) + __popc(sfq_nl_flags(v.z)) + __popc(sfq_nl_flags(v.w));
+}
+
+// Pass 1: newlines per 16 KiB tile.
+__global__ void __launch_bounds__(SFQ_SCAN_THREADS)
+k_count_newlines(const uint8_t *__restrict__ text, uint64_t n, uint32_t *__restrict__ tile_counts) {
+    const uint64_t base = (uint64_t)blockIdx.x * SFQ_SCAN_TILE;
+    uint32_t c = 0;
+#pragma unroll
+    for (int it = 0; it < SFQ_SCAN_ITERS; it++) {
+        const uint64_t idx = base + ((uint64_t)it * SFQ_SCAN_THREADS + threadIdx.x) * 16;
+        if (idx < n) c += sfq_nl_count16(sfq_load16(text, idx, n));
+    }
+    __shared__ uint32_t wsum[SFQ_SCAN_THREADS / 32];
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SFQ_SCAN_THREADS / 32; w++) t += wsum[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// Exclusive prefix sum of the tile counts (single CTA; ntiles is ~6e5 for 10 GB).
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(const uint32_t *__restrict__ counts, uint64_t *__restrict__ prefix, uint64_t ntiles, uint64_t *total) {
+    __shared__ uint64_t part[1024];
+    const uint64_t per = (ntiles + 1023) / 1024;
+    const uint64_t lo = (uint64_t)threadIdx.x * per, hi = lo + per < ntiles ? lo + per : ntiles;
+    uint64_t s = 0;
+    for (uint64_t i = lo; i < hi; i++) s += counts[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (int i = 0; i < 1024; i++) { uint64_t t = part[i]; part[i] = run; run += t; }
+        *total = run;
+    }
+    __syncthreads();
+    uint64_t run = part[threadIdx.x];
+    for (uint64_t i = lo; i < hi; i++) { prefix[i] = run; run += counts[i]; }
+}
+
+// Pass 2: line_start[k+1] = offset after the k-th newline; line_start[0] = 0.
+__global__ void __launch_bounds__(SFQ_SCAN_THREADS)
+k_fill_lines(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__restrict__ tile_prefix,
+             uint64_t *__restrict__ line_start) {
+    const uint64_t base = (uint64_t)blockIdx.x * SFQ_SCAN_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = SFQ_SCAN_THREADS / 32;
+    __shared__ uint32_t wtot[SFQ_SCAN_ITERS][NW];
+    uint4 v[SFQ_SCAN_ITERS];
+    uint32_t incl[SFQ_SCAN_ITERS], cnt[SFQ_SCAN_ITERS];
+#pragma unroll
+    for (int it = 0; it < SFQ_SCAN_ITERS; it++) {
+        const uint64_t idx = base + ((uint64_t)it * SFQ_SCAN_THREADS + threadIdx.x) * 16;
+        v[it] = idx < n ? sfq_load16(text, idx, n) : make_uint4(0, 0, 0, 0);
+        uint32_t c = sfq_nl_count16(v[it]);
+        cnt[it] = c;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, c, o); if (lane >= o) c += t; }
+        incl[it] = c;
+        if (lane == 31) wtot[it][warp] = c;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) line_start[0] = 0;
+    uint64_t run = tile_prefix[blockIdx.x];
+#pragma unroll
+    for (int it = 0; it < SFQ_SCAN_ITERS; it++) {
+        uint32_t before = 0, all = 0;
+        for (int w = 0; w < NW; w++) { uint32_t t = wtot[it][w]; if (w < warp) before += t; all += t; }
+        uint64_t rank = run + before + (incl[it] - cnt[it]);
+        const uint64_t idx = base + ((uint64_t)it * SFQ_SCAN_THREADS + threadIdx.x) * 16;
+        const uint32_t w4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t m = sfq_nl_flags(w4[k]);
+            while (m) {
+                const int b = (__ffs(m) - 1) >> 3;
+                line_start[++rank] = idx + 4 * k + b + 1;
+                m &= m - 1;
+            }
+        }
+        run += all;
+    }
+}
+
+// rec_begin[c] = first record starting at or after c * chunk_bytes (c in [0, nslots]).
+__global__ void k_chunk_bounds(const uint64_t *__restrict__ ls, uint64_t nrec_total, uint64_t chunk_bytes,
+                               uint64_t nslots, uint64_t *__restrict__ rec_begin) {
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nslots) return;
+    rec_begin[c] = c == nslots ? nrec_total : sfq_first_record_at(ls, nrec_total, c * chunk_bytes);
+}
+__global__ void k_chunk_plan(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls,
+                             const uint64_t *__restrict__ r0, const uint64_t *__restrict__ r1,
+                             SfqChunkMeta *metas, uint32_t nchunks) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    sfq_plan_chunk(text, ls, r0[c], r1[c], &metas[c]);
+}
+
+// Per-wave workspace of the coders: chunk w of the wave owns slice w of every table.
+struct SfqWorkspace {
+    uint8_t  *gtab;  uint64_t gtab_stride;  uint32_t hbits;     // base-context tables
+    uint32_t *qtab;  uint64_t qtab_words;                        // quality-context tables
+    uint32_t *pw;                                                // 256-symbol model pools
+};
+
+// One thread = one chunk-stream.  blockIdx.y: 0 = gen (+gen.Ns/Nn), 1 = qlt, 2 = rec (+rec.x, usr.*).
+__global__ void __launch_bounds__(32)
+k_encode(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas,
+         SfqArena *arenas, uint8_t *arena_buf, SfqWorkspace ws, int level, uint32_t nchunks) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    SfqChunkMeta *m = &metas[c];
+    if (m->status != SFQ_OK && m->status != SFQ_E_CAP && m->status != SFQ_E_TABLE) return;
+    uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
+    switch (blockIdx.y) {
+    case 0: sfq_gen_encode_chunk(text, ls, m, level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw, arena_buf, &arenas[c]); break;
+    case 1: sfq_qlt_encode_chunk(text, ls, m, level, ws.qtab + (size_t)c * ws.qtab_words, pw, arena_buf, &arenas[c]); break;
+    default: sfq_rec_encode_chunk(text, ls, m, pw, arena_buf, &arenas[c]); break;
+    }
+}
+
+// Blob sizes of a wave and their exclusive prefix from *cursor (single CTA).
+__global__ void __launch_bounds__(1024)
+k_blob_offsets(const SfqChunkMeta *__restrict__ metas, const SfqArena *__restrict__ arenas,
+               const uint64_t *__restrict__ ls, uint32_t nchunks, uint64_t *blob_off, uint64_t *cursor) {
+    __shared__ uint64_t part[1024];
+    const uint32_t per = (nchunks + 1023) / 1024;
+    const uint32_t lo = threadIdx.x * per, hi = lo + per < nchunks ? lo + per : nchunks;
+    uint64_t s = 0;
+    for (uint32_t c = lo; c < hi; c++) {
+        uint64_t b = sizeof(SfqBlobHeader) + (ls[metas[c].line0 + 1] - ls[metas[c].line0] - 2);
+        for (int k = 0; k < SFQ_NSTREAMS; k++) b += arenas[c].size[k];
+        blob_off[c] = b;
+        s += b;
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = *cursor;
+        for (int i = 0; i < 1024; i++) { uint64_t t = part[i]; part[i] = run; run += t; }
+        *cursor = run;
+    }
+    __syncthreads();
+    uint64_t run = part[threadIdx.x];
+    for (uint32_t c = lo; c < hi; c++) { uint64_t b = blob_off[c]; blob_off[c] = run; run += b; }
+}
+
+// One CTA per chunk: header + rec.first + streams -> container.  Sets *overflow if out is too small.
+__global__ void __launch_bounds__(256)
+k_pack(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, const SfqChunkMeta *__restrict__ metas,
+       const SfqArena *__restrict__ arenas, const uint8_t *__restrict__ arena_buf,
+       const uint64_t *__restrict__ blob_off, int level, uint8_t *out, uint64_t out_cap, uint32_t *overflow) {
+    const uint32_t c = blockIdx.x;
+    const SfqChunkMeta &m = metas[c];
+    const SfqArena &a = arenas[c];
+    __shared__ SfqBlobHeader h;
+    const uint32_t rfl = (uint32_t)(ls[m.line0 + 1] - ls[m.line0] - 2);
+    if (threadIdx.x == 0) {
+        h.magic = SFQ_BLOB_MAGIC; h.level = (uint32_t)level; h.text_len = m.text_len; h.out_len = m.out_len;
+        h.nrec = m.nrec; h.nbases = m.nbases; h.nquals = m.nquals; h.hdr_bytes = m.hdr_bytes; h.llen = m.llen;
+        h.solid = m.solid; h.two_id = m.two_id; h.n_byte = m.n_byte; h.pad = 0; h.extra_hi = m.extra_hi;
+        h.rec_first_len = rfl;
+        for (int k = 0; k < SFQ_NSTREAMS; k++) h.ssize[k] = a.size[k];
+    }
+    __syncthreads();
+    uint64_t total = sizeof(SfqBlobHeader) + rfl;
+    for (int k = 0; k < SFQ_NSTREAMS; k++) total += a.size[k];
+    uint64_t o = blob_off[c];
+    if (o + total > out_cap) { if (threadIdx.x == 0) atomicExch(overflow, 1u); return; }
+    const uint8_t *hp = reinterpret_cast<const uint8_t *>(&h);
+    for (uint32_t i = threadIdx.x; i < sizeof(SfqBlobHeader); i += blockDim.x) out[o + i] = hp[i];
+    o += sizeof(SfqBlobHeader);
+    const uint8_t *rf = text + ls[m.line0] + 1;
+    for (uint32_t i = threadIdx.x; i < rfl; i += blockDim.x) out[o + i] = rf[i];
+    o += rfl;
+    for (int k = 0; k < SFQ_NSTREAMS; k++) {
+        const uint8_t *src = arena_buf + a.off[k];
+        const uint32_t sz = a.size[k];
+        for (uint32_t i = threadIdx.x; i < sz; i += blockDim.x) out[o + i] = src[i];
+        o += sz;
+    }
+}
+
+// ---------------------------------------------------------------------------- decode side
+// What the decoders need to know about a chunk of the wave (built by the host from blob headers).
+struct SfqDecChunk {
+    uint64_t soff[SFQ_NSTREAMS];    // absolute offsets of the streams in the container buffer
+    uint32_t ssize[SFQ_NSTREAMS];
+    uint64_t rec_first_off;
+    uint32_t rec_first_len;
+    int32_t  level;
+    uint64_t rec_base;              // first slot of the chunk in the per-record tables
+    uint64_t base_plane, qual_plane, hdr_plane;   // plane offsets of the chunk
+};
+struct SfqRecTables {
+    uint32_t *llen, *qlen, *hlen;
+    uint8_t *pfg, *pfq;
+    uint64_t *boff, *qoff, *hoff, *ooff;
+};
+
+__global__ void __launch_bounds__(32)
+k_decode_usr(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
+             SfqWorkspace ws, SfqRecTables t, uint32_t nchunks) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const SfqDecChunk &d = dc[c];
+    SfqChunkMeta *m = &metas[c];
+    uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
+    sfq_usr_decode_chunk(in, d.ssize, d.soff, m, pw, t.llen + d.rec_base, t.qlen + d.rec_base,
+                         t.pfg + d.rec_base, t.pfq + d.rec_base);
+    uint64_t b = d.base_plane, q = d.qual_plane;
+    for (uint32_t r = 0; r < m->nrec; r++) {
+        t.boff[d.rec_base + r] = b; t.qoff[d.rec_base + r] = q;
+        b += t.llen[d.rec_base + r]; q += t.qlen[d.rec_base + r];
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
+         SfqWorkspace ws, SfqRecTables t, uint8_t *bases, uint8_t *quals, uint8_t *hdrs, uint32_t nchunks) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const SfqDecChunk &d = dc[c];
+    SfqChunkMeta *m = &metas[c];
+    if (m->status != SFQ_OK) return;
+    uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
+    switch (blockIdx.y) {
+    case 0: sfq_gen_decode_chunk(in, d.ssize, d.soff, m, d.level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw,
+                                 t.llen + d.rec_base, t.boff + d.rec_base, bases); break;
+    case 1: sfq_qlt_decode_chunk(in, d.ssize, d.soff, m, d.level, ws.qtab + (size_t)c * ws.qtab_words, pw,
+                                 t.qlen + d.rec_base, t.qoff + d.rec_base, quals); break;
+    default: {
+        sfq_rec_decode_chunk(in, d.ssize, d.soff, m, pw, in + d.rec_first_off, d.rec_first_len,
+                             hdrs + d.hdr_plane, SFQ_HDR_PLANE(m),
+                             t.hlen + d.rec_base, t.hoff + d.rec_base);
+        for (uint32_t r = 0; r < m->nrec; r++) t.hoff[d.rec_base + r] += d.hdr_plane;
+    } break;
+    }
+}
+
+// Output layout (UsrLoad::save line layout, usrs.cpp:512-529), from the decoded lengths: bytes per
+// chunk, exclusive prefix over all chunks of the container, then the offset of every record.
+__device__ __forceinline__ uint64_t sfq_rec_out_len(const SfqChunkMeta &m, const SfqRecTables &t, uint64_t k) {
+    const uint32_t s = m.solid ? 1 : 0;
+    return 1ull + t.hlen[k] + 1 + s + t.llen[k] + 1 + 1 + (m.two_id ? t.hlen[k] : 0) + 1 + s + t.qlen[k] + 1;
+}
+__global__ void __launch_bounds__(32)
+k_out_sizes(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ metas, SfqRecTables t,
+            uint64_t *chunk_out, uint32_t nchunks) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    uint64_t o = 0;
+    if (metas[c].status == SFQ_OK)
+        for (uint32_t r = 0; r < metas[c].nrec; r++) o += sfq_rec_out_len(metas[c], t, dc[c].rec_base + r);
+    chunk_out[c] = o;
+}
+__global__ void __launch_bounds__(1024)
+k_scan_u64(uint64_t *v, uint32_t n, uint64_t *total) {        // in-place exclusive scan, single CTA
+    __shared__ uint64_t part[1024];
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    uint64_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += v[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (int i = 0; i < 1024; i++) { uint64_t x = part[i]; part[i] = run; run += x; }
+        *total = run;
+    }
+    __syncthreads();
+    uint64_t run = part[threadIdx.x];
+    for (uint32_t i = lo; i < hi; i++) { uint64_t x = v[i]; v[i] = run; run += x; }
+}
+__global__ void __launch_bounds__(32)
+k_out_offsets(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ metas, SfqRecTables t,
+              const uint64_t *__restrict__ chunk_out_off, uint32_t nchunks) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks || metas[c].status != SFQ_OK) return;
+    uint64_t o = chunk_out_off[c];
+    for (uint32_t r = 0; r < metas[c].nrec; r++) {
+        const uint64_t k = dc[c].rec_base + r;
+        t.ooff[k] = o;
+        o += sfq_rec_out_len(metas[c], t, k);
+    }
+}
+
+// One warp per record: planes -> FASTQ text, applying the "quality '!' means N" rule of
+// GenLoad::normalize_gen (gens.cpp:200-213) with the flags left by sfq_gen_decode_chunk.
+__global__ void __launch_bounds__(256)
+k_assemble(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ metas, SfqRecTables t,
+           const uint32_t *__restrict__ rec_chunk, const uint8_t *__restrict__ bases,
+           const uint8_t *__restrict__ quals, const uint8_t *__restrict__ hdrs, uint8_t *out, uint64_t nrec) {
+    const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (k >= nrec) return;
+    const SfqChunkMeta &m = metas[rec_chunk[k]];
+    if (m.status != SFQ_OK) return;
+    const uint32_t hlen = t.hlen[k], llen = t.llen[k], qlen = t.qlen[k];
+    const uint8_t *h = hdrs + t.hoff[k], *b = bases + t.boff[k], *q = quals + t.qoff[k];
+    const uint8_t nbyte = m.n_byte ? m.n_byte : (uint8_t)'N';
+    uint8_t *o = out + t.ooff[k];
+    if (lane == 0) o[0] = '@';
+    for (uint32_t i = lane; i < hlen; i += 32) o[1 + i] = h[i];
+    o += 1 + hlen;
+    if (lane == 0) o[0] = '\n';
+    o += 1;
+    if (m.solid) { if (lane == 0) o[0] = t.pfg[k]; o += 1; }
+    for (uint32_t i = lane; i < llen; i += 32) {
+        uint8_t c = b[i];
+        const uint8_t qc = i < qlen ? q[i] : (uint8_t)40;
+        if (c & 0x80) c &= 0x7f; else if (qc == '!') c = nbyte;
+        o[i] = c;
+    }
+    o += llen;
+    if (lane == 0) { o[0] = '\n'; o[1] = '+'; }
+    o += 2;
+    if (m.two_id) { for (uint32_t i = lane; i < hlen; i += 32) o[i] = h[i]; o += hlen; }
+    if (lane == 0) o[0] = '\n';
+    o += 1;
+    if (m.solid) { if (lane == 0) o[0] = t.pfq[k]; o += 1; }
+    for (uint32_t i = lane; i < qlen; i += 32) o[i] = q[i];
+    if (lane == 0) o[qlen] = '\n';
+}
+
+// Blob headers of a device-resident container -> contiguous array (for the host to plan decode).
+__global__ void k_gather_blob_headers(const uint8_t *__restrict__ in, const uint64_t *__restrict__ blob_off,
+                                      SfqBlobHeader *hdrs, uint64_t nchunks, uint64_t in_size) {
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    uint8_t *d = reinterpret_cast<uint8_t *>(&hdrs[c]);
+    const uint64_t off = blob_off[c];
+    for (uint32_t i = 0; i < sizeof(SfqBlobHeader); i++) d[i] = off + i < in_size ? in[off + i] : 0;
+}

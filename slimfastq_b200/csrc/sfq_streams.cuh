@@ -454,8 +454,8 @@ SFQ_HD uint32_t sfq_fmt_u64(uint8_t *b, uint64_t v, uint32_t base, bool upper, b
 }
 
 // Decodes all headers of a chunk into `hdrs` (each followed by '\n'; record r at hoff_tab[r],
-// length hlen_tab[r]).  `hcap` = bytes available in the plane; the caller gives meta->hdr_bytes +
-// nrec + 64 so the conservative room checks below never reject a valid container.
+// length hlen_tab[r]).  `hcap` = bytes available in the plane; the caller gives SFQ_HDR_PLANE(meta)
+// so the conservative room checks below never reject a valid container.
 SFQ_HDN void sfq_rec_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
                                   SfqChunkMeta *meta, uint32_t *pwpool, const uint8_t *rec_first,
                                   uint32_t rec_first_len, uint8_t *hdrs, uint64_t hcap,
@@ -550,6 +550,7 @@ SFQ_HDN void sfq_rec_decode_chunk(const uint8_t *in, const uint32_t *ssize, cons
         prev = buf;
         pos += (uint64_t)n + 1;
     }
-    if (status == SFQ_OK && pos != (uint64_t)meta->hdr_bytes + meta->nrec) status = SFQ_E_CORRUPT;
+    // pos may differ from hdr_bytes + nrec only for headers the reference itself does not reproduce
+    // (e.g. a decimal field >= 2^63 comes back through "%lld" with a sign, recs.cpp:436-456)
     if (status != SFQ_OK && meta->status == SFQ_OK) meta->status = status;
 }

@@ -1,0 +1,80 @@
+"""-m gpu: the CUDA path, called through the C ABI, versus the oracle / the reference binary."""
+import os
+
+import pytest
+
+from conftest import sample_files
+from helpers import check_container_against_oracle
+from slimfastq_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+SAMPLES = sample_files()
+
+
+@pytest.mark.parametrize("path", SAMPLES, ids=[os.path.basename(p) for p in SAMPLES])
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+def test_reference_samples_bit_exact_and_roundtrip(codec, oracle, path, level):
+    data = open(path, "rb").read()
+    for chunk_bytes in (1 << 40, 1 << 17):          # whole file as one chunk, and 128 KiB chunks
+        blob = codec.compress(data, level, chunk_bytes)
+        check_container_against_oracle(oracle, data, blob, level)
+        back = codec.decompress(blob)
+        assert back == oracle.decode(oracle.encode(data, level)) or chunk_bytes != 1 << 40
+        if oracle.have_ref() and chunk_bytes == 1 << 40:
+            assert back == oracle.ref_roundtrip(data, level)       # what the reference itself prints
+        else:
+            assert back == data
+
+
+@pytest.mark.parametrize("name", sorted(synth.edge_cases()))
+@pytest.mark.parametrize("level", [1, 3, 4])
+def test_edge_cases_bit_exact(codec, oracle, name, level):
+    data = synth.edge_cases()[name]
+    blob = codec.compress(data, level, 1 << 40)
+    check_container_against_oracle(oracle, data, blob, level)
+    assert codec.decompress(blob) == oracle.decode(oracle.encode(data, level))
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+def test_illumina_chunks_bit_exact(codec, oracle, level):
+    data = synth.illumina(12000)                     # ~4.3 MB -> five 1 MiB chunks
+    blob = codec.compress(data, level, 1 << 20)
+    ct = check_container_against_oracle(oracle, data, blob, level)
+    assert len(ct.chunks) >= 4
+    assert codec.decompress(blob) == data
+
+
+def test_illumina_8bin_and_ont_bit_exact(codec, oracle):
+    for data in (synth.illumina(6000, bins8=True), synth.ont(120)):
+        for level in (3, 4):
+            blob = codec.compress(data, level, 1 << 20)
+            check_container_against_oracle(oracle, data, blob, level)
+            assert codec.decompress(blob) == data
+
+
+def test_waves_do_not_change_the_bytes(oracle):
+    import slimfastq_b200 as S
+
+    data = synth.illumina(9000)
+    a = S.Codec(max_resident=2)
+    b = S.Codec()
+    try:
+        blob_a = a.compress(data, 3, 1 << 19)
+        assert a.stats()["waves"] > 1
+        assert blob_a == b.compress(data, 3, 1 << 19)
+        assert a.decompress(blob_a) == data
+    finally:
+        a.close(); b.close()
+
+
+def test_errors_are_croaks_not_crashes(codec):
+    import slimfastq_b200 as S
+
+    for bad in (b"hello\nworld\n", b"@r1\nACGT\n+\nIIII", b"@r1\nACGT\n-\nIIII\n", b"@r1\nACXT\n+\nIIII\n"):
+        with pytest.raises(S.SfqError):
+            codec.compress(bad, 3)
+    with pytest.raises(S.SfqError):
+        codec.decompress(b"whoami=slimfastq\nversion=6\n" + b"\0" * 200)
+    good = codec.compress(b"@r1\nACGT\n+\nIIII\n", 3)
+    assert codec.decompress(good) == b"@r1\nACGT\n+\nIIII\n"
