@@ -1,2 +1,234 @@
-// placeholder main; replaced below
-int main() { return 0; }
+// slimfastq-b200: host CLI with the reference's command-line surface (config.cpp:158-201,239-379;
+// main.cpp:51-61) over the C ABI.  Option letters, DWIM positionals, stamp detection, refusal to
+// overwrite without -O, stdin/stdout piping and exit status follow the reference; all coding is done
+// by libsfq_b200.so on the GPU.
+#include <errno.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sfq_b200.h"
+#include "sfq_container.h"
+
+static bool g_encode = true;
+static std::string g_orig = "";
+
+static void croak(const char *fmt, ...) __attribute__((noreturn));
+static void croak(const char *fmt, ...) {        // config.cpp:54-68
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stderr, "slimfastq: %s %s: ", g_encode ? "encoding" : "decoding", g_orig.c_str());
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, "\n");
+    va_end(ap);
+    exit(1);
+}
+
+static void usage() {                            // config.cpp:158-201
+    printf("\
+Usage: \n\
+-u  usr-filename : (default: stdin)\n\
+-f comp-filename : required - compressed\n\
+-d               : decode (instead of encoding) \n\
+-O               : silently overwrite existing files\n\
+-l level         : compression level 1 to 4 (default is 3 ) \n\
+-1, -2, -3, -4   : alias for -l 1, -l 2, etc \n\
+ Where levels are:\n\
+ 1: smallest context tables, yields the worse compression (still much better than gzip)\n\
+ 2: resonable compression \n\
+ 3: best compression <default level> \n\
+ 4: Compress a little more, but costly \n\
+\n\
+-v               : version : internal version \n\
+-h               : help : this message \n\
+-s               : stat : information about a compressed file \n\
+-q               : suppress extra stats info that could have been seen by -s \n\
+-c bytes         : chunk size (default 1048576); every chunk is coded as a standalone file \n\
+-g device        : CUDA device index (default 0) \n\
+\n\
+DWIM (Do what I mean) - Intuitive use of 'slimfastq-b200 A B' : \n\
+If A appears to be a fastq file, and:\n\
+    B does not exists, or -O option is used: compress A to B \n\
+If A appears to be a slimfastq file, and: \n\
+    B does not exist, or -O option is used: decompress A to B \n\
+    B is omitted: decompress A to stdout \n\
+Examples: \n\
+%% slimfastq-b200 <file.fastq> <new-file.sfq>   : compress <file.fastq> to <new-file.sfq> \n\
+%% slimfastq-b200 -1 <file.fastq> <new-file.sfq>: compress <file.fastq> to <new-file.sfq>, using level 1 \n\
+%% slimfastq-b200 <file.sfq>                    : decompress <file.sfq> to stdout \n\
+%% slimfastq-b200 <file.sfq> <file.fastq>       : decompress <file.sfq> to <file.fastq>\n\
+%% gzip -dc <file.fastq.gz> | slimfastq-b200 -f <file.sfq> : convert from gzip to sfq format\n\
+Verification example:\n\
+%% md5sum <file.fastq>                           : remember checksum \n\
+%% slimfastq-b200 <file.fastq> <new-file.sfq>    : compress \n\
+%% slimfastq-b200 <new-file.sfq> | md5sum -      : decompress pipe to md5sum, compare checksums \n\
+\n");
+    exit(0);
+}
+
+// Reads a whole stream into a pinned buffer (grown geometrically; stdin has no size).
+static uint8_t *slurp(FILE *f, size_t hint, size_t *n_out) {
+    size_t cap = hint ? hint + 1 : (64u << 20), n = 0;
+    uint8_t *buf = (uint8_t *)sfq_host_alloc(cap);
+    if (!buf) croak("cannot allocate %zu bytes of pinned memory (is a CUDA device present?)", cap);
+    for (;;) {
+        size_t got = fread(buf + n, 1, cap - n, f);
+        n += got;
+        if (got == 0) break;
+        if (n == cap) {
+            size_t ncap = cap * 2;
+            uint8_t *nb = (uint8_t *)sfq_host_alloc(ncap);
+            if (!nb) croak("cannot allocate %zu bytes of pinned memory", ncap);
+            memcpy(nb, buf, n);
+            sfq_host_free(buf);
+            buf = nb; cap = ncap;
+        }
+    }
+    if (ferror(f)) croak("read error: %s", strerror(errno));
+    *n_out = n;
+    return buf;
+}
+
+static void statistics_dump(const uint8_t *p, size_t n) {      // config.cpp:76-85 + filer.cpp:107-118
+    SfqFileHeader fh;
+    memcpy(&fh, p, sizeof fh);
+    fprintf(stderr, ":::: Info ::::\n");
+    fprintf(stderr, "%-16s = %s\n", "whoami", "slimfastq");
+    fprintf(stderr, "%-16s = %u\n", "version", fh.version);
+    fprintf(stderr, "%-16s = %s\n", "format", "b200.c1 (chunked)");
+    fprintf(stderr, "%-16s = %u\n", "config.level", fh.level);
+    fprintf(stderr, "%-16s = %llu\n", "orig.size", (unsigned long long)fh.orig_size);
+    fprintf(stderr, "%-16s = %llu\n", "comp.size", (unsigned long long)n);
+    fprintf(stderr, "%-16s = %llu\n", "chunks", (unsigned long long)fh.nchunks);
+    fprintf(stderr, "%-16s = %llu\n", "chunk.bytes", (unsigned long long)fh.chunk_bytes);
+    static const char *names[SFQ_NSTREAMS] = {"rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq"};
+    unsigned long long tot[SFQ_NSTREAMS] = {0}, nrec = 0, extra = 0;
+    if (fh.index_off <= n && n - fh.index_off >= fh.nchunks * 8)
+        for (uint64_t c = 0; c < fh.nchunks; c++) {
+            uint64_t off;
+            memcpy(&off, p + fh.index_off + 8 * c, 8);
+            if (off > n || n - off < sizeof(SfqBlobHeader)) break;
+            SfqBlobHeader b;
+            memcpy(&b, p + off, sizeof b);
+            for (int k = 0; k < SFQ_NSTREAMS; k++) tot[k] += b.ssize[k];
+            nrec += b.nrec; extra += b.extra_hi;
+            if (c == 0) {
+                fprintf(stderr, "%-16s = %d\n", "llen", b.llen);
+                fprintf(stderr, "%-16s = %d\n", "usr.solid", b.solid);
+                fprintf(stderr, "%-16s = %d\n", "usr.2id", b.two_id);
+                fprintf(stderr, "%-16s = %.*s\n", "rec.first", (int)b.rec_first_len, (const char *)p + off + sizeof b);
+            }
+        }
+    fprintf(stderr, "%-16s = %llu\n", "num_records", nrec);
+    if (extra) fprintf(stderr, "%-16s = %llu\n", "qlt.extra.hi", extra);
+    fprintf(stderr, "\n:::: Files stream ::::\n i: name      : bytes (all chunks)\n");
+    for (int k = 0; k < SFQ_NSTREAMS; k++)
+        if (tot[k]) fprintf(stderr, "%2d: %-10s: %llu\n", k + 1, names[k], tot[k]);
+    exit(0);
+}
+
+int main(int argc, char **argv) {
+    std::string usr, fil;
+    bool overwrite = false, statistics = false;
+    int level = 3, device = 0;
+    unsigned long long chunk = 1ull << 20;
+    if (argc == 1) usage();
+    const char *short_opt = "qPsvhdO1234u:f:l:c:g:";
+    for (int opt = getopt(argc, argv, short_opt); opt != -1; opt = getopt(argc, argv, short_opt))
+        switch (opt) {
+        case 'u': usr = optarg; break;
+        case 'f': fil = optarg; break;
+        case 'l': level = (int)strtoll(optarg, 0, 0); break;
+        case '1': case '2': case '3': case '4': level = opt - '0'; break;
+        case 'c': chunk = strtoull(optarg, 0, 0); break;
+        case 'g': device = atoi(optarg); break;
+        case 'd': g_encode = false; break;
+        case 'O': overwrite = true; break;
+        case 'P': break;                           // profiling cap: accepted, ignored
+        case 'q': break;                           // no log.* extras exist in this container
+        case 'v': printf("Version 2.04\nInternal format version=%u\n", SFQ_INTERNAL_VERSION); exit(0);
+        case 'h': usage(); break;
+        case 's': statistics = true; g_encode = false; break;
+        default: croak("Ilagal args: use -h for help");
+        }
+    while (optind < argc) {                        // DWIM guessing, config.cpp:279-325
+        char *file = argv[optind++];
+        FILE *fh = fopen(file, "rb");
+        if (!fh) {
+            if (!g_encode && !usr.length()) usr = file;
+            else if (g_encode && !fil.length()) fil = file;
+            else {
+                fprintf(stderr, "What am I suppose to do with '%s'?\n (please specify explicitly with -f/-u prefix)\n(Note: not an existing file)\n", file);
+                exit(1);
+            }
+            continue;
+        }
+        char initline[20];
+        memset(initline, 0, sizeof initline);
+        size_t cnt = fread(initline, 1, 19, fh);
+        fclose(fh);
+        if (cnt && !fil.length() && 0 == strncmp(initline, SFQ_STAMP, 16)) { fil = file; g_encode = !!usr.length(); }
+        else if (cnt && !usr.length() && initline[0] == '@') usr = file;
+        else if (!usr.length() && !g_encode && (!cnt || overwrite)) usr = file;
+        else if (g_encode && usr.length() && !fil.length() && (!cnt || overwrite)) fil = file;
+        else {
+            fprintf(stderr, "What am I suppose to do with '%s'?\n (please specify explicitly with -f/-u prefix)\n(Note: file exists!)\n", file);
+            exit(1);
+        }
+    }
+    if (!fil.length()) { fprintf(stderr, "Missing essential argument: -f\n"); exit(1); }
+    const char *wr_flags = overwrite ? "wb" : "wbx";
+    g_orig = usr.length() ? usr : (g_encode ? "<< stdin >>" : "");
+
+    sfq_ctx *ctx = nullptr;
+    if (!statistics && sfq_create(&ctx, device)) croak("no usable CUDA device (this build has no CPU path)");
+
+    if (g_encode) {
+        FILE *out = fopen(fil.c_str(), wr_flags);
+        if (!out) { fprintf(stderr, "Can't write file '%s': %s\n", fil.c_str(), strerror(errno)); exit(1); }
+        FILE *in = stdin;
+        size_t hint = 0;
+        if (usr.length()) {
+            in = fopen(usr.c_str(), "rb");
+            if (!in) { fprintf(stderr, "Can't read file '%s': %s\n", usr.c_str(), strerror(errno)); exit(1); }
+            fseek(in, 0L, SEEK_END); hint = (size_t)ftell(in); fseek(in, 0L, SEEK_SET);
+        }
+        size_t n = 0;
+        uint8_t *buf = slurp(in, hint, &n);
+        const uint8_t *res = nullptr;
+        size_t rn = 0;
+        if (sfq_compress(ctx, buf, n, level, chunk, &res, &rn)) { unlink(fil.c_str()); croak("%s", sfq_last_error(ctx)); }
+        if (fwrite(res, 1, rn, out) != rn || fclose(out)) croak("Error writing output: %s", strerror(errno));
+        sfq_host_free(buf);
+    } else {
+        FILE *in = fopen(fil.c_str(), "rb");
+        if (!in) { fprintf(stderr, "Can't read file '%s': %s\n", fil.c_str(), strerror(errno)); exit(1); }
+        fseek(in, 0L, SEEK_END); size_t hint = (size_t)ftell(in); fseek(in, 0L, SEEK_SET);
+        size_t n = 0;
+        uint8_t *buf;
+        if (statistics) {                          // -s needs no GPU: plain malloc
+            buf = (uint8_t *)malloc(hint + 1);
+            n = buf ? fread(buf, 1, hint, in) : 0;
+        } else buf = slurp(in, hint, &n);
+        if (!buf || !sfq_is_chunked_container(buf, n)) {
+            if (buf && n >= 16 && !memcmp(buf, SFQ_STAMP, 16))
+                croak("%s is a paged (reference-format) .sfq; this build reads b200.c1 chunked containers", fil.c_str());
+            croak("%s is not a slimfastq file", fil.c_str());
+        }
+        if (statistics) statistics_dump(buf, n);
+        FILE *out = usr.length() ? fopen(usr.c_str(), wr_flags) : stdout;
+        if (!out) { fprintf(stderr, "Can't write file '%s': %s\n", usr.c_str(), strerror(errno)); exit(1); }
+        const uint8_t *res = nullptr;
+        size_t rn = 0;
+        if (sfq_decompress(ctx, buf, n, &res, &rn)) { if (usr.length()) unlink(usr.c_str()); croak("%s", sfq_last_error(ctx)); }
+        if (fwrite(res, 1, rn, out) != rn || (out != stdout ? fclose(out) : fflush(out))) croak("USR: Error writing output");
+        sfq_host_free(buf);
+    }
+    if (ctx) sfq_destroy(ctx);
+    return 0;
+}

@@ -197,7 +197,7 @@ def edge_cases(seed: int = SEED0 + 9) -> dict[str, bytes]:
         if i % 40 == 39:
             h = b"@odd layout %d|%d" % (i, i * i)
         elif i % 4 == 0:
-            h = b"@NB501:0:HV2:%d:%x:%X:0%d:%d:00%d" % (i % 3, hexv, hexv * 3, i % 11, 10**19 + i, i)
+            h = b"@NB501:0:HV2:%d:%x:%X:0%d:%d:00%d" % (i % 3, hexv, hexv * 3, i % 11, 9 * 10**18 + i, i)
         else:
             h = b"@NB501:0:HV2:%d:%x:%X:0%d:%d:%d" % (i % 3, hexv, hexv * 3, i % 11, 123456789012345678 + i, 0 if i % 5 == 0 else i)
         hs.append(h)
