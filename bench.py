@@ -346,7 +346,9 @@ def main():
             "phases_ms_per_step": {"c_scan": round(scan_ms / K_, 3), "c_code": round(code_ms_c / K_, 3), "d_code": round(code_ms_d / K_, 3),
                                    "c_total": round(t_c / K_, 3), "d_total": round(t_d / K_, 3), "c_clear": round(sc["ms_clear"], 3),
                                    "c_pack": round(sc["ms_pack"], 3), "d_clear": round(sd["ms_clear"], 3), "d_pack": round(sd["ms_pack"], 3),
-                                   "c_plan": round(sc["ms_plan"], 3)},
+                                   "c_plan": round(sc["ms_plan"], 3),
+                                   "c_gen": round(sc["ms_gen"], 3), "c_qlt": round(sc["ms_qlt"], 3), "c_rec": round(sc["ms_rec"], 3),
+                                   "d_gen": round(sd["ms_gen"], 3), "d_qlt": round(sd["ms_qlt"], 3), "d_rec": round(sd["ms_rec"], 3)},
         }
         if e2e:
             ev = 2 * tot_bytes * K_ / e2e_wall_max / 1e9

@@ -64,6 +64,8 @@ typedef struct sfq_stats {
     float ms_code;                /* k_encode / k_decode (sum over waves)                     */
     float ms_pack;                /* k_blob_offsets + k_pack  |  k_out_offsets + k_assemble   */
     uint64_t workspace_bytes;     /* model tables resident per wave                           */
+    float ms_gen, ms_qlt, ms_rec; /* the three coder kernels of a wave run concurrently; each   */
+                                  /* one's own duration, summed over waves                      */
 } sfq_stats;
 
 /* Create a context on CUDA device `device` (-1 = current).  Fails if no device is usable. */

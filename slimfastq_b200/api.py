@@ -13,7 +13,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsfq_b200.so")
+LIB_PATH = os.environ.get("SFQ_B200_LIB") or os.path.join(HERE, "libsfq_b200.so")    # override = A/B kernel variants
 DEFAULT_CHUNK = 1 << 20
 
 
@@ -30,7 +30,7 @@ class Stats(C.Structure):
         ("waves", C.c_uint32), ("resident_chunks", C.c_uint32), ("kernel_launches", C.c_uint32), ("retries", C.c_uint32),
         ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_scan", C.c_float),
         ("ms_plan", C.c_float), ("ms_clear", C.c_float), ("ms_code", C.c_float), ("ms_pack", C.c_float),
-        ("workspace_bytes", C.c_uint64),
+        ("workspace_bytes", C.c_uint64), ("ms_gen", C.c_float), ("ms_qlt", C.c_float), ("ms_rec", C.c_float),
     ]
 
     def as_dict(self) -> dict:

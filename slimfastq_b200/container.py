@@ -12,7 +12,7 @@ STAMP = b"whoami=slimfastq"
 KIND = b"\nformat=b200.c1\n"
 STREAM_NAMES = ["rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq"]
 FILE_HDR = struct.Struct("<16s16sIIQQQQQ")
-BLOB_HDR = struct.Struct("<IIQQIIIIiBBBBII10I")
+BLOB_HDR = struct.Struct("<IIQQIIIIiBBBBIIII10I")
 BLOB_MAGIC = 0x43514653
 
 
@@ -65,8 +65,8 @@ def parse(blob: bytes) -> Container:
         f = BLOB_HDR.unpack_from(blob, off)
         if f[0] != BLOB_MAGIC:
             raise ValueError("bad chunk magic")
-        (_, lvl, text_len, out_len, nrec, nb, nq, hb, llen, solid, two_id, n_byte, _pad, extra_hi, rfl) = f[:15]
-        ssize = f[15:]
+        (_, lvl, text_len, out_len, nrec, nb, nq, hb, llen, solid, two_id, n_byte, _pad, extra_hi, rfl, _qu, _gu) = f[:17]
+        ssize = f[17:]
         p = off + BLOB_HDR.size
         rec_first = blob[p:p + rfl]
         p += rfl

@@ -46,17 +46,21 @@ struct HostBuf {
 };
 
 enum { EV_START = 0, EV_H2D, EV_SCAN, EV_PLAN, EV_CODE_END, EV_D2H, EV_COUNT };
+enum { WEV = 10 };   // events per wave
 
 }  // namespace
 
 struct sfq_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};     // the qlt and rec coder kernels run beside gen
+    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     std::string err;
     sfq_stats st{};
     uint32_t max_resident = 0;
+    uint32_t lanes = 32;                    // chunk-streams per coder warp (SFQ_LANES)
     cudaEvent_t ev[EV_COUNT]{};
-    std::vector<cudaEvent_t> wave_ev;       // 4 per wave: clear start, code start, code end, pack end
+    std::vector<cudaEvent_t> wave_ev;       // 10 per wave: clear start, code start, code end, pack end, then start/end of gen, qlt, rec
     // device buffers (grow-only, reused across calls)
     DevBuf text, out, tiles, tile_prefix, lines, scalars, rec_begin, r0, r1, metas, arenas, arena_buf,
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
@@ -73,6 +77,16 @@ struct sfq_ctx {
 };
 
 namespace {
+
+// Large caller-facing buffers win over the cached coder workspace: on OOM drop it and retry.
+cudaError_t ensure_big(sfq_ctx *ctx, DevBuf &b, size_t bytes) {
+    cudaError_t e = b.ensure(bytes);
+    if (e != cudaErrorMemoryAllocation) return e;
+    cudaGetLastError();
+    ctx->gtab.release(); ctx->qtab.release(); ctx->pw.release(); ctx->arena_buf.release();
+    ctx->bases.release(); ctx->quals.release(); ctx->hdrs.release();
+    return b.ensure(bytes);
+}
 
 int fail(sfq_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -114,7 +128,7 @@ int status_to_error(sfq_ctx *ctx, const SfqChunkMeta &m, uint64_t chunk, uint64_
 uint32_t pick_resident(sfq_ctx *ctx, uint64_t nchunks, uint64_t per_chunk, uint64_t already_have) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    uint64_t budget = (uint64_t)((double)(free_b + already_have) * 0.90);
+    uint64_t budget = (uint64_t)((double)(free_b + already_have) * 0.85);
     uint64_t r = budget / per_chunk;
     if (r < 1) r = 1;
     if (ctx->max_resident && r > ctx->max_resident) r = ctx->max_resident;
@@ -130,7 +144,7 @@ uint32_t pick_resident(sfq_ctx *ctx, uint64_t nchunks, uint64_t per_chunk, uint6
 float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 int ensure_wave_events(sfq_ctx *ctx, size_t waves) {
-    while (ctx->wave_ev.size() < waves * 4) {
+    while (ctx->wave_ev.size() < waves * WEV) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         ctx->wave_ev.push_back(e);
@@ -215,7 +229,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     st.retries = 0;
     for (uint32_t grow = 0;; grow++) {
         const uint32_t hbits = sfq_gen_hbits(level, max_bases, grow);
-        const uint64_t gstride = sfq_gtable_bytes(level, hbits), qbytes = sfq_qtable_bytes(level), pbytes = sfq_pwpool_bytes();
+        const uint32_t cbits = sfq_q_cbits(level, grow);
+        const uint64_t gstride = sfq_gtable_bytes(level, hbits), qbytes = sfq_qhash_bytes(level, cbits), pbytes = sfq_pwpool_bytes();
         uint64_t max_arena = 0;
         for (uint32_t c = 0; c < nchunks; c++) {
             uint64_t end; SfqArena a;
@@ -241,20 +256,38 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         CK(cudaMemcpyAsync(d_scal, h_small, 24, cudaMemcpyHostToDevice, s));
         SfqWorkspace ws;
         ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
-        ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.pw = ctx->pw.as<uint32_t>();
+        ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.cbits = cbits; ws.pw = ctx->pw.as<uint32_t>();
         for (uint32_t w = 0; w < nwaves; w++) {
             const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
-            CK(cudaEventRecord(ctx->wave_ev[4 * w + 0], s));
+            CK(cudaEventRecord(ctx->wave_ev[WEV * w + 0], s));
             CK(cudaMemsetAsync(ctx->gtab.p, 0, nc * gstride, s));
             CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
             CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
-            CK(cudaEventRecord(ctx->wave_ev[4 * w + 1], s));
-            k_encode<<<dim3((nc + 31) / 32, 3), 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), ws, level, nc); LAUNCHED();
-            CK(cudaEventRecord(ctx->wave_ev[4 * w + 2], s));
+            CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
+            {   // fork: gen on the main stream, qlt and rec beside it; join before packing
+                const unsigned nb = (nc + ctx->lanes - 1) / ctx->lanes;
+                CK(cudaEventRecord(ctx->fork_ev, s));
+                CK(cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0));
+                CK(cudaStreamWaitEvent(ctx->side[1], ctx->fork_ev, 0));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
+                k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), ws, level, nc, ctx->lanes); LAUNCHED();
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], ctx->side[0]));
+                k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, ctx->side[0]>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), ws, level, nc, ctx->lanes); LAUNCHED();
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], ctx->side[0]));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], ctx->side[1]));
+                k_encode<2><<<nb, 32, 0, ctx->side[1]>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), ws, level, nc, ctx->lanes); LAUNCHED();
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], ctx->side[1]));
+                CK(cudaEventRecord(ctx->join_ev[0], ctx->side[0]));
+                CK(cudaEventRecord(ctx->join_ev[1], ctx->side[1]));
+                CK(cudaStreamWaitEvent(s, ctx->join_ev[0], 0));
+                CK(cudaStreamWaitEvent(s, ctx->join_ev[1], 0));
+            }
+            CK(cudaEventRecord(ctx->wave_ev[WEV * w + 2], s));
             k_blob_offsets<<<1, 1024, 0, s>>>(d_metas + c0, d_arenas + c0, d_ls, nc, d_blob_off + c0, d_scal + 1); LAUNCHED();
             k_pack<<<nc, 256, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), d_blob_off + c0, level,
                                       d_out, out_cap, reinterpret_cast<uint32_t *>(d_scal + 2)); LAUNCHED();
-            CK(cudaEventRecord(ctx->wave_ev[4 * w + 3], s));
+            CK(cudaEventRecord(ctx->wave_ev[WEV * w + 3], s));
         }
         CK(cudaMemcpyAsync(metas.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(arenas.data(), d_arenas, nchunks * sizeof(SfqArena), cudaMemcpyDeviceToHost, s));
@@ -267,11 +300,14 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             if (metas[c].status == SFQ_E_CAP || metas[c].status == SFQ_E_TABLE) again = true;
             else if (metas[c].status) return status_to_error(ctx, metas[c], c, r0[c]);
         }
-        st.ms_clear = st.ms_code = st.ms_pack = 0;
+        st.ms_clear = st.ms_code = st.ms_pack = st.ms_gen = st.ms_qlt = st.ms_rec = 0;
         for (uint32_t w = 0; w < nwaves; w++) {
-            st.ms_clear += ev_ms(ctx->wave_ev[4 * w], ctx->wave_ev[4 * w + 1]);
-            st.ms_code += ev_ms(ctx->wave_ev[4 * w + 1], ctx->wave_ev[4 * w + 2]);
-            st.ms_pack += ev_ms(ctx->wave_ev[4 * w + 2], ctx->wave_ev[4 * w + 3]);
+            st.ms_clear += ev_ms(ctx->wave_ev[WEV * w], ctx->wave_ev[WEV * w + 1]);
+            st.ms_code += ev_ms(ctx->wave_ev[WEV * w + 1], ctx->wave_ev[WEV * w + 2]);
+            st.ms_pack += ev_ms(ctx->wave_ev[WEV * w + 2], ctx->wave_ev[WEV * w + 3]);
+            st.ms_gen += ev_ms(ctx->wave_ev[WEV * w + 4], ctx->wave_ev[WEV * w + 5]);
+            st.ms_qlt += ev_ms(ctx->wave_ev[WEV * w + 6], ctx->wave_ev[WEV * w + 7]);
+            st.ms_rec += ev_ms(ctx->wave_ev[WEV * w + 8], ctx->wave_ev[WEV * w + 9]);
         }
         if (!again) { end_cursor = h_small[1]; if (*reinterpret_cast<uint32_t *>(&h_small[2])) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need more than %llu bytes)", (unsigned long long)out_cap); break; }
         if (grow >= 6) return fail(ctx, SFQ_ERR_CUDA, "stream arena still too small after 6 doublings");
@@ -342,7 +378,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
 
     CK(ctx->metas.ensure(nchunks * sizeof(SfqChunkMeta)));
     CK(ctx->dchunks.ensure(nchunks * sizeof(SfqDecChunk)));
-    CK(ctx->bases.ensure(nb + 16)); CK(ctx->quals.ensure(nq + 16)); CK(ctx->hdrs.ensure(nh + 16));
+    CK(ensure_big(ctx, ctx->bases, nb + 16)); CK(ensure_big(ctx, ctx->quals, nq + 16)); CK(ensure_big(ctx, ctx->hdrs, nh + 16));
     CK(ctx->rec_chunk.ensure(nrec * 4));
     CK(ctx->t_llen.ensure(nrec * 4)); CK(ctx->t_qlen.ensure(nrec * 4)); CK(ctx->t_hlen.ensure(nrec * 4));
     CK(ctx->t_pfg.ensure(nrec)); CK(ctx->t_pfq.ensure(nrec));
@@ -360,45 +396,85 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
     t.boff = ctx->t_boff.as<uint64_t>(); t.qoff = ctx->t_qoff.as<uint64_t>(); t.hoff = ctx->t_hoff.as<uint64_t>(); t.ooff = ctx->t_ooff.as<uint64_t>();
     CK(cudaEventRecord(ctx->ev[EV_PLAN], s));
 
-    // all chunks of a container share one table geometry (sized for the largest level / chunk)
-    const uint32_t hbits = sfq_gen_hbits(max_level, max_bases, 0);
-    const uint64_t gstride = std::max(sfq_gtable_bytes(max_level, hbits), sfq_gtable_bytes(1, 18));
-    const uint64_t qbytes = sfq_qtable_bytes(max_level), pbytes = sfq_pwpool_bytes();
-    const uint32_t R = pick_resident(ctx, nchunks, gstride + qbytes + pbytes + 4096, ctx->gtab.cap + ctx->qtab.cap + ctx->pw.cap);
-    CK(ctx->gtab.ensure(R * gstride)); CK(ctx->qtab.ensure(R * qbytes)); CK(ctx->pw.ensure(R * pbytes));
-    const uint32_t nwaves = (nchunks + R - 1) / R;
-    if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
-    st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * (gstride + qbytes + pbytes);
-    SfqWorkspace ws;
-    ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
-    ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.pw = ctx->pw.as<uint32_t>();
-    for (uint32_t w = 0; w < nwaves; w++) {
-        const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
-        CK(cudaEventRecord(ctx->wave_ev[4 * w + 0], s));
-        CK(cudaMemsetAsync(ctx->gtab.p, 0, nc * gstride, s));
-        CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
-        CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
-        CK(cudaEventRecord(ctx->wave_ev[4 * w + 1], s));
-        k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, nc); LAUNCHED();
-        k_decode<<<dim3((nc + 31) / 32, 3), 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, ctx->bases.as<uint8_t>(),
-                                                     ctx->quals.as<uint8_t>(), ctx->hdrs.as<uint8_t>(), nc); LAUNCHED();
-        CK(cudaEventRecord(ctx->wave_ev[4 * w + 2], s));
-        CK(cudaEventRecord(ctx->wave_ev[4 * w + 3], s));
+    // all chunks of a container share one table geometry, sized from the blobs' context counts; a table
+    // that still fills up (hint missing or wrong) reruns the decode one size larger
+    uint64_t max_q = 0, max_g = 0;
+    bool have_hints = true;
+    for (uint32_t c = 0; c < nchunks; c++) {
+        max_q = std::max<uint64_t>(max_q, blobs[c].q_used); max_g = std::max<uint64_t>(max_g, blobs[c].g_used);
+        if (!blobs[c].g_used || (!blobs[c].q_used && blobs[c].level > 1)) have_hints = false;
     }
+    uint32_t nwaves = 0;
     cudaEvent_t asm0 = ctx->ev[EV_SCAN];    // reused as "assemble start" on the decode timeline
-    CK(cudaEventRecord(asm0, s));
-    // output layout from the decoded lengths; equals the recorded out_len except where the reference
-    // itself prints a header differently from how it read it
-    uint64_t *d_cout = ctx->blob_off.as<uint64_t>();
-    k_out_sizes<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks); LAUNCHED();
-    k_scan_u64<<<1, 1024, 0, s>>>(d_cout, nchunks, ctx->scalars.as<uint64_t>()); LAUNCHED();
-    k_out_offsets<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks); LAUNCHED();
     uint64_t *h_total = ctx->h_small.as<uint64_t>();
-    CK(cudaMemcpyAsync(h_total, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(metas.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    for (uint32_t c = 0; c < nchunks; c++)
-        if (metas[c].status) return status_to_error(ctx, metas[c], c, dcs[c].rec_base);
+    st.retries = 0;
+    for (uint32_t grow = 0;; grow++) {
+        const uint32_t hbits = sfq_gen_hbits(max_level, have_hints ? max_g : max_bases, grow);
+        uint32_t cbits = have_hints ? std::max(10u, sfq_ceil_log2(2 * max_q + 16)) + grow : sfq_q_cbits(max_level, grow);
+        if (cbits > 16) cbits = 16;
+        const uint64_t gstride = std::max(sfq_gtable_bytes(max_level, hbits), sfq_gtable_bytes(1, 18));
+        const uint64_t qbytes = std::max(sfq_qhash_bytes(max_level, cbits), sfq_qhash_bytes(1, 12)), pbytes = sfq_pwpool_bytes();
+        const uint32_t R = pick_resident(ctx, nchunks, gstride + qbytes + pbytes + 4096, ctx->gtab.cap + ctx->qtab.cap + ctx->pw.cap);
+        CK(ctx->gtab.ensure(R * gstride)); CK(ctx->qtab.ensure(R * qbytes)); CK(ctx->pw.ensure(R * pbytes));
+        nwaves = (nchunks + R - 1) / R;
+        if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
+        st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * (gstride + qbytes + pbytes);
+        SfqWorkspace ws;
+        ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
+        ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.cbits = cbits; ws.pw = ctx->pw.as<uint32_t>();
+        for (uint32_t w = 0; w < nwaves; w++) {
+            const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
+            CK(cudaEventRecord(ctx->wave_ev[WEV * w + 0], s));
+            CK(cudaMemsetAsync(ctx->gtab.p, 0, nc * gstride, s));
+            CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
+            CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
+            CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
+            k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, nc); LAUNCHED();
+            {
+                const unsigned nb = (nc + ctx->lanes - 1) / ctx->lanes;
+                uint8_t *pb = ctx->bases.as<uint8_t>(), *pq = ctx->quals.as<uint8_t>(), *ph = ctx->hdrs.as<uint8_t>();
+                CK(cudaEventRecord(ctx->fork_ev, s));
+                CK(cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0));
+                CK(cudaStreamWaitEvent(ctx->side[1], ctx->fork_ev, 0));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
+                k_decode<0><<<nb, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], ctx->side[0]));
+                k_decode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, ctx->side[0]>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], ctx->side[0]));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], ctx->side[1]));
+                k_decode<2><<<nb, 32, 0, ctx->side[1]>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], ctx->side[1]));
+                CK(cudaEventRecord(ctx->join_ev[0], ctx->side[0]));
+                CK(cudaEventRecord(ctx->join_ev[1], ctx->side[1]));
+                CK(cudaStreamWaitEvent(s, ctx->join_ev[0], 0));
+                CK(cudaStreamWaitEvent(s, ctx->join_ev[1], 0));
+            }
+            CK(cudaEventRecord(ctx->wave_ev[WEV * w + 2], s));
+            CK(cudaEventRecord(ctx->wave_ev[WEV * w + 3], s));
+        }
+        CK(cudaEventRecord(asm0, s));
+        // output layout from the decoded lengths; equals the recorded out_len except where the reference
+        // itself prints a header differently from how it read it
+        uint64_t *d_cout = ctx->blob_off.as<uint64_t>();
+        k_out_sizes<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks); LAUNCHED();
+        k_scan_u64<<<1, 1024, 0, s>>>(d_cout, nchunks, ctx->scalars.as<uint64_t>()); LAUNCHED();
+        k_out_offsets<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks); LAUNCHED();
+        CK(cudaMemcpyAsync(h_total, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, s));
+        std::vector<SfqChunkMeta> got(nchunks);
+        CK(cudaMemcpyAsync(got.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        bool again = false;
+        for (uint32_t c = 0; c < nchunks; c++) {
+            if (got[c].status == SFQ_E_TABLE) again = true;
+            else if (got[c].status) return status_to_error(ctx, got[c], c, dcs[c].rec_base);
+        }
+        if (!again) break;
+        if (grow >= 8) return fail(ctx, SFQ_ERR_FORMAT, "context tables still too small after 8 doublings: corrupt container?");
+        st.retries++;
+        CK(cudaMemcpyAsync(d_metas, metas.data(), nchunks * sizeof(SfqChunkMeta), cudaMemcpyHostToDevice, s));
+    }
     no = *h_total;
     if (no > out_cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)no);
     k_assemble<<<(unsigned)((nrec * 32 + 255) / 256), 256, 0, s>>>(d_dcs, d_metas, t, ctx->rec_chunk.as<uint32_t>(), ctx->bases.as<uint8_t>(),
@@ -406,11 +482,14 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
     CK(cudaEventRecord(ctx->ev[EV_CODE_END], s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
-    st.ms_clear = st.ms_code = st.ms_pack = 0;
+    st.ms_clear = st.ms_code = st.ms_pack = st.ms_gen = st.ms_qlt = st.ms_rec = 0;
     for (uint32_t w = 0; w < nwaves; w++) {
-        st.ms_clear += ev_ms(ctx->wave_ev[4 * w], ctx->wave_ev[4 * w + 1]);
-        st.ms_code += ev_ms(ctx->wave_ev[4 * w + 1], ctx->wave_ev[4 * w + 2]);
-        st.ms_pack += ev_ms(ctx->wave_ev[4 * w + 2], ctx->wave_ev[4 * w + 3]);
+        st.ms_clear += ev_ms(ctx->wave_ev[WEV * w], ctx->wave_ev[WEV * w + 1]);
+        st.ms_code += ev_ms(ctx->wave_ev[WEV * w + 1], ctx->wave_ev[WEV * w + 2]);
+        st.ms_pack += ev_ms(ctx->wave_ev[WEV * w + 2], ctx->wave_ev[WEV * w + 3]);
+        st.ms_gen += ev_ms(ctx->wave_ev[WEV * w + 4], ctx->wave_ev[WEV * w + 5]);
+        st.ms_qlt += ev_ms(ctx->wave_ev[WEV * w + 6], ctx->wave_ev[WEV * w + 7]);
+        st.ms_rec += ev_ms(ctx->wave_ev[WEV * w + 8], ctx->wave_ev[WEV * w + 9]);
     }
     st.ms_pack += ev_ms(asm0, ctx->ev[EV_CODE_END]);
     st.ms_scan = 0;
@@ -461,7 +540,12 @@ int sfq_create(sfq_ctx **out, int device) {
     sfq_ctx *ctx = new sfq_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    for (int k = 0; k < 2; k++)
+        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     *out = ctx;
     return 0;
 }
@@ -473,6 +557,8 @@ void sfq_destroy(sfq_ctx *ctx) {
     ctx->release_all();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->wave_ev) cudaEventDestroy(e);
+    for (int k = 0; k < 2; k++) { if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]); if (ctx->join_ev[k]) cudaEventDestroy(ctx->join_ev[k]); }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -508,8 +594,8 @@ int sfq_compress(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64
     begin_call(ctx);
     if (n == 0) return fail(ctx, SFQ_ERR_FASTQ, "no records were found");
     const size_t cap = sfq_compress_bound(n, chunk_bytes);
-    CK(ctx->text.ensure(n + 16));
-    CK(ctx->out.ensure(cap));
+    CK(ensure_big(ctx, ctx->text, n + 16));
+    CK(ensure_big(ctx, ctx->out, cap));
     CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
     CK(cudaMemcpyAsync(ctx->text.p, fastq, n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
@@ -547,8 +633,8 @@ int sfq_decompress(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **o
     if (rc) return rc;
     uint64_t total = 4096;
     for (auto &b : blobs) total += b.out_len + 8ull * b.nrec;      // slack: see SFQ_HDR_PLANE
-    CK(ctx->text.ensure(n + 16));          // container bytes
-    CK(ctx->out.ensure(total + 16));
+    CK(ensure_big(ctx, ctx->text, n + 16));          // container bytes
+    CK(ensure_big(ctx, ctx->out, total + 16));
     CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
     CK(cudaMemcpyAsync(ctx->text.p, sfq, n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));

@@ -13,19 +13,78 @@
 //     untouched context is by definition (3,3,3,3) (base2_ranger.hpp:69-72).
 #pragma once
 #include "sfq_common.cuh"
+#include <string.h>
 
 #define SFQ_RC_TOP (1u << 24)
 
+// ------------------------------------------------------------------ 16-byte accesses / prefetch
+struct SfqU4 { uint32_t x, y, z, w; };
+SFQ_HD SfqU4 sfq_ld16(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    SfqU4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+    SfqU4 r; memcpy(&r, p, 16); return r;
+#endif
+}
+SFQ_HD void sfq_st16(uint32_t *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4 *>(p) = make_uint4(x, y, z, w);
+#else
+    p[0] = x; p[1] = y; p[2] = z; p[3] = w;
+#endif
+}
+// Bring the sector holding *p towards the SM ahead of its use (contexts of an encoder are known
+// from the input alone, so a run-ahead cursor can name them long before the coder needs them).
+SFQ_HD void sfq_prefetch(const void *p) {
+#if defined(__CUDA_ARCH__) && defined(SFQ_PREFETCH_L1)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif defined(__CUDA_ARCH__) && !defined(SFQ_NO_PREFETCH)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // ------------------------------------------------------------------ byte sink / source
+// Output bytes are gathered in a 64-bit register and stored 8 at a time (the arena sub-ranges are
+// 16-byte aligned and their capacities multiples of 8).
 struct SfqSink {
     uint8_t *p;
     uint32_t n, cap;
-    SFQ_HD void init(uint8_t *buf, uint32_t capacity) { p = buf; n = 0; cap = capacity; }
+    uint64_t acc;
+    bool mute;             // lane-cooperative coders: every lane counts, only one lane stores
+    SFQ_HD void init(uint8_t *buf, uint32_t capacity) { p = buf; n = 0; cap = capacity & ~7u; acc = 0; mute = false; }
     SFQ_HD void put(uint8_t c) {
-        if (n < cap) p[n] = c;
-        n++;                      // n > cap afterwards <=> overflow (reported as SFQ_E_CAP)
+        acc |= (uint64_t)c << (8 * (n & 7u));
+        n++;
+        if ((n & 7u) == 0) {
+            if (n <= cap && !mute) *reinterpret_cast<uint64_t *>(p + n - 8) = acc;
+            acc = 0;
+        }
+    }
+    SFQ_HD void flush() {                 // the last partial word; n > cap afterwards <=> overflow (SFQ_E_CAP)
+        const uint32_t base = n & ~7u;
+        for (uint32_t k = base; k < n; k++)
+            if (k < cap && !mute) p[k] = (uint8_t)(acc >> (8 * (k - base)));
     }
     SFQ_HD bool overflow() const { return n > cap; }
+};
+
+// Sequential reader over text bytes: one aligned 8-byte load per 8 symbols.
+struct SfqReader {
+    const uint8_t *p;
+    uint64_t word;
+    SFQ_HD void seek(const uint8_t *q) {
+        p = q;
+        word = *reinterpret_cast<const uint64_t *>((uintptr_t)q & ~(uintptr_t)7);
+    }
+    SFQ_HD uint8_t next() {
+        const uint32_t k = (uint32_t)((uintptr_t)p & 7u);
+        if (k == 0) word = *reinterpret_cast<const uint64_t *>(p);
+        p++;
+        return (uint8_t)(word >> (8 * k));
+    }
 };
 
 // ------------------------------------------------------------------ encoder  (coder.hpp:34-39,52-81)
@@ -34,7 +93,7 @@ struct SfqEnc {
     uint32_t range;
     SfqSink out;
     bool live;
-    SFQ_HD void reset() { live = false; low = 0; range = 0xFFFFFFFFu; out.p = nullptr; out.n = 0; out.cap = 0; }
+    SFQ_HD void reset() { live = false; low = 0; range = 0xFFFFFFFFu; out.p = nullptr; out.n = 0; out.cap = 0; out.acc = 0; out.mute = false; }
     SFQ_HD void start(uint8_t *buf, uint32_t cap) { low = 0; range = 0xFFFFFFFFu; out.init(buf, cap); live = true; }
     SFQ_HD void encode(uint32_t cum, uint32_t freq, uint32_t tot) {
         range /= tot;
@@ -50,6 +109,7 @@ struct SfqEnc {
     }
     SFQ_HD void finish() {
         for (int i = 0; i < 8; i++) { out.put((uint8_t)(low >> 56)); low <<= 8; }
+        out.flush();
     }
 };
 
@@ -59,10 +119,18 @@ struct SfqDec {
     uint32_t range;
     const uint8_t *p;
     uint32_t n, pos;
-    bool valid;
-    SFQ_HD uint8_t next() { return pos < n ? p[pos++] : (uint8_t)0; }   // EOF reads as 0, filer.hpp:94-97
+    uint64_t word;         // the aligned 8 bytes of the stream that hold byte `pos`
+    bool valid, have;
+    SFQ_HD uint8_t next() {                                             // EOF reads as 0, filer.hpp:94-97
+        if (pos >= n) return 0;
+        const uint8_t *q = p + pos;
+        const uint32_t k = (uint32_t)((uintptr_t)q & 7u);
+        if (k == 0 || !have) { word = *reinterpret_cast<const uint64_t *>(q - k); have = true; }
+        pos++;
+        return (uint8_t)(word >> (8 * k));
+    }
     SFQ_HD void start(const uint8_t *buf, uint32_t size) {
-        p = buf; n = size; pos = 0; low = 0; range = 0xFFFFFFFFu; code = 0;
+        p = buf; n = size; pos = 0; low = 0; range = 0xFFFFFFFFu; code = 0; word = 0; have = false;
         valid = (buf != nullptr && size != 0);
         for (int i = 0; i < 8; i++) code = (code << 8) | next();
     }
@@ -148,6 +216,10 @@ struct SfqGenTable {
             h = (h + 1u) & mask;
         }
     }
+    SFQ_HD void prefetch(uint32_t ctx) const {
+        if (dense) sfq_prefetch((const uint32_t *)slots + ctx);
+        else sfq_prefetch(slots + ((ctx * 2654435761u) >> (32 - hbits)));
+    }
     SFQ_HD void store(uint32_t slot, uint32_t ctx, uint32_t v) {
         if (dense) ((uint32_t *)slots)[slot] = v ^ 0x03030303u;
         else slots[slot] = ((uint64_t)(ctx + 1u) << 32) | v;
@@ -216,7 +288,8 @@ struct SfqAModel {
         return sym;
     }
 
-    SFQ_HD void put(SfqEnc &rc, uint32_t sym) {      // log64:98-112, power:93-106
+    // Reference-shaped paths over memory: any slot, normalisation, corrupt input.
+    SFQ_HD void put_slow(SfqEnc &rc, uint32_t sym) {      // log64:98-112, power:93-106
         if (iend() <= sym) set_iend(sym + 1u);
         uint32_t i = 0, sumf = 0, s;
         for (;; i++) {
@@ -228,10 +301,7 @@ struct SfqAModel {
         rc.encode(sumf + i, freq_of(s) + 1u, tot + NSYM);
         update(i, tot);
     }
-
-    SFQ_HD uint32_t get(SfqDec &rc) {                // log64:114-138, power:108-130
-        const uint32_t tot = total();
-        const uint32_t prob = rc.get_freq(tot + NSYM);
+    SFQ_HD uint32_t get_slow(SfqDec &rc, uint32_t prob, uint32_t tot) {   // log64:114-138, power:108-130
         uint32_t i = 0, sumf = 0, f = 0;
         for (; i < NSYM; i++) {
             f = freq_of(m[i]);
@@ -241,6 +311,71 @@ struct SfqAModel {
         if (iend() <= i) set_iend(i + 1u);
         rc.decode(sumf, f + 1u);
         return update(i, tot);
+    }
+
+    // Register paths: the symbol sits in slots 0..7 (one 32-byte sector) and no halving is due -
+    // nearly always, since hot symbols migrate to the front.  Everything happens in registers
+    // between one pair of 16-byte loads and one or two 16-byte stores.
+    SFQ_HD static void set_aux(uint32_t &s, uint32_t a) { s = (s & 0x00ffffffu) | (a << 24); }
+    SFQ_HD void finish_fast(uint32_t (&w)[8], uint32_t i, uint32_t f, uint32_t tot, uint32_t iend_old, uint32_t iend_new) {
+        f += STEP;
+        tot += STEP;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) if (k == i) w[k] = (w[k] & 0xffff0000u) | f;
+        set_aux(w[0], tot & 0xffu); set_aux(w[1], (tot >> 8) & 0xffu); set_aux(w[2], (tot >> 16) & 0xffu);
+        if (iend_new != iend_old) { set_aux(w[4], iend_new & 0xffu); set_aux(w[5], (iend_new >> 8) & 0xffu); }
+        if (i != 0) {
+            const uint32_t count = (aux_of(w[3]) + 1u) & 0xffu;
+            set_aux(w[3], count);
+            if ((count & 0xfu) == 0) {
+#pragma unroll
+                for (uint32_t k = 1; k < 8; k++)
+                    if (k == i) {
+                        const uint32_t a = w[k], b = w[k - 1];
+                        if (freq_of(a) > freq_of(b)) {
+                            w[k]     = pack(aux_of(a), sym_of(b, k - 1), k,     freq_of(b));
+                            w[k - 1] = pack(aux_of(b), sym_of(a, k),     k - 1, freq_of(a));
+                        }
+                    }
+            }
+        }
+        sfq_st16(m, w[0], w[1], w[2], w[3]);
+        if (i >= 4 || iend_new != iend_old) sfq_st16(m + 4, w[4], w[5], w[6], w[7]);
+    }
+
+    SFQ_HD void put(SfqEnc &rc, uint32_t sym) {
+        uint32_t w[8];
+        { const SfqU4 a = sfq_ld16(m), b = sfq_ld16(m + 4);
+          w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; }
+        uint32_t i = 8, sumf = 0, f = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++)
+            if (i == 8) { if (sym_of(w[k], k) == sym) { i = k; f = freq_of(w[k]); } else sumf += freq_of(w[k]); }
+        if (i == 8 || f > (uint32_t)(MAXF - STEP)) { put_slow(rc, sym); return; }
+        const uint32_t tot = aux_of(w[0]) | (aux_of(w[1]) << 8) | (aux_of(w[2]) << 16);
+        const uint32_t ie = aux_of(w[4]) | (aux_of(w[5]) << 8);
+        rc.encode(sumf + i, f + 1u, tot + NSYM);
+        finish_fast(w, i, f, tot, ie, ie <= sym ? sym + 1u : ie);
+    }
+
+    SFQ_HD uint32_t get(SfqDec &rc) {
+        uint32_t w[8];
+        { const SfqU4 a = sfq_ld16(m), b = sfq_ld16(m + 4);
+          w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; }
+        const uint32_t tot = aux_of(w[0]) | (aux_of(w[1]) << 8) | (aux_of(w[2]) << 16);
+        const uint32_t prob = rc.get_freq(tot + NSYM);
+        uint32_t i = 8, sumf = 0, f = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++)
+            if (i == 8) { const uint32_t fk = freq_of(w[k]); if (sumf + fk + 1u <= prob) sumf += fk + 1u; else { i = k; f = fk; } }
+        if (i == 8 || f > (uint32_t)(MAXF - STEP)) return get_slow(rc, prob, tot);
+        uint32_t sym = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) if (k == i) sym = sym_of(w[k], k);
+        const uint32_t ie = aux_of(w[4]) | (aux_of(w[5]) << 8);
+        rc.decode(sumf, f + 1u);
+        finish_fast(w, i, f, tot, ie, ie <= i ? i + 1u : ie);
+        return sym;
     }
 };
 typedef SfqAModel<64, 6, 65472, 20> SfqLog64;

@@ -84,6 +84,8 @@ struct SfqChunkMeta {
     uint8_t  n_byte;        // gen.N_byte (gens.cpp:100-105); 0 = key absent
     uint8_t  pad;
     uint32_t extra_hi;      // qlt.extra.hi (qlts.cpp:57-60)
+    uint32_t q_used;        // distinct quality contexts the chunk touched (sizes the decoder's table)
+    uint32_t g_used;        // distinct base contexts the chunk touched
     uint32_t status;        // SFQ_OK or first error
     uint32_t status_arg;    // record number / offending byte for the message
 };

@@ -42,8 +42,9 @@ struct SfqBlobHeader {
     uint8_t  solid, two_id, n_byte, pad;
     uint32_t extra_hi;       // qlt.extra.hi
     uint32_t rec_first_len;  // rec.first follows the header
+    uint32_t q_used, g_used; // distinct quality / base contexts touched (decoder table sizing hint; 0 = unknown)
     uint32_t ssize[SFQ_NSTREAMS];
-};                           // 96 bytes
+};                           // 104 bytes
 #pragma pack(pop)
 
 static inline void sfq_file_header_init(SfqFileHeader *h, int level, uint64_t orig, uint64_t nchunks,

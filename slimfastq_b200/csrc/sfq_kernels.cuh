@@ -9,6 +9,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "sfq_streams.cuh"
+#include "sfq_qlt_group.cuh"
 #include "sfq_plan.cuh"
 #include "sfq_container.h"
 
@@ -133,24 +134,35 @@ __global__ void k_chunk_plan(const uint8_t *__restrict__ text, const uint64_t *_
 // Per-wave workspace of the coders: chunk w of the wave owns slice w of every table.
 struct SfqWorkspace {
     uint8_t  *gtab;  uint64_t gtab_stride;  uint32_t hbits;     // base-context tables
-    uint32_t *qtab;  uint64_t qtab_words;                        // quality-context tables
+    uint32_t *qtab;  uint64_t qtab_words;   uint32_t cbits;     // quality-context tables (hashed)
     uint32_t *pw;                                                // 256-symbol model pools
 };
 
-// One thread = one chunk-stream.  blockIdx.y: 0 = gen (+gen.Ns/Nn), 1 = qlt, 2 = rec (+rec.x, usr.*).
+// One thread = one chunk-stream.  ROLE 0 = gen (+gen.Ns/Nn), 1 = qlt, 2 = rec (+rec.x, usr.*); the three
+// roles of a wave are separate kernels launched on three streams so they overlap on the device and
+// each gets its own register allocation.
+// `lanes` = chunk-streams per warp (<= 32): fewer lanes per warp means more warps, so one lane's
+// cache miss or slow path stalls fewer neighbours.
+template <int ROLE>
 __global__ void __launch_bounds__(32)
 k_encode(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas,
-         SfqArena *arenas, uint8_t *arena_buf, SfqWorkspace ws, int level, uint32_t nchunks) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nchunks) return;
-    SfqChunkMeta *m = &metas[c];
-    if (m->status != SFQ_OK && m->status != SFQ_E_CAP && m->status != SFQ_E_TABLE) return;
-    uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
-    switch (blockIdx.y) {
-    case 0: sfq_gen_encode_chunk(text, ls, m, level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw, arena_buf, &arenas[c]); break;
-    case 1: sfq_qlt_encode_chunk(text, ls, m, level, ws.qtab + (size_t)c * ws.qtab_words, pw, arena_buf, &arenas[c]); break;
-    default: sfq_rec_encode_chunk(text, ls, m, pw, arena_buf, &arenas[c]); break;
+         SfqArena *arenas, uint8_t *arena_buf, SfqWorkspace ws, int level, uint32_t nchunks, uint32_t lanes) {
+    if (ROLE == 1) {                       // lane-cooperative: SFQ_QG lanes per chunk
+        const uint32_t c = blockIdx.x * (32 / SFQ_QG) + threadIdx.x / SFQ_QG;
+        if (c >= nchunks || metas[c].status != SFQ_OK) return;
+        SfqQGroup g;
+        g.lane = threadIdx.x % SFQ_QG; g.gbase = threadIdx.x & ~(SFQ_QG - 1u); g.gmask = ((1u << SFQ_QG) - 1u) << g.gbase;
+        sfq_qlt_encode_group(text, ls, &metas[c], level, ws.qtab + (size_t)c * ws.qtab_words, ws.cbits,
+                             ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS, arena_buf, &arenas[c], g);
+        return;
     }
+    const uint32_t c = blockIdx.x * lanes + threadIdx.x;
+    if (threadIdx.x >= lanes || c >= nchunks) return;
+    SfqChunkMeta *m = &metas[c];
+    if (m->status != SFQ_OK) return;
+    uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
+    if (ROLE == 0) sfq_gen_encode_chunk(text, ls, m, level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw, arena_buf, &arenas[c]);
+    else sfq_rec_encode_chunk(text, ls, m, pw, arena_buf, &arenas[c]);
 }
 
 // Blob sizes of a wave and their exclusive prefix from *cursor (single CTA).
@@ -193,7 +205,7 @@ k_pack(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, const 
         h.magic = SFQ_BLOB_MAGIC; h.level = (uint32_t)level; h.text_len = m.text_len; h.out_len = m.out_len;
         h.nrec = m.nrec; h.nbases = m.nbases; h.nquals = m.nquals; h.hdr_bytes = m.hdr_bytes; h.llen = m.llen;
         h.solid = m.solid; h.two_id = m.two_id; h.n_byte = m.n_byte; h.pad = 0; h.extra_hi = m.extra_hi;
-        h.rec_first_len = rfl;
+        h.rec_first_len = rfl; h.q_used = m.q_used; h.g_used = m.g_used;
         for (int k = 0; k < SFQ_NSTREAMS; k++) h.ssize[k] = a.size[k];
     }
     __syncthreads();
@@ -249,26 +261,33 @@ k_decode_usr(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
     }
 }
 
+template <int ROLE>
 __global__ void __launch_bounds__(32)
 k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
-         SfqWorkspace ws, SfqRecTables t, uint8_t *bases, uint8_t *quals, uint8_t *hdrs, uint32_t nchunks) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nchunks) return;
+         SfqWorkspace ws, SfqRecTables t, uint8_t *bases, uint8_t *quals, uint8_t *hdrs, uint32_t nchunks, uint32_t lanes) {
+    if (ROLE == 1) {
+        const uint32_t c = blockIdx.x * (32 / SFQ_QG) + threadIdx.x / SFQ_QG;
+        if (c >= nchunks || metas[c].status != SFQ_OK) return;
+        const SfqDecChunk &d = dc[c];
+        SfqQGroup g;
+        g.lane = threadIdx.x % SFQ_QG; g.gbase = threadIdx.x & ~(SFQ_QG - 1u); g.gmask = ((1u << SFQ_QG) - 1u) << g.gbase;
+        sfq_qlt_decode_group(in, d.ssize, d.soff, &metas[c], d.level, ws.qtab + (size_t)c * ws.qtab_words, ws.cbits,
+                             ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS, t.qlen + d.rec_base, t.qoff + d.rec_base, quals, g);
+        return;
+    }
+    const uint32_t c = blockIdx.x * lanes + threadIdx.x;
+    if (threadIdx.x >= lanes || c >= nchunks) return;
     const SfqDecChunk &d = dc[c];
     SfqChunkMeta *m = &metas[c];
     if (m->status != SFQ_OK) return;
     uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
-    switch (blockIdx.y) {
-    case 0: sfq_gen_decode_chunk(in, d.ssize, d.soff, m, d.level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw,
-                                 t.llen + d.rec_base, t.boff + d.rec_base, bases); break;
-    case 1: sfq_qlt_decode_chunk(in, d.ssize, d.soff, m, d.level, ws.qtab + (size_t)c * ws.qtab_words, pw,
-                                 t.qlen + d.rec_base, t.qoff + d.rec_base, quals); break;
-    default: {
+    if (ROLE == 0)
+        sfq_gen_decode_chunk(in, d.ssize, d.soff, m, d.level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw,
+                             t.llen + d.rec_base, t.boff + d.rec_base, bases);
+    else {
         sfq_rec_decode_chunk(in, d.ssize, d.soff, m, pw, in + d.rec_first_off, d.rec_first_len,
-                             hdrs + d.hdr_plane, SFQ_HDR_PLANE(m),
-                             t.hlen + d.rec_base, t.hoff + d.rec_base);
+                             hdrs + d.hdr_plane, SFQ_HDR_PLANE(m), t.hlen + d.rec_base, t.hoff + d.rec_base);
         for (uint32_t r = 0; r < m->nrec; r++) t.hoff[d.rec_base + r] += d.hdr_plane;
-    } break;
     }
 }
 

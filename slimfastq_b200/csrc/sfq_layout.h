@@ -8,6 +8,15 @@ static inline uint32_t sfq_ceil_log2(uint64_t v) { uint32_t b = 0; while ((1ull 
 
 // Quality-context table: 4096 contexts at level 1, 65536 otherwise (qlts.cpp:34-39), 256 B each.
 static inline uint64_t sfq_qtable_bytes(int level) { return (level <= 1 ? 4096ull : 65536ull) * SFQ_L64_WORDS * 4; }
+// Hashed quality-context table of the lane-cooperative coder: a 1 MiB chunk touches ~4-8 k of the
+// 65536 contexts at level 3/4 and 10-27 k at level 2, so 2^14 / 2^15 entries to start with; a chunk
+// that fills its table is rerun with one more bit (16 bits = the direct table).
+static inline uint32_t sfq_q_cbits(int level, uint32_t grow) {
+    if (level <= 1) return 12;
+    uint32_t b = (level == 2 ? 15u : 14u) + grow;
+    return b > 16 ? 16 : b;
+}
+static inline uint64_t sfq_qhash_bytes(int level, uint32_t cbits) { return (level <= 1 ? 4096ull : (1ull << cbits)) * SFQ_L64_WORDS * 4; }
 // Base-context table.  Level 1: direct 2^18 x u32.  Levels 2-4: open-addressing hash of 64-bit
 // slots sized for a load factor <= 0.5 at `max_bases` insertions, never larger than the dense table
 // of the level would be.

@@ -23,7 +23,7 @@ SFQ_HDN void sfq_plan_chunk(const uint8_t *text, const uint64_t *ls, uint64_t r0
     m->nrec = (uint32_t)(r1 - r0);
     m->nbases = m->nquals = m->hdr_bytes = 0;
     m->llen = 0; m->solid = 0; m->two_id = 0; m->n_byte = 0; m->pad = 0;
-    m->extra_hi = 0; m->status = SFQ_OK; m->status_arg = 0;
+    m->extra_hi = 0; m->q_used = 0; m->g_used = 0; m->status = SFQ_OK; m->status_arg = 0;
     if (r1 == r0) return;
 
     uint32_t status = SFQ_OK, arg = 0;

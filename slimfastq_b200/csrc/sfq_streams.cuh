@@ -52,6 +52,41 @@ SFQ_HD uint32_t sfq_gen_mask(int level) {           // gens.hpp:43-53,74-82
 }
 
 // ============================================================================ gen: encode
+// Run-ahead cursor: an encoder's contexts depend on the input alone, so a second cursor walks the
+// bases SFQ_GEN_AHEAD symbols ahead of the coder and prefetches the table slot each one will need;
+// the coder then finds its slot in cache instead of paying an HBM round trip per base.
+#define SFQ_GEN_AHEAD 48u
+struct SfqGenCursor {
+    const uint8_t *text; const uint64_t *ls; uint64_t line0;
+    uint32_t nrec, solid, mask, r, i, llen, last;
+    SfqReader rd;
+    SFQ_HD void open_record() {
+        while (r < nrec) {
+            const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+            llen = v.llen; i = 0; last = 0x007616c7u;
+            if (llen) { rd.seek(v.seq); return; }
+            r++;
+        }
+        llen = 0;
+    }
+    SFQ_HD void init(const uint8_t *t, const uint64_t *l, const SfqChunkMeta *m, uint32_t msk) {
+        text = t; ls = l; line0 = m->line0; nrec = m->nrec; solid = m->solid; mask = msk; r = 0;
+        open_record();
+    }
+    // advance up to `count` bases, prefetching each one's slot
+    SFQ_HD void run(const SfqGenTable &tab, uint32_t count) {
+        while (count && r < nrec) {
+            uint32_t n = sfq_gencode(rd.next());
+            if (n > 3) n = 0;
+            last &= mask;
+            tab.prefetch(last);
+            last = (last << 2) | n;
+            count--;
+            if (++i == llen) { r++; open_record(); }
+        }
+    }
+};
+
 SFQ_HDN void sfq_gen_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *meta, int level,
                                   void *table_mem, uint32_t hbits, uint32_t *pwpool,
                                   uint8_t *arena, SfqArena *ar) {
@@ -67,13 +102,20 @@ SFQ_HDN void sfq_gen_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
     uint64_t genofs = 0, ns_index = 0, nn_index = 0;     // g_genofs_count, m_last.*  (gens.hpp:56-60)
     uint8_t n_byte = 0;
     uint32_t status = SFQ_OK, status_arg = 0;
+    SfqGenCursor ahead;
+    ahead.init(text, ls, meta, mask);
+    ahead.run(tab, SFQ_GEN_AHEAD);
 
     for (uint32_t r = 0; r < meta->nrec && status == SFQ_OK; r++) {
         const SfqRecView v = sfq_rec_view(text, ls, meta->line0, r, solid);
         uint32_t last = 0x007616c7u;                                           // gens.cpp:139
+        SfqReader rs, rq;
+        if (v.llen) rs.seek(v.seq);
+        if (v.qlen) rq.seek(v.qual);
         for (uint32_t i = 0; i < v.llen; i++) {
-            const uint8_t g = v.seq[i];
-            const uint8_t q = i < v.qlen ? v.qual[i] : (uint8_t)40;            // gens.cpp:153
+            if ((i & 15u) == 0) ahead.run(tab, 16);
+            const uint8_t g = rs.next();
+            const uint8_t q = i < v.qlen ? rq.next() : (uint8_t)40;            // gens.cpp:153
             uint32_t n = sfq_gencode(g);
             const bool bad_q = (q == '!');
             bool bad_n = false;
@@ -105,6 +147,7 @@ SFQ_HDN void sfq_gen_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
     ar->size[SFQ_S_GEN_NN] = xnn.close(ovf);
     if (status == SFQ_OK && ovf) status = SFQ_E_CAP;
     meta->n_byte = (n_byte && n_byte != 'N') ? n_byte : 0;                     // gens.cpp:103-104
+    meta->g_used = tab.used;
     if (status != SFQ_OK && meta->status == SFQ_OK) { meta->status = status; meta->status_arg = status_arg; }
 }
 
@@ -172,6 +215,38 @@ SFQ_HD void sfq_q_next(SfqQCtx &c, int level, uint8_t b) {
     else             { c.last = sfq_q_delta_ctx(c.delta, b, c.q2, c.q1); c.q1 = b; }
 }
 
+// Run-ahead cursor of the quality encoder (same idea as SfqGenCursor): replays the context function
+// on the input SFQ_QLT_AHEAD symbols ahead and prefetches the 32-byte hot sector of each context.
+#define SFQ_QLT_AHEAD 48u
+struct SfqQltCursor {
+    const uint8_t *text; const uint64_t *ls; uint64_t line0;
+    uint32_t nrec, solid, r, i, qlen;
+    int level;
+    SfqQCtx c;
+    SfqReader rd;
+    SFQ_HD void open_record() {
+        while (r < nrec) {
+            const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+            qlen = v.qlen; i = 0; c.reset();
+            if (qlen) { rd.seek(v.qual); return; }
+            r++;
+        }
+        qlen = 0;
+    }
+    SFQ_HD void init(const uint8_t *t, const uint64_t *l, const SfqChunkMeta *m, int lvl) {
+        text = t; ls = l; line0 = m->line0; nrec = m->nrec; solid = m->solid; level = lvl; r = 0;
+        open_record();
+    }
+    SFQ_HD void run(const uint32_t *qtable, uint32_t count) {
+        while (count && r < nrec) {
+            sfq_prefetch(qtable + (size_t)c.last * SFQ_L64_WORDS);
+            sfq_q_next(c, level, (uint8_t)(rd.next() - '!'));
+            count--;
+            if (++i == qlen) { r++; open_record(); }
+        }
+    }
+};
+
 SFQ_HDN void sfq_qlt_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *meta, int level,
                                   uint32_t *qtable, uint32_t *pwpool, uint8_t *arena, SfqArena *ar) {
     SfqEnc rc;
@@ -179,11 +254,17 @@ SFQ_HDN void sfq_qlt_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
     SfqPower ex; ex.m = pwpool + (size_t)SFQ_PW_QEX * SFQ_PW_WORDS;
     const uint32_t solid = meta->solid;
     uint32_t extra_hi = 0;
+    SfqQltCursor ahead;
+    ahead.init(text, ls, meta, level);
+    ahead.run(qtable, SFQ_QLT_AHEAD);
     for (uint32_t r = 0; r < meta->nrec; r++) {
         const SfqRecView v = sfq_rec_view(text, ls, meta->line0, r, solid);
         SfqQCtx c; c.reset();
+        SfqReader rq;
+        if (v.qlen) rq.seek(v.qual);
         for (uint32_t i = 0; i < v.qlen; i++) {
-            const uint8_t b = (uint8_t)(v.qual[i] - '!');
+            if ((i & 15u) == 0) ahead.run(qtable, 16);
+            const uint8_t b = (uint8_t)(rq.next() - '!');
             SfqLog64 m; m.m = qtable + (size_t)c.last * SFQ_L64_WORDS;
             if (b < 63) m.put(rc, b);
             else { m.put(rc, 63); ex.put(rc, b); extra_hi++; }                  // qlts.cpp:120-125

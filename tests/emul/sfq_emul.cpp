@@ -14,8 +14,17 @@ static void put_bytes(std::vector<uint8_t> &o, const void *p, size_t n) {
     const uint8_t *b = (const uint8_t *)p; o.insert(o.end(), b, b + n);
 }
 
-extern "C" int sfq_emul_compress(const uint8_t *text, size_t n, int level, uint64_t chunk_bytes,
+// the device buffers are 16-byte aligned and padded; give the CPU run the same guarantees
+static std::vector<uint8_t> padded(const uint8_t *p, size_t n) {
+    std::vector<uint8_t> v(n + 64, 0);
+    if (n) memcpy(v.data(), p, n);
+    return v;
+}
+
+extern "C" int sfq_emul_compress(const uint8_t *text_in, size_t n, int level, uint64_t chunk_bytes,
                                  uint8_t **out, size_t *out_n, uint32_t *status_out) {
+    const std::vector<uint8_t> text_copy = padded(text_in, n);
+    const uint8_t *text = text_copy.data();
     level = level > 4 ? 4 : level < 1 ? 1 : level;
     *status_out = 0;
     std::vector<uint64_t> ls;
@@ -53,7 +62,7 @@ extern "C" int sfq_emul_compress(const uint8_t *text, size_t n, int level, uint6
             b.magic = SFQ_BLOB_MAGIC; b.level = level; b.text_len = m.text_len; b.out_len = m.out_len; b.nrec = m.nrec;
             b.nbases = m.nbases; b.nquals = m.nquals; b.hdr_bytes = m.hdr_bytes; b.llen = m.llen;
             b.solid = m.solid; b.two_id = m.two_id; b.n_byte = m.n_byte; b.extra_hi = m.extra_hi;
-            b.rec_first_len = (uint32_t)(ls[m.line0 + 1] - ls[m.line0] - 2);
+            b.rec_first_len = (uint32_t)(ls[m.line0 + 1] - ls[m.line0] - 2); b.g_used = m.g_used;
             for (int k = 0; k < SFQ_NSTREAMS; k++) b.ssize[k] = ar.size[k];
             index.push_back(file.size());
             out_total += m.out_len;
@@ -73,7 +82,9 @@ extern "C" int sfq_emul_compress(const uint8_t *text, size_t n, int level, uint6
     return 0;
 }
 
-extern "C" int sfq_emul_decompress(const uint8_t *sfq, size_t n, uint8_t **out, size_t *out_n, uint32_t *status_out) {
+extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **out, size_t *out_n, uint32_t *status_out) {
+    const std::vector<uint8_t> sfq_copy = padded(sfq_in, n);
+    const uint8_t *sfq = sfq_copy.data();
     *status_out = 0;
     if (!sfq_is_chunked_container(sfq, n)) { *status_out = SFQ_E_CORRUPT; return 1; }
     SfqFileHeader h; memcpy(&h, sfq, sizeof h);
@@ -133,3 +144,32 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq, size_t n, uint8_t **out, 
     return 0;
 }
 extern "C" void sfq_emul_free(void *p) { free(p); }
+
+// Diagnostics: how many quality contexts / base contexts one chunk touches (sizing of the sparse tables).
+extern "C" int sfq_emul_context_counts(const uint8_t *text_in, size_t n, int level, uint64_t *qctx, uint64_t *gctx, uint64_t *nbases) {
+    const std::vector<uint8_t> text_copy = padded(text_in, n);
+    const uint8_t *text = text_copy.data();
+    std::vector<uint64_t> ls;
+    ls.push_back(0);
+    for (size_t i = 0; i < n; i++) if (text[i] == '\n') ls.push_back(i + 1);
+    if ((ls.size() - 1) % 4) return 1;
+    SfqChunkMeta m;
+    sfq_plan_chunk(text, ls.data(), 0, (ls.size() - 1) / 4, &m);
+    if (m.status) return 1;
+    SfqArena ar; uint64_t end;
+    sfq_arena_layout(&m, 2, 0, &ar, &end);
+    std::vector<uint8_t> arena(end);
+    uint32_t hbits = sfq_gen_hbits(level, m.nbases, 0);
+    uint64_t *gt = (uint64_t *)calloc(1, sfq_gtable_bytes(level, hbits));
+    uint32_t *qt = (uint32_t *)calloc(1, sfq_qtable_bytes(level));
+    uint32_t *pw = (uint32_t *)calloc(1, sfq_pwpool_bytes());
+    sfq_gen_encode_chunk(text, ls.data(), &m, level, gt, hbits, pw, arena.data(), &ar);
+    sfq_qlt_encode_chunk(text, ls.data(), &m, level, qt, pw, arena.data(), &ar);
+    uint64_t q = 0, g = 0;
+    const uint64_t nctx = sfq_qtable_bytes(level) / 256;
+    for (uint64_t c = 0; c < nctx; c++) { bool used = false; for (int k = 0; k < 64 && !used; k++) used = qt[c * 64 + k] != 0; q += used; }
+    if (level > 1) for (uint64_t k = 0; k < (1ull << hbits); k++) g += gt[k] != 0;
+    *qctx = q; *gctx = g; *nbases = m.nbases;
+    free(gt); free(qt); free(pw);
+    return 0;
+}
