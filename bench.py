@@ -254,6 +254,8 @@ def main():
         h_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
         h_text.copy_(d_text)
         torch.cuda.synchronize()
+        del d_text, d_sfq, d_back                  # the host-buffer entry points stage through the library's own buffers
+        torch.cuda.empty_cache()
         h_sfq = torch.empty(csz, dtype=torch.uint8, pin_memory=True)
 
         def step_e2e():

@@ -58,7 +58,7 @@ struct sfq_ctx {
     std::string err;
     sfq_stats st{};
     uint32_t max_resident = 0;
-    uint32_t lanes = 32;                    // chunk-streams per coder warp (SFQ_LANES)
+    uint32_t lanes = 4;                     // chunk-streams per gen/rec coder warp (SFQ_LANES)
     cudaEvent_t ev[EV_COUNT]{};
     std::vector<cudaEvent_t> wave_ev;       // 10 per wave: clear start, code start, code end, pack end, then start/end of gen, qlt, rec
     // device buffers (grow-only, reused across calls)

@@ -200,13 +200,16 @@ struct SfqGenTable {
             v = ((const uint32_t *)slots)[ctx] ^ 0x03030303u;
             return ctx;
         }
+        const uint32_t h = (ctx * 2654435761u) >> (32 - hbits);
+        const uint64_t k = slots[h];
+        const uint32_t kk = (uint32_t)(k >> 32);
+        if (kk == ctx + 1u) { v = (uint32_t)k; return h; }          // the usual case: home slot
+        return find_probe(ctx, h, kk, v);
+    }
+    SFQ_COLD uint32_t find_probe(uint32_t ctx, uint32_t h, uint32_t kk, uint32_t &v) {
         const uint32_t mask = (1u << hbits) - 1u;
-        uint32_t h = (ctx * 2654435761u) >> (32 - hbits);
         const uint32_t key = ctx + 1u;
         for (;;) {
-            uint64_t k = slots[h];
-            uint32_t kk = (uint32_t)(k >> 32);
-            if (kk == key) { v = (uint32_t)k; return h; }
             if (kk == 0) {
                 if (used + 1u >= mask) return 0xFFFFFFFFu;
                 used++;
@@ -214,6 +217,9 @@ struct SfqGenTable {
                 return h;
             }
             h = (h + 1u) & mask;
+            const uint64_t k = slots[h];
+            kk = (uint32_t)(k >> 32);
+            if (kk == key) { v = (uint32_t)k; return h; }
         }
     }
     SFQ_HD void prefetch(uint32_t ctx) const {
@@ -289,7 +295,7 @@ struct SfqAModel {
     }
 
     // Reference-shaped paths over memory: any slot, normalisation, corrupt input.
-    SFQ_HD void put_slow(SfqEnc &rc, uint32_t sym) {      // log64:98-112, power:93-106
+    SFQ_COLD void put_slow(SfqEnc &rc, uint32_t sym) {      // log64:98-112, power:93-106
         if (iend() <= sym) set_iend(sym + 1u);
         uint32_t i = 0, sumf = 0, s;
         for (;; i++) {
@@ -301,7 +307,7 @@ struct SfqAModel {
         rc.encode(sumf + i, freq_of(s) + 1u, tot + NSYM);
         update(i, tot);
     }
-    SFQ_HD uint32_t get_slow(SfqDec &rc, uint32_t prob, uint32_t tot) {   // log64:114-138, power:108-130
+    SFQ_COLD uint32_t get_slow(SfqDec &rc, uint32_t prob, uint32_t tot) {   // log64:114-138, power:108-130
         uint32_t i = 0, sumf = 0, f = 0;
         for (; i < NSYM; i++) {
             f = freq_of(m[i]);
@@ -385,7 +391,7 @@ typedef SfqAModel<256, 14, 32736, 256> SfqPower;
 struct SfqPowerU {
     uint32_t *m;   // 14 models, SFQ_PW_WORDS apart
     SFQ_HD SfqPower at(int k) const { SfqPower p; p.m = m + (size_t)k * SFQ_PW_WORDS; return p; }
-    SFQ_HD void put(SfqEnc &rc, uint64_t num) {
+    SFQ_COLD void put(SfqEnc &rc, uint64_t num) {
         if (num <= 0x7f) { at(0).put(rc, (uint32_t)num); return; }
         if (num < 0x7ffe) {
             at(0).put(rc, (uint32_t)(0xff & (0x80 | (num >> 8))));
@@ -401,7 +407,7 @@ struct SfqPowerU {
             for (int sh = 0, i = 6; sh < 64; sh += 8, i++) at(i).put(rc, (uint32_t)(0xff & (num >> sh)));
         }
     }
-    SFQ_HD uint64_t get(SfqDec &rc) {
+    SFQ_COLD uint64_t get(SfqDec &rc) {
         uint64_t num = at(0).get(rc);
         if (num > 0x7f) {
             num = (num << 8) | at(1).get(rc);
@@ -433,10 +439,10 @@ struct SfqXSave {
         buf = out; cap = capacity;
     }
     SFQ_HD void open() { if (!rc.live) rc.start(buf, cap); }
-    SFQ_HD void put(uint64_t v) { open(); num.put(rc, v); }
-    SFQ_HD void put_chr(uint8_t c) { open(); str.put(rc, c); }
+    SFQ_COLD void put(uint64_t v) { open(); num.put(rc, v); }
+    SFQ_COLD void put_chr(uint8_t c) { open(); str.put(rc, c); }
     // returns stream size (0 = never created); sets ovf on arena overflow
-    SFQ_HD uint32_t close(bool &ovf) {
+    SFQ_COLD uint32_t close(bool &ovf) {
         if (!rc.live) return 0;
         put(0);
         rc.finish();
@@ -453,6 +459,6 @@ struct SfqXLoad {
         str.m = num.m + (size_t)14 * SFQ_PW_WORDS;
         rc.start(in, size);
     }
-    SFQ_HD uint64_t get() { return rc.valid ? num.get(rc) : 0; }   // absent stream reads 0 forever, xfile.cpp:90-93
-    SFQ_HD uint8_t get_chr() { return (uint8_t)str.get(rc); }
+    SFQ_COLD uint64_t get() { return rc.valid ? num.get(rc) : 0; }   // absent stream reads 0 forever, xfile.cpp:90-93
+    SFQ_COLD uint8_t get_chr() { return (uint8_t)str.get(rc); }
 };

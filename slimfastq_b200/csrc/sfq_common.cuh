@@ -12,9 +12,12 @@
 #if defined(__CUDACC__)
 #define SFQ_HD __host__ __device__ __forceinline__
 #define SFQ_HDN static __host__ __device__
+// rare paths are kept out of line so the hot loops stay small enough for the instruction caches
+#define SFQ_COLD __host__ __device__ __noinline__
 #else
 #define SFQ_HD inline
 #define SFQ_HDN static
+#define SFQ_COLD
 #endif
 
 // Stream ids inside a chunk.  Names/ordering follow the reference's stream creation sites

@@ -30,6 +30,38 @@ struct SfqQTable {
     __device__ __forceinline__ void prefetch(uint32_t ctx, uint32_t lane) const { sfq_prefetch(base + (size_t)home(ctx) * 64 + lane * SFQ_QS); }
 };
 
+// Run-ahead cursor of the quality encoder: replays the context function on the input SFQ_QLT_AHEAD
+// symbols ahead of the coder (contexts depend on the input alone) and prefetches the sector of the
+// context's home entry that this lane will load.
+struct SfqQltCursor {
+    const uint8_t *text; const uint64_t *ls; uint64_t line0;
+    uint32_t nrec, solid, r, i, qlen;
+    int level;
+    SfqQCtx c;
+    SfqReader rd;
+    __device__ __forceinline__ void open_record() {
+        while (r < nrec) {
+            const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+            qlen = v.qlen; i = 0; c.reset();
+            if (qlen) { rd.seek(v.qual); return; }
+            r++;
+        }
+        qlen = 0;
+    }
+    __device__ __forceinline__ void init(const uint8_t *t, const uint64_t *l, const SfqChunkMeta *m, int lvl) {
+        text = t; ls = l; line0 = m->line0; nrec = m->nrec; solid = m->solid; level = lvl; r = 0;
+        open_record();
+    }
+    __device__ __forceinline__ void run(const SfqQTable &tab, uint32_t lane, uint32_t count) {
+        while (count && r < nrec) {
+            tab.prefetch(c.last, lane);
+            sfq_q_next(c, level, (uint8_t)(rd.next() - '!'));
+            count--;
+            if (++i == qlen) { r++; open_record(); }
+        }
+    }
+};
+
 struct SfqQGroup {
     unsigned gmask;      // lanes of this group within the warp
     uint32_t lane;       // 0..7 inside the group
@@ -72,21 +104,22 @@ struct SfqQGroup {
         }
     }
 
-    // update_freq (log64_ranger.hpp:69-87) on slot i = 8*hl + hk holding frequency f; tot/iend are the
-    // context's current values.  Stores whatever changed.
-    __device__ __forceinline__ void update(uint32_t hl, uint32_t hk, uint32_t f, uint32_t tot, uint32_t iend_new) {
+    // update_freq (log64_ranger.hpp:69-87) on slot i = 8*hl + hk holding frequency f; tot/count are the
+    // context's current values.  Stores whatever changed.  (`iend` is not kept: with the sym^index slot
+    // encoding every slot is always valid, and slots past the reference's iend have freq 0, so its only
+    // uses - the bounds of the search and of normalize() - change nothing.)
+    __device__ __forceinline__ void update(uint32_t hl, uint32_t hk, uint32_t f, uint32_t tot, uint32_t count) {
         const uint32_t i = hl * SFQ_QS + hk;
         bool all_dirty = false;
         if (f > 65472u - 6u) {
             if (i == 0 && f + 20u > tot) {                  // saturated front slot: no update at all
-                if (lane == 0) { set_iend(iend_new); store(); }
+                if (lane == 0) store();                     // (persists a fresh claim)
                 return;
             }
             uint32_t s = 0;
 #pragma unroll
             for (int k = 0; k < SFQ_QS; k++) { const uint32_t fk = (w[k] & 0xffffu) >> 1; w[k] = (w[k] & 0xffff0000u) | fk; s += fk; }
-            for (int d = 1; d < SFQ_QG; d <<= 1) s += __shfl_xor_sync(gmask, s, d, SFQ_QG);
-            tot = s;
+            tot = __reduce_add_sync(gmask, s);
             f >>= 1;
             all_dirty = true;
         }
@@ -98,7 +131,7 @@ struct SfqQGroup {
         }
         bool prev_dirty = false;
         if (i != 0) {
-            const uint32_t count = (bcast(w[3] >> 24, 0) + 1u) & 0xffu;
+            count = (count + 1u) & 0xffu;
             if (lane == 0) w[3] = (w[3] & 0x00ffffffu) | (count << 24);
             if ((count & 0xfu) == 0) {                      // maybe swap slot i with slot i-1
                 // the neighbour is slot hk-1 of the same lane, or slot 7 of the lane before
@@ -126,18 +159,16 @@ struct SfqQGroup {
             w[0] = (w[0] & 0x00ffffffu) | ((tot & 0xffu) << 24);
             w[1] = (w[1] & 0x00ffffffu) | (((tot >> 8) & 0xffu) << 24);
             w[2] = (w[2] & 0x00ffffffu) | (((tot >> 16) & 0xffu) << 24);
-            set_iend(iend_new);
         }
         if (all_dirty || lane == 0 || lane == hl || prev_dirty) store();
     }
-    __device__ __forceinline__ void set_iend(uint32_t e) {   // lane 0 only; keeps the "occupied" bit
-        w[4] = (w[4] & 0x00ffffffu) | ((e & 0xffu) << 24);
-        w[5] = (w[5] & 0x00ffffffu) | ((((w[5] >> 24) & 0xfeu) | ((e >> 8) & 1u)) << 24);
+    // total (bits 0..23) and count (bits 24..31) of the loaded context, from lane 0
+    __device__ __forceinline__ uint32_t header() const {
+        return bcast((w[0] >> 24) | ((w[1] >> 24) << 8) | ((w[2] >> 24) << 16) | (w[3] & 0xff000000u), 0);
     }
-    __device__ __forceinline__ uint32_t total0() const { return (w[0] >> 24) | ((w[1] >> 24) << 8) | ((w[2] >> 24) << 16); }
-    __device__ __forceinline__ uint32_t iend0() const { return (w[4] >> 24) | (((w[5] >> 24) & 1u) << 8); }
 
-    // Log64Ranger::put (log64_ranger.hpp:98-112) on the loaded context.
+    // Log64Ranger::put (log64_ranger.hpp:98-112) on the loaded context: 8-way local compare, one
+    // ballot for the slot, two warp reductions for the cumulative frequency and the slot's own.
     __device__ __forceinline__ void put(SfqEnc &rc, uint32_t sym) {
         int hit = -1;
         uint32_t before = 0, lsum = 0, fh = 0;
@@ -148,32 +179,30 @@ struct SfqQGroup {
             if (hit < 0) { if (s == sym) { hit = k; fh = f; } else before += f; }
             lsum += f;
         }
-        uint32_t incl = lsum;
-        for (int d = 1; d < SFQ_QG; d <<= 1) { const uint32_t t = __shfl_up_sync(gmask, incl, d, SFQ_QG); if ((int)lane >= d) incl += t; }
-        const unsigned ball = __ballot_sync(gmask, hit >= 0) >> gbase;
-        const uint32_t hl = (uint32_t)(__ffs(ball & 0xffu) - 1);
-        const uint32_t sumf = bcast(incl - lsum + before, hl);
-        const uint32_t f = bcast(fh, hl);
-        const uint32_t hk = bcast((uint32_t)hit, hl);
-        const uint32_t tot = bcast(total0(), 0);
-        const uint32_t ie = bcast(iend0(), 0);
+        const uint32_t hdr = header();
+        const unsigned ball = (__ballot_sync(gmask, hit >= 0) >> gbase) & 0xffu;
+        const uint32_t hl = (uint32_t)(__ffs(ball) - 1);
+        const uint32_t sumf = __reduce_add_sync(gmask, lane < hl ? lsum : (lane == hl ? before : 0u));
+        const uint32_t fk = __reduce_or_sync(gmask, lane == hl ? (fh | ((uint32_t)hit << 16)) : 0u);
+        const uint32_t f = fk & 0xffffu, hk = fk >> 16, tot = hdr & 0x00ffffffu;
         rc.encode(sumf + hl * SFQ_QS + hk, f + 1u, tot + 64u);
-        update(hl, hk, f, tot, ie <= sym ? sym + 1u : ie);
+        update(hl, hk, f, tot, hdr >> 24);
     }
 
     // Log64Ranger::get (log64_ranger.hpp:114-138) on the loaded context.
     __device__ __forceinline__ uint32_t get(SfqDec &rc) {
-        const uint32_t tot = bcast(total0(), 0);
-        const uint32_t ie = bcast(iend0(), 0);
+        const uint32_t hdr = header();
+        const uint32_t tot = hdr & 0x00ffffffu;
         const uint32_t prob = rc.get_freq(tot + 64u);
         uint32_t lsum = 0;
 #pragma unroll
         for (int k = 0; k < SFQ_QS; k++) lsum += (w[k] & 0xffffu) + 1u;
-        uint32_t incl = lsum;
-        for (int d = 1; d < SFQ_QG; d <<= 1) { const uint32_t t = __shfl_up_sync(gmask, incl, d, SFQ_QG); if ((int)lane >= d) incl += t; }
-        const unsigned ball = (__ballot_sync(gmask, prob < incl) >> gbase) & 0xffu;
+        uint32_t excl = 0;                                   // 7 independent shuffles instead of a 3-step dependent scan
+#pragma unroll
+        for (int d = 1; d < SFQ_QG; d++) { const uint32_t t = __shfl_up_sync(gmask, lsum, d, SFQ_QG); if ((int)lane >= d) excl += t; }
+        const unsigned ball = (__ballot_sync(gmask, prob < excl + lsum) >> gbase) & 0xffu;
         const uint32_t hl = ball ? (uint32_t)(__ffs(ball) - 1) : (uint32_t)(SFQ_QG - 1);     // no lane: corrupt stream
-        uint32_t cum = incl - lsum, fh = 0, sh = 0;
+        uint32_t cum = excl, fh = 0, sh = 0;
         int hit = -1;
 #pragma unroll
         for (int k = 0; k < SFQ_QS; k++) {
@@ -183,10 +212,11 @@ struct SfqQGroup {
                 else { hit = k; fh = f; sh = ((w[k] >> 16) & 0xffu) ^ (lane * SFQ_QS + k); }
             }
         }
-        const uint32_t sumf = bcast(cum, hl), f = bcast(fh, hl), hk = bcast((uint32_t)hit, hl), sym = bcast(sh, hl);
-        const uint32_t i = hl * SFQ_QS + hk;
+        const uint32_t sumf = __reduce_or_sync(gmask, lane == hl ? cum : 0u);
+        const uint32_t pk = __reduce_or_sync(gmask, lane == hl ? (fh | ((uint32_t)hit << 16) | (sh << 19)) : 0u);
+        const uint32_t f = pk & 0xffffu, hk = (pk >> 16) & 7u, sym = pk >> 19;
         rc.decode(sumf, f + 1u);
-        update(hl, hk, f, tot, ie <= i ? i + 1u : ie);
+        update(hl, hk, f, tot, hdr >> 24);
         return sym;
     }
 };
@@ -204,12 +234,16 @@ __device__ __forceinline__ void sfq_qlt_encode_group(const uint8_t *text, const 
     const uint32_t solid = meta->solid;
     uint32_t extra_hi = 0;
     bool full = false;
+    SfqQltCursor ahead;                      // run-ahead prefetch: every lane touches its own sector
+    ahead.init(text, ls, meta, level);
+    ahead.run(tab, g.lane, SFQ_QLT_AHEAD);
     for (uint32_t r = 0; r < meta->nrec && !full; r++) {
         const SfqRecView v = sfq_rec_view(text, ls, meta->line0, r, solid);
         SfqQCtx c; c.reset();
         SfqReader rq;
         if (v.qlen) rq.seek(v.qual);
         for (uint32_t i = 0; i < v.qlen; i++) {
+            if ((i & 15u) == 0) ahead.run(tab, g.lane, 16);
             const uint8_t b = (uint8_t)(rq.next() - '!');
             if (!g.locate(tab, c.last)) { full = true; break; }
             if (b < 63) g.put(rc, b);

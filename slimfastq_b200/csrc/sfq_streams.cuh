@@ -37,15 +37,16 @@ SFQ_HD SfqRecView sfq_rec_view(const uint8_t *text, const uint64_t *ls, uint64_t
     return v;
 }
 
-SFQ_HD uint32_t sfq_gencode(uint8_t c) {            // gencodes[], gens.cpp:72-77
-    switch (c) {
-    case '0': case 'A': case 'a': return 0;
-    case '1': case 'C': case 'c': return 1;
-    case '2': case 'G': case 'g': return 2;
-    case '3': case 'T': case 't': return 3;
-    case '.': case 'N': case 'n': return 4;
-    default: return 0x10;
-    }
+// gencodes[] (gens.cpp:72-77) without a table or a jump: ACGT/acgt/0123 -> 0..3, N n . -> 4, else 0x10.
+SFQ_HD uint32_t sfq_gencode(uint8_t c) {
+    const uint32_t u = c & 0xDFu;                         // fold case (also maps '0'..'3' -> 0x10..0x13)
+    // A=0x41 C=0x43 G=0x47 T=0x54: bits 1..2 give 0,1,3,2 -> swap the last two
+    uint32_t n = (u >> 1) & 3u;
+    n ^= n >> 1;
+    const bool acgt = (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');
+    const bool digit = (uint32_t)(c - '0') < 4u;
+    const bool isn = (u == 'N') | (c == '.');
+    return acgt ? n : digit ? (uint32_t)(c - '0') : isn ? 4u : 0x10u;
 }
 SFQ_HD uint32_t sfq_gen_mask(int level) {           // gens.hpp:43-53,74-82
     return level <= 1 ? (1u << 18) - 1 : level == 2 ? (1u << 22) - 1 : level == 3 ? (1u << 24) - 1 : (1u << 26) - 1;
@@ -215,38 +216,10 @@ SFQ_HD void sfq_q_next(SfqQCtx &c, int level, uint8_t b) {
     else             { c.last = sfq_q_delta_ctx(c.delta, b, c.q2, c.q1); c.q1 = b; }
 }
 
-// Run-ahead cursor of the quality encoder (same idea as SfqGenCursor): replays the context function
-// on the input SFQ_QLT_AHEAD symbols ahead and prefetches the 32-byte hot sector of each context.
 #define SFQ_QLT_AHEAD 48u
-struct SfqQltCursor {
-    const uint8_t *text; const uint64_t *ls; uint64_t line0;
-    uint32_t nrec, solid, r, i, qlen;
-    int level;
-    SfqQCtx c;
-    SfqReader rd;
-    SFQ_HD void open_record() {
-        while (r < nrec) {
-            const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
-            qlen = v.qlen; i = 0; c.reset();
-            if (qlen) { rd.seek(v.qual); return; }
-            r++;
-        }
-        qlen = 0;
-    }
-    SFQ_HD void init(const uint8_t *t, const uint64_t *l, const SfqChunkMeta *m, int lvl) {
-        text = t; ls = l; line0 = m->line0; nrec = m->nrec; solid = m->solid; level = lvl; r = 0;
-        open_record();
-    }
-    SFQ_HD void run(const uint32_t *qtable, uint32_t count) {
-        while (count && r < nrec) {
-            sfq_prefetch(qtable + (size_t)c.last * SFQ_L64_WORDS);
-            sfq_q_next(c, level, (uint8_t)(rd.next() - '!'));
-            count--;
-            if (++i == qlen) { r++; open_record(); }
-        }
-    }
-};
-
+// Thread-serial form of the quality coder over a direct table.  The GPU runs the lane-cooperative form
+// (sfq_qlt_group.cuh); this one is what the CPU emulation checks against the oracle and it defines
+// the behaviour the cooperative form must reproduce.
 SFQ_HDN void sfq_qlt_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *meta, int level,
                                   uint32_t *qtable, uint32_t *pwpool, uint8_t *arena, SfqArena *ar) {
     SfqEnc rc;
@@ -254,16 +227,12 @@ SFQ_HDN void sfq_qlt_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
     SfqPower ex; ex.m = pwpool + (size_t)SFQ_PW_QEX * SFQ_PW_WORDS;
     const uint32_t solid = meta->solid;
     uint32_t extra_hi = 0;
-    SfqQltCursor ahead;
-    ahead.init(text, ls, meta, level);
-    ahead.run(qtable, SFQ_QLT_AHEAD);
     for (uint32_t r = 0; r < meta->nrec; r++) {
         const SfqRecView v = sfq_rec_view(text, ls, meta->line0, r, solid);
         SfqQCtx c; c.reset();
         SfqReader rq;
         if (v.qlen) rq.seek(v.qual);
         for (uint32_t i = 0; i < v.qlen; i++) {
-            if ((i & 15u) == 0) ahead.run(qtable, 16);
             const uint8_t b = (uint8_t)(rq.next() - '!');
             SfqLog64 m; m.m = qtable + (size_t)c.last * SFQ_L64_WORDS;
             if (b < 63) m.put(rc, b);
