@@ -59,18 +59,22 @@ struct sfq_ctx {
     sfq_stats st{};
     uint32_t max_resident = 0;
     uint32_t lanes = 4;                     // chunk-streams per gen/rec coder warp (SFQ_LANES)
+    int sm_count = 148;
     cudaEvent_t ev[EV_COUNT]{};
     std::vector<cudaEvent_t> wave_ev;       // 10 per wave: clear start, code start, code end, pack end, then start/end of gen, qlt, rec
     // device buffers (grow-only, reused across calls)
     DevBuf text, out, tiles, tile_prefix, lines, scalars, rec_begin, r0, r1, metas, arenas, arena_buf,
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
-           t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff;
+           t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
+           e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks;
+    bool serial_encoder = false;            // SFQ_ENC_SERIAL=1: single-pass coders (one chain per chunk-stream) for A/B runs
     HostBuf h_out, h_small;
     void release_all() {
         DevBuf *all[] = {&text, &out, &tiles, &tile_prefix, &lines, &scalars, &rec_begin, &r0, &r1, &metas,
                          &arenas, &arena_buf, &blob_off, &gtab, &qtab, &pw, &dchunks, &bhdrs, &bases, &quals,
                          &hdrs, &rec_chunk, &t_llen, &t_qlen, &t_hlen, &t_pfg, &t_pfq, &t_boff, &t_qoff,
-                         &t_hoff, &t_ooff};
+                         &t_hoff, &t_ooff, &e2_gsteps, &e2_qkey, &e2_qb, &e2_sorted, &e2_qsteps, &e2_cnt, &e2_esorted,
+                         &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks};
         for (DevBuf *b : all) b->release();
         h_out.release(); h_small.release();
     }
@@ -85,6 +89,9 @@ cudaError_t ensure_big(sfq_ctx *ctx, DevBuf &b, size_t bytes) {
     cudaGetLastError();
     ctx->gtab.release(); ctx->qtab.release(); ctx->pw.release(); ctx->arena_buf.release();
     ctx->bases.release(); ctx->quals.release(); ctx->hdrs.release();
+    DevBuf *e2[] = {&ctx->e2_gsteps, &ctx->e2_qkey, &ctx->e2_qb, &ctx->e2_sorted, &ctx->e2_qsteps, &ctx->e2_cnt,
+                    &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs};
+    for (DevBuf *d : e2) d->release();
     return b.ensure(bytes);
 }
 
@@ -140,6 +147,9 @@ uint32_t pick_resident(sfq_ctx *ctx, uint64_t nchunks, uint64_t per_chunk, uint6
     r = (nchunks + nw - 1) / nw;
     return (uint32_t)r;
 }
+
+// kernels index the per-chunk pools by the chunk's position in the wave
+SfqWorkspace ws_at(const SfqWorkspace &ws, uint32_t) { return ws; }
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
@@ -237,20 +247,50 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             sfq_arena_layout(&metas[c], grow, 0, &a, &end);
             max_arena = std::max(max_arena, end);
         }
-        const uint64_t per_chunk = gstride + qbytes + pbytes + max_arena + 4096;
-        const uint32_t R = pick_resident(ctx, nchunks, per_chunk, ctx->gtab.cap + ctx->qtab.cap + ctx->pw.cap + ctx->arena_buf.cap);
-        CK(ctx->gtab.ensure(R * gstride)); CK(ctx->qtab.ensure(R * qbytes)); CK(ctx->pw.ensure(R * pbytes));
+        const bool two_phase = !ctx->serial_encoder;
+        uint64_t max_nb = 0, max_nq = 0;
+        for (uint32_t c = 0; c < nchunks; c++) { max_nb = std::max<uint64_t>(max_nb, metas[c].nbases); max_nq = std::max<uint64_t>(max_nq, metas[c].nquals); }
+        if (two_phase && max_nq >= (1u << 24)) return fail(ctx, SFQ_ERR_UNSUPPORTED, "chunk of %llu quality values: chunk_bytes is too large (limit 16 Mi values per chunk)", (unsigned long long)max_nq);
+        auto esc_cap = [grow](uint64_t nq) { return std::min<uint64_t>(nq, (nq >> 4) << grow) + 64; };
+        auto seg_cap = [](uint64_t nq) { return std::min<uint64_t>(SFQ_Q_NCTX, nq) + 1; };
+        // two-phase encoder: no quality-model table in global memory, but the coding steps of every symbol
+        const uint64_t e2_per_chunk = 4 * max_nb + 15 * max_nq + SFQ_Q_CNT * 4ull + 16 * seg_cap(max_nq) + 12 * esc_cap(max_nq) + 256;
+        const uint64_t per_chunk = gstride + pbytes + max_arena + 4096 + (two_phase ? e2_per_chunk : qbytes);
+        const uint64_t have_now = ctx->gtab.cap + ctx->qtab.cap + ctx->pw.cap + ctx->arena_buf.cap + ctx->e2_gsteps.cap + ctx->e2_qkey.cap +
+                                  ctx->e2_qb.cap + ctx->e2_sorted.cap + ctx->e2_qsteps.cap + ctx->e2_cnt.cap + ctx->e2_esorted.cap +
+                                  ctx->e2_esteps.cap + ctx->e2_segs.cap;
+        const uint32_t R = pick_resident(ctx, nchunks, per_chunk, have_now);
+        CK(ctx->gtab.ensure(R * gstride)); CK(ctx->pw.ensure(R * pbytes));
+        if (!two_phase) CK(ctx->qtab.ensure(R * qbytes));
         const uint32_t nwaves = (nchunks + R - 1) / R;
         if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
-        st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * (gstride + qbytes + pbytes);
-        // arena layout: offsets restart at 0 for every wave
-        uint64_t wave_arena_max = 0;
+        st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * per_chunk;
+        // arena layout: offsets restart at 0 for every wave; same for the coding-step arrays
+        uint64_t wave_arena_max = 0, wave_nb = 0, wave_nq = 0, wave_ne = 0, wave_seg = 0;
+        std::vector<SfqEnc2Chunk> e2c(nchunks);
         for (uint32_t w = 0; w < nwaves; w++) {
-            uint64_t o = 0;
-            for (uint32_t c = w * R; c < std::min(nchunks, (w + 1) * R); c++) sfq_arena_layout(&metas[c], grow, o, &arenas[c], &o);
+            uint64_t o = 0, gb = 0, qb = 0, eb = 0, sg = 0;
+            for (uint32_t c = w * R; c < std::min(nchunks, (w + 1) * R); c++) {
+                sfq_arena_layout(&metas[c], grow, o, &arenas[c], &o);
+                e2c[c].goff = gb; e2c[c].qoff = qb; e2c[c].eoff = eb; e2c[c].ecap = (uint32_t)esc_cap(metas[c].nquals); e2c[c].pad = 0;
+                gb += (metas[c].nbases + 3ull) & ~3ull; qb += (metas[c].nquals + 15ull) & ~15ull; eb += e2c[c].ecap; sg += seg_cap(metas[c].nquals);
+            }
             wave_arena_max = std::max(wave_arena_max, o);
+            wave_nb = std::max(wave_nb, gb); wave_nq = std::max(wave_nq, qb); wave_ne = std::max(wave_ne, eb); wave_seg = std::max(wave_seg, sg);
         }
         CK(ctx->arena_buf.ensure(wave_arena_max + 64));
+        SfqEnc2Ws e2{};
+        if (two_phase) {
+            CK(ctx->e2_gsteps.ensure(wave_nb * 4 + 64)); CK(ctx->e2_qkey.ensure(wave_nq * 2 + 64)); CK(ctx->e2_qb.ensure(wave_nq + 64));
+            CK(ctx->e2_sorted.ensure(wave_nq * 4 + 64)); CK(ctx->e2_qsteps.ensure(wave_nq * 8 + 64)); CK(ctx->e2_cnt.ensure((uint64_t)R * SFQ_Q_CNT * 4));
+            CK(ctx->e2_esorted.ensure(wave_ne * 4 + 64)); CK(ctx->e2_esteps.ensure(wave_ne * 8 + 64)); CK(ctx->e2_segs.ensure(wave_seg * sizeof(SfqSeg)));
+            CK(ctx->e2_ctr.ensure(64)); CK(ctx->e2_chunks.ensure(nchunks * sizeof(SfqEnc2Chunk)));
+            CK(cudaMemcpyAsync(ctx->e2_chunks.p, e2c.data(), nchunks * sizeof(SfqEnc2Chunk), cudaMemcpyHostToDevice, s));
+            e2.gsteps = ctx->e2_gsteps.as<uint32_t>(); e2.qkey = ctx->e2_qkey.as<uint16_t>(); e2.qb = ctx->e2_qb.as<uint8_t>();
+            e2.sorted = ctx->e2_sorted.as<uint32_t>(); e2.qsteps = ctx->e2_qsteps.as<uint64_t>(); e2.cnt = ctx->e2_cnt.as<uint32_t>();
+            e2.esorted = ctx->e2_esorted.as<uint32_t>(); e2.esteps = ctx->e2_esteps.as<uint64_t>(); e2.segs = ctx->e2_segs.as<SfqSeg>();
+            e2.seg_cap = wave_seg; e2.ctr = ctx->e2_ctr.as<uint32_t>();
+        }
         CK(cudaMemcpyAsync(d_arenas, arenas.data(), nchunks * sizeof(SfqArena), cudaMemcpyHostToDevice, s));
         h_small[0] = 0; h_small[1] = sizeof(SfqFileHeader); h_small[2] = 0;
         CK(cudaMemcpyAsync(d_scal, h_small, 24, cudaMemcpyHostToDevice, s));
@@ -261,22 +301,41 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 0], s));
             CK(cudaMemsetAsync(ctx->gtab.p, 0, nc * gstride, s));
-            CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
+            if (!two_phase) CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
+            else { CK(cudaMemsetAsync(ctx->e2_cnt.p, 0, (uint64_t)nc * SFQ_Q_CNT * 4, s)); CK(cudaMemsetAsync(ctx->e2_ctr.p, 0, 64, s)); }
             CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
             {   // fork: gen on the main stream, qlt and rec beside it; join before packing
                 const unsigned nb = (nc + ctx->lanes - 1) / ctx->lanes;
+                const unsigned nwarp_blocks = (nc * 32u + 127u) / 128u;       // one warp per chunk, 4 warps per CTA
+                const SfqEnc2Chunk *d_e2c = ctx->e2_chunks.as<SfqEnc2Chunk>() + c0;
+                uint8_t *abuf = ctx->arena_buf.as<uint8_t>();
                 CK(cudaEventRecord(ctx->fork_ev, s));
                 CK(cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0));
                 CK(cudaStreamWaitEvent(ctx->side[1], ctx->fork_ev, 0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
-                k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), ws, level, nc, ctx->lanes); LAUNCHED();
+                if (two_phase) {
+                    k_gen_model<<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); LAUNCHED();
+                    k_rc_encode<<<(nc + 31) / 32, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, 32, 0); LAUNCHED();
+                } else {
+                    k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
+                }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], ctx->side[0]));
-                k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, ctx->side[0]>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), ws, level, nc, ctx->lanes); LAUNCHED();
+                if (two_phase) {
+                    cudaStream_t q = ctx->side[0];
+                    k_qlt_keys<<<nwarp_blocks, 128, 0, q>>>(d_text, d_ls, d_metas + c0, e2, d_e2c, level, nc); LAUNCHED();
+                    k_qlt_scan<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
+                    k_qlt_scatter<<<nwarp_blocks, 128, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
+                    k_qlt_model<<<ctx->sm_count * 4, SFQ_QM_THREADS, 0, q>>>(d_metas + c0, ws_at(ws, c0), e2, d_e2c, c0); LAUNCHED();
+                    k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
+                    k_rc_encode<<<(nc + 31) / 32, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, 32, 1); LAUNCHED();
+                } else {
+                    k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, ctx->side[0]>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
+                }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], ctx->side[0]));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], ctx->side[1]));
-                k_encode<2><<<nb, 32, 0, ctx->side[1]>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), ws, level, nc, ctx->lanes); LAUNCHED();
+                k_encode<2><<<nb, 32, 0, ctx->side[1]>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], ctx->side[1]));
                 CK(cudaEventRecord(ctx->join_ev[0], ctx->side[0]));
                 CK(cudaEventRecord(ctx->join_ev[1], ctx->side[1]));
@@ -541,6 +600,8 @@ int sfq_create(sfq_ctx **out, int device) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
+    if (const char *e = getenv("SFQ_ENC_SERIAL")) ctx->serial_encoder = atoi(e) != 0;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     for (int k = 0; k < 2; k++)
         if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess ||

@@ -295,7 +295,7 @@ struct SfqAModel {
     }
 
     // Reference-shaped paths over memory: any slot, normalisation, corrupt input.
-    SFQ_COLD void put_slow(SfqEnc &rc, uint32_t sym) {      // log64:98-112, power:93-106
+    template <class RC> SFQ_COLD void put_slow(RC &rc, uint32_t sym) {      // log64:98-112, power:93-106
         if (iend() <= sym) set_iend(sym + 1u);
         uint32_t i = 0, sumf = 0, s;
         for (;; i++) {
@@ -349,7 +349,7 @@ struct SfqAModel {
         if (i >= 4 || iend_new != iend_old) sfq_st16(m + 4, w[4], w[5], w[6], w[7]);
     }
 
-    SFQ_HD void put(SfqEnc &rc, uint32_t sym) {
+    template <class RC> SFQ_HD void put(RC &rc, uint32_t sym) {
         uint32_t w[8];
         { const SfqU4 a = sfq_ld16(m), b = sfq_ld16(m + 4);
           w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; }

@@ -103,3 +103,11 @@ struct SfqArena {
     uint32_t cap[SFQ_NSTREAMS];
     uint32_t size[SFQ_NSTREAMS];   // filled by the coders (0 = stream never created)
 };
+
+// Per-wave workspace of the coders: chunk w of the wave owns slice w of every table.
+struct SfqWorkspace {
+    uint8_t  *gtab;  uint64_t gtab_stride;  uint32_t hbits;     // base-context tables
+    uint32_t *qtab;  uint64_t qtab_words;   uint32_t cbits;     // quality-context tables (hashed)
+    uint32_t *pw;                                                // 256-symbol model pools
+};
+

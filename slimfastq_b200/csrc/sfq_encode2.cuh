@@ -1,0 +1,569 @@
+// Two-phase encoder for the gen and qlt streams.
+//
+// An adaptive range coder is two recurrences glued together: the *model* recurrence (the frequency
+// table of a context changes only when that context is visited) and the *coder* recurrence
+// (low/range change with every symbol).  An encoder knows every context from the input alone, so
+// only the second one is a chain over the whole stream.  The kernels here split them:
+//
+//   phase 1 (parallel)  for every symbol, the (cumFreq, freq, totFreq) triple its model hands to
+//                       RCoder::Encode (coder.hpp:66), in stream order:
+//       gen   k_gen_model    one warp per chunk walks the bases 32 at a time; lanes whose contexts
+//                            differ update their table slots independently, lanes sharing a context
+//                            are replayed in lane order (base2_ranger.hpp:74-84, gens.cpp:138-159)
+//       qlt   k_qlt_keys     context of every quality (qlts.hpp:52-74) + per-context histogram
+//             k_qlt_scan     exclusive scan -> one segment per visited context
+//             k_qlt_scatter  stable counting sort of the positions by context
+//             k_qlt_model    one thread per context replays its Log64Ranger (log64_ranger.hpp:69-112)
+//                            over the context's positions with the whole model in shared memory
+//   phase 2 (chain)     k_rc_encode   one thread per chunk-stream feeds the triples to the coder:
+//                       a divide, two multiplies and the renormalisation loop per symbol.
+//
+// The bytes are those of the single-pass coder (same triples, same order); what changes is that the
+// per-symbol table work no longer sits on a 438 k-step dependency chain per chunk.
+#pragma once
+#include "sfq_streams.cuh"
+
+// ---------------------------------------------------------------------------- packed coding steps
+// gen: cum (10 bit) | freq (8 bit) << 10 | tot (10 bit) << 18          (tot <= 4 * 255)
+// qlt: cum (22 bit) | freq (17 bit) << 22 | tot (22 bit) << 39 | escape-follows << 61
+//      (tot <= 64 * 65472 + 64 < 2^22, freq <= 65473; power_ranger escape steps use the same packing:
+//       tot <= 256 * 32736 + 256 < 2^24 does NOT fit 22 bits, so escape steps use SFQ_ESTEP_* below)
+SFQ_HD uint32_t sfq_gstep_pack(uint32_t cum, uint32_t f, uint32_t tot) { return cum | (f << 10) | (tot << 18); }
+SFQ_HD uint64_t sfq_qstep_pack(uint32_t cum, uint32_t f, uint32_t tot, bool esc) {
+    return (uint64_t)cum | ((uint64_t)f << 22) | ((uint64_t)tot << 39) | ((uint64_t)(esc ? 1u : 0u) << 61);
+}
+// escape (256-symbol model) steps: cum (24) | freq (16) << 24 | tot (24) << 40
+SFQ_HD uint64_t sfq_estep_pack(uint32_t cum, uint32_t f, uint32_t tot) {
+    return (uint64_t)cum | ((uint64_t)f << 24) | ((uint64_t)tot << 40);
+}
+
+// A coder stand-in that records the triples instead of coding them (phase 1 of the escape model).
+struct SfqStepSink {
+    uint64_t *out;
+    SFQ_HD void encode(uint32_t cum, uint32_t freq, uint32_t tot) { *out++ = sfq_estep_pack(cum, freq, tot); }
+};
+
+// Where the intermediate arrays of a wave's chunk live.
+struct SfqEnc2Chunk {
+    uint64_t goff;          // first entry of the chunk in gsteps
+    uint64_t qoff;          // first entry in qkey / qb / sorted / qsteps
+    uint64_t eoff;          // first entry in esorted / esteps
+    uint32_t ecap;          // entries reserved there
+    uint32_t pad;
+};
+#define SFQ_Q_NCTX   65536u
+#define SFQ_Q_CNT    65544u           // counters per chunk: 65536 contexts + [65536] = escapes, padded
+#define SFQ_SEG_BIG  2048u            // segments at least this long are scheduled first
+struct SfqSeg { uint32_t chunk, start, count, flags; };      // flags bit 0: escape segment
+struct SfqEnc2Ws {
+    uint32_t *gsteps;
+    uint16_t *qkey;
+    uint8_t  *qb;
+    uint32_t *sorted;       // pos (24 bit) | symbol << 24, grouped by context, position order inside
+    uint64_t *qsteps;
+    uint32_t *cnt;          // SFQ_Q_CNT per chunk: histogram, then cursors
+    uint32_t *esorted;
+    uint64_t *esteps;
+    SfqSeg   *segs;         // small segments grow from the front, big ones from the back
+    uint64_t  seg_cap;
+    uint32_t *ctr;          // [0] small segments, [1] big segments, [2] next segment to hand out
+};
+
+// ---------------------------------------------------------------------------- Log64Ranger, replay form
+// One context's model with O(1) slot lookup and two-level cumulative sums, sized for shared memory
+// (log64_ranger.hpp:36-96).  `W` = distance in 32-bit words between consecutive fields of one model
+// (models of neighbouring threads are interleaved at an odd stride to spread the banks).
+//   words 0..31   freq[64] as u16 pairs
+//   words 32..47  syms[64] bytes
+//   words 48..63  pos[64] bytes (inverse of syms)
+//   words 64..71  gsum[8]  (sum of freq over slots 8g..8g+7)
+//   word  72      total;   word 73  count
+#define SFQ_L64R_WORDS 75u
+struct SfqL64Replay {
+    uint32_t *w;
+    SFQ_HD uint16_t *freq() const { return reinterpret_cast<uint16_t *>(w); }
+    SFQ_HD uint8_t *syms() const { return reinterpret_cast<uint8_t *>(w + 32); }
+    SFQ_HD uint8_t *pos() const { return reinterpret_cast<uint8_t *>(w + 48); }
+    SFQ_HD uint32_t *gsum() const { return w + 64; }
+    SFQ_HD void reset() {
+        for (uint32_t k = 0; k < 32; k++) w[k] = 0;
+        for (uint32_t k = 0; k < 16; k++) { const uint32_t b = 4 * k; const uint32_t v = b | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24); w[32 + k] = v; w[48 + k] = v; }
+        for (uint32_t k = 64; k < 74; k++) w[k] = 0;
+    }
+    // Log64Ranger::put + update_freq for symbol `sym` (< 64); returns the packed coding step.
+    SFQ_HD uint64_t step(uint32_t sym, bool esc) {
+        uint16_t *fr = freq();
+        const uint32_t i = pos()[sym], g = i >> 3, k = i & 7u;
+        uint32_t f = fr[i], tot = w[72];
+        uint32_t sumf = 0;
+        const uint32_t *gs = gsum();
+#pragma unroll
+        for (uint32_t j = 0; j < 7; j++) sumf += j < g ? gs[j] : 0u;
+#pragma unroll
+        for (uint32_t j = 0; j < 7; j++) sumf += j < k ? (uint32_t)fr[(i & ~7u) + j] : 0u;
+        const uint64_t st = sfq_qstep_pack(sumf + i, f + 1u, tot + 64u, esc);
+        // update_freq (log64_ranger.hpp:69-87)
+        if (f > 65472u - 6u) {
+            if (i == 0 && f + 20u > tot) return st;
+            tot = 0;
+            for (uint32_t gg = 0; gg < 8; gg++) {
+                uint32_t s = 0;
+                for (uint32_t j = 0; j < 8; j++) { const uint32_t h = fr[8 * gg + j] >> 1; fr[8 * gg + j] = (uint16_t)h; s += h; }
+                gsum()[gg] = s;
+                tot += s;
+            }
+            f = fr[i];
+        }
+        f += 6u;
+        fr[i] = (uint16_t)f;
+        gsum()[g] += 6u;
+        w[72] = tot + 6u;
+        if (i != 0) {
+            const uint32_t count = (w[73] + 1u) & 0xffu;
+            w[73] = count;
+            if ((count & 0xfu) == 0) {
+                const uint32_t fp = fr[i - 1];
+                if (f > fp) {                               // down_level(): swap slots i and i-1
+                    uint8_t *sy = syms(), *ps = pos();
+                    const uint8_t sp = sy[i - 1];
+                    sy[i - 1] = (uint8_t)sym; sy[i] = sp;
+                    ps[sym] = (uint8_t)(i - 1); ps[sp] = (uint8_t)i;
+                    fr[i - 1] = (uint16_t)f; fr[i] = (uint16_t)fp;
+                    if (k == 0) { gsum()[g - 1] += f - fp; gsum()[g] -= f - fp; }
+                }
+            }
+        }
+        return st;
+    }
+};
+
+// Context used to code position i of a record, in closed form: b1, b2, b3 = the symbols at i-1, i-2, i-3
+// (0 before the record starts), delta = 5 + the drops max(0, b[j-1] - b[j]) summed over j <= i-1
+// (qlts.hpp:52-74, qlts.cpp:109-134; the reference's q1/q2 ping-pong is just "previous, one before").
+SFQ_HD uint32_t sfq_q_ctx_closed(int level, uint32_t i, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t delta) {
+    if (level <= 1) return (b1 | (b2 << 6)) & 0xFFFu;
+    if (level == 2) return (b1 | (b2 << 6) | (b3 << 12)) & 0xFFFFu;
+    if (i == 0) return 0;
+    const uint32_t d = delta >> 3;
+    return (b1 | ((b2 < b3 ? b3 : b2) << 6) | ((uint32_t)(b2 == b3) << 12) | ((d < 7u ? d : 7u) << 13)) & 0xFFFFu;
+}
+
+// ---------------------------------------------------------------------------- phase 2: the coder chain
+SFQ_HDN void sfq_rc_gen_chunk(const uint32_t *steps, uint32_t n, uint8_t *out, uint32_t cap, uint32_t *size_out, bool *ovf) {
+    SfqEnc rc;
+    rc.start(out, cap);
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t s = steps[i];
+        rc.encode(s & 1023u, (s >> 10) & 255u, s >> 18);
+    }
+    rc.finish();
+    *size_out = rc.out.n;
+    *ovf = rc.out.overflow();
+}
+SFQ_HDN void sfq_rc_qlt_chunk(const uint64_t *steps, const uint64_t *esteps, uint32_t n, uint8_t *out, uint32_t cap,
+                              uint32_t *size_out, bool *ovf) {
+    SfqEnc rc;
+    rc.start(out, cap);
+    uint32_t e = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t s = steps[i];
+        rc.encode((uint32_t)s & 0x3fffffu, (uint32_t)(s >> 22) & 0x1ffffu, (uint32_t)(s >> 39) & 0x3fffffu);
+        if (s >> 61) {                                                          // qlts.cpp:120-125
+            const uint64_t x = esteps[e++];
+            rc.encode((uint32_t)x & 0xffffffu, (uint32_t)(x >> 24) & 0xffffu, (uint32_t)(x >> 40));
+        }
+    }
+    rc.finish();
+    *size_out = rc.out.n;
+    *ovf = rc.out.overflow();
+}
+
+#if defined(__CUDACC__)
+// ============================================================================ gen, phase 1
+// Context of a quality / base position needs the symbols before it in the record: windows of 32
+// positions, history carried between windows in `prev`.
+__device__ __forceinline__ uint32_t sfq_ldcg32(const uint32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ uint64_t sfq_ldcg64(const uint64_t *p) { return __ldcg(reinterpret_cast<const unsigned long long *>(p)); }
+
+__global__ void __launch_bounds__(128)
+k_gen_model(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas,
+            SfqArena *arenas, uint8_t *arena_buf, SfqWorkspace ws, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c,
+            int level, uint32_t nchunks) {
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (c >= nchunks) return;
+    SfqChunkMeta *meta = &metas[c];
+    if (meta->status != SFQ_OK) return;
+    SfqArena *ar = &arenas[c];
+    uint32_t *pwpool = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
+    SfqXSave xns, xnn;
+    xns.init(pwpool, SFQ_X_NS, arena_buf + ar->off[SFQ_S_GEN_NS], ar->cap[SFQ_S_GEN_NS]);
+    xnn.init(pwpool, SFQ_X_NN, arena_buf + ar->off[SFQ_S_GEN_NN], ar->cap[SFQ_S_GEN_NN]);
+    const bool dense = level <= 1;
+    uint64_t *slots = reinterpret_cast<uint64_t *>(ws.gtab + (size_t)c * ws.gtab_stride);
+    uint32_t *dtab = reinterpret_cast<uint32_t *>(slots);
+    const uint32_t hbits = ws.hbits, hmask = (1u << hbits) - 1u;
+    const uint32_t mask = sfq_gen_mask(level);
+    const uint32_t solid = meta->solid, nrec = meta->nrec;
+    const uint64_t line0 = meta->line0;
+    uint32_t *gsteps = e2.gsteps + e2c[c].goff;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+
+    uint32_t gbase = 0;                  // bases coded so far (g_genofs_count before this window)
+    uint64_t ns_index = 0, nn_index = 0;
+    uint32_t n_byte = 0, used = 0;
+    uint32_t status = SFQ_OK, status_arg = 0;
+
+    for (uint32_t r = 0; r < nrec && status == SFQ_OK; r++) {
+        const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+        uint32_t prev = 0x007616c7u;                                           // gens.cpp:139
+        for (uint32_t w0 = 0; w0 < v.llen; w0 += 32) {
+            const uint32_t i = w0 + lane;
+            const bool active = i < v.llen;
+            const uint8_t g = active ? v.seq[i] : (uint8_t)'A';
+            const uint8_t q = active ? (i < v.qlen ? v.qual[i] : (uint8_t)40) : (uint8_t)'I';   // gens.cpp:153
+            uint32_t n = sfq_gencode(g);
+            const bool bad_n = n == 4u;
+            const unsigned errb = __ballot_sync(FULL, n > 4u);
+            if (bad_n) n = 0;
+            const bool bad_q = q == '!';
+            unsigned excb = __ballot_sync(FULL, active && (bad_n || bad_q));
+            if (errb) {                  // the bases before the offending one still produce their exceptions; nothing is kept anyway
+                const int first = __ffs(errb) - 1;
+                status = SFQ_E_BASE; status_arg = __shfl_sync(FULL, (uint32_t)g, first);
+                break;
+            }
+            // ---- exception lists, in base order (gens.cpp:91-114); rare
+            while (excb && status == SFQ_OK) {
+                const int b = __ffs(excb) - 1;
+                excb &= excb - 1;
+                const bool bn = __shfl_sync(FULL, (int)bad_n, b) != 0, bq = __shfl_sync(FULL, (int)bad_q, b) != 0;
+                const uint32_t gb = __shfl_sync(FULL, (uint32_t)g, b);
+                const uint64_t genofs = (uint64_t)gbase + (uint32_t)b + 1u;
+                if (!bn) { if (lane == 0) xnn.put(genofs - nn_index); nn_index = genofs; }
+                else {
+                    if (!n_byte) n_byte = gb;
+                    if (gb != n_byte) { status = SFQ_E_NBYTE; status_arg = gb; break; }
+                    if (!bq) { if (lane == 0) xns.put(genofs - ns_index); ns_index = genofs; }
+                }
+            }
+            if (status != SFQ_OK) break;
+            // ---- context of every lane: inclusive packed history, 2 bits per base, newest lowest
+            uint32_t h = n, t;
+            t = __shfl_up_sync(FULL, h, 1); if (lane >= 1) h |= t << 2;
+            t = __shfl_up_sync(FULL, h, 2); if (lane >= 2) h |= t << 4;
+            t = __shfl_up_sync(FULL, h, 4); if (lane >= 4) h |= t << 8;
+            t = __shfl_up_sync(FULL, h, 8); if (lane >= 8) h |= t << 16;
+            t = __shfl_up_sync(FULL, h, 1);
+            const uint32_t ctx = ((lane < 16 ? prev << (2 * lane) : 0u) | (lane ? t : 0u)) & mask;
+            prev = __shfl_sync(FULL, h, 31);
+            // ---- lanes sharing a context form a group; its first lane finds (or claims) the slot
+            const unsigned peers = __match_any_sync(FULL, active ? ctx : 0xffffffffu);
+            const uint32_t rank = __popc(peers & lt), gsize = __popc(peers);
+            uint32_t slot = 0, fv = 0x03030303u;
+            bool full = false;
+            if (active && rank == 0) {
+                if (dense) { slot = ctx; fv = sfq_ldcg32(dtab + ctx) ^ 0x03030303u; }
+                else {
+                    const uint32_t key = ctx + 1u;
+                    uint32_t hh = (ctx * 2654435761u) >> (32 - hbits);
+                    for (uint32_t probes = 0;; probes++) {
+                        uint64_t k = sfq_ldcg64(slots + hh);
+                        if (k == 0) {
+                            k = atomicCAS(reinterpret_cast<unsigned long long *>(slots + hh), 0ull, ((unsigned long long)key << 32) | 0x03030303ull);
+                            if (k == 0) { used++; slot = hh; break; }
+                        }
+                        if ((uint32_t)(k >> 32) == key) { slot = hh; fv = (uint32_t)k; break; }
+                        if (probes >= hmask) { full = true; break; }
+                        hh = (hh + 1u) & hmask;
+                    }
+                }
+            }
+            if (__any_sync(FULL, full)) { status = SFQ_E_TABLE; break; }
+            const int leader = __ffs(peers) - 1;
+            slot = __shfl_sync(FULL, slot, leader);
+            fv = __shfl_sync(FULL, fv, leader);
+            // ---- replay the group in lane order
+            const uint32_t maxrank = __reduce_max_sync(FULL, active ? rank : 0u);
+            uint32_t step = 0;
+            for (uint32_t rr = 0; rr <= maxrank; rr++) {
+                if (rank == rr) {
+                    const uint32_t f0 = fv & 0xff, f1 = (fv >> 8) & 0xff, f2 = (fv >> 16) & 0xff, f3 = fv >> 24;
+                    const uint32_t cum = (n > 0 ? f0 : 0) + (n > 1 ? f1 : 0) + (n > 2 ? f2 : 0);
+                    step = sfq_gstep_pack(cum, (fv >> (8 * n)) & 0xffu, f0 + f1 + f2 + f3);
+                    fv = sfq_b2_update(fv, n);
+                }
+                if (rr < maxrank) {
+                    const int src = __fns(peers, 0, rr + 1);                   // lane holding rank rr of my group
+                    const uint32_t nv = __shfl_sync(FULL, fv, src < 0 ? 0 : src);
+                    if (rank > rr) fv = nv;
+                }
+            }
+            if (active) {
+                gsteps[gbase + lane] = step;
+                if (rank + 1 == gsize) {
+                    if (dense) dtab[slot] = fv ^ 0x03030303u;
+                    else slots[slot] = ((uint64_t)(ctx + 1u) << 32) | fv;
+                }
+            }
+            gbase += min(32u, v.llen - w0);
+            __syncwarp();
+        }
+    }
+    used = __reduce_add_sync(FULL, used);
+    if (lane == 0) {
+        bool ovf = false;
+        ar->size[SFQ_S_GEN_NS] = xns.close(ovf);
+        ar->size[SFQ_S_GEN_NN] = xnn.close(ovf);
+        if (status == SFQ_OK && ovf) status = SFQ_E_CAP;
+        meta->n_byte = (n_byte && n_byte != 'N') ? (uint8_t)n_byte : 0;        // gens.cpp:103-104
+        meta->g_used = used;
+        if (status != SFQ_OK && meta->status == SFQ_OK) { meta->status = status; meta->status_arg = status_arg; }
+    }
+}
+
+// ============================================================================ qlt, phase 1
+// Context of position i from b[i-1], b[i-2], b[i-3] and the running sum of drops (qlts.hpp:52-74,
+// qlts.cpp:109-134).  Lanes = 32 consecutive positions of a record.
+struct SfqQWin {
+    uint32_t p1, p2, p3, dsum;           // carries from the previous window of the record
+    __device__ __forceinline__ void reset() { p1 = p2 = p3 = 0; dsum = 0; }
+    // b = this lane's symbol (0 for inactive lanes; they are the tail of the record)
+    __device__ __forceinline__ uint32_t ctx(uint32_t b, uint32_t lane, uint32_t i, int level) {
+        const unsigned FULL = 0xffffffffu;
+        uint32_t b1 = __shfl_up_sync(FULL, b, 1), b2 = __shfl_up_sync(FULL, b, 2), b3 = __shfl_up_sync(FULL, b, 3);
+        if (lane < 1) b1 = p1;
+        if (lane < 2) b2 = lane == 0 ? p2 : p1;
+        if (lane < 3) b3 = lane == 0 ? p3 : lane == 1 ? p2 : p1;
+        uint32_t e = b2 > b1 ? b2 - b1 : 0u, t;          // drop paid when position i-1 was coded
+        t = __shfl_up_sync(FULL, e, 1);  if (lane >= 1)  e += t;
+        t = __shfl_up_sync(FULL, e, 2);  if (lane >= 2)  e += t;
+        t = __shfl_up_sync(FULL, e, 4);  if (lane >= 4)  e += t;
+        t = __shfl_up_sync(FULL, e, 8);  if (lane >= 8)  e += t;
+        t = __shfl_up_sync(FULL, e, 16); if (lane >= 16) e += t;
+        const uint32_t delta = 5u + dsum + e;
+        // carries for the next window: positions 31, 30, 29 of this one (lane 0 of the next window adds
+        // the drop of position 31 itself)
+        const uint32_t n1 = __shfl_sync(FULL, b, 31), n2 = __shfl_sync(FULL, b, 30), n3 = __shfl_sync(FULL, b, 29);
+        const uint32_t e31 = __shfl_sync(FULL, e, 31);
+        dsum += e31;
+        p1 = n1; p2 = n2; p3 = n3;
+        return sfq_q_ctx_closed(level, i, b1, b2, b3, delta);
+    }
+};
+
+__global__ void __launch_bounds__(128)
+k_qlt_keys(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas,
+           SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, int level, uint32_t nchunks) {
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (c >= nchunks) return;
+    const SfqChunkMeta *meta = &metas[c];
+    if (meta->status != SFQ_OK) return;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t solid = meta->solid, nrec = meta->nrec;
+    const uint64_t line0 = meta->line0;
+    uint16_t *qkey = e2.qkey + e2c[c].qoff;
+    uint8_t *qb = e2.qb + e2c[c].qoff;
+    uint32_t *cnt = e2.cnt + (size_t)c * SFQ_Q_CNT;
+    uint32_t qbase = 0, nesc = 0;
+    for (uint32_t r = 0; r < nrec; r++) {
+        const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+        SfqQWin win; win.reset();
+        for (uint32_t w0 = 0; w0 < v.qlen; w0 += 32) {
+            const uint32_t i = w0 + lane;
+            const bool active = i < v.qlen;
+            const uint32_t b = active ? (uint32_t)(uint8_t)(v.qual[i] - '!') : 0u;
+            const uint32_t ctx = win.ctx(b, lane, i, level);
+            nesc += __popc(__ballot_sync(FULL, active && b >= 63u));
+            const unsigned peers = __match_any_sync(FULL, active ? ctx : 0xffffffffu);
+            if (active) {
+                qkey[qbase + lane] = (uint16_t)ctx;
+                qb[qbase + lane] = (uint8_t)b;
+                if ((peers & ((1u << lane) - 1u)) == 0) cnt[ctx] = sfq_ldcg32(cnt + ctx) + __popc(peers);
+            }
+            qbase += min(32u, v.qlen - w0);
+            __syncwarp();
+        }
+    }
+    if (lane == 0) cnt[SFQ_Q_NCTX] = nesc;
+}
+
+// One CTA per chunk: histogram -> cursors (in place) + the segment list.
+__global__ void __launch_bounds__(256)
+k_qlt_scan(SfqChunkMeta *metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, uint32_t nchunks) {
+    const uint32_t c = blockIdx.x;
+    SfqChunkMeta *meta = &metas[c];
+    if (meta->status != SFQ_OK) return;
+    uint32_t *cnt = e2.cnt + (size_t)c * SFQ_Q_CNT;
+    constexpr uint32_t PER = SFQ_Q_NCTX / 256;
+    const uint32_t lo = threadIdx.x * PER;
+    uint32_t s = 0, ks = 0, kb = 0;
+    for (uint32_t k = 0; k < PER; k++) {
+        const uint32_t v = cnt[lo + k];
+        s += v;
+        if (v >= SFQ_SEG_BIG) kb++; else if (v) ks++;
+    }
+    __shared__ uint32_t sh[3][256];
+    __shared__ uint32_t base[2];
+    sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = ks; sh[2][threadIdx.x] = kb;
+    __syncthreads();
+    if (threadIdx.x < 3) {               // three tiny serial scans, one thread each
+        uint32_t run = 0;
+        uint32_t *a = sh[threadIdx.x];
+        for (int k = 0; k < 256; k++) { const uint32_t v = a[k]; a[k] = run; run += v; }
+        const uint32_t nesc = cnt[SFQ_Q_NCTX];
+        if (threadIdx.x == 1) base[0] = atomicAdd(e2.ctr + 0, run);
+        if (threadIdx.x == 2) base[1] = atomicAdd(e2.ctr + 1, run + (nesc ? 1u : 0u)) + (nesc ? 1u : 0u);
+        if (threadIdx.x == 1) meta->q_used = run;           // + big ones, added below
+        if (threadIdx.x == 0) {
+            meta->extra_hi = nesc;
+            if (nesc > e2c[c].ecap && meta->status == SFQ_OK) meta->status = SFQ_E_CAP;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) atomicAdd(&meta->q_used, sh[2][255] + kb);
+    if (threadIdx.x == 0) {
+        const uint32_t nesc = cnt[SFQ_Q_NCTX];
+        if (nesc) {                      // the escape model's segment goes first among the big ones
+            SfqSeg sg; sg.chunk = c; sg.start = 0; sg.count = nesc; sg.flags = 1;
+            e2.segs[e2.seg_cap - 1 - (base[1] - 1u)] = sg;
+        }
+        cnt[SFQ_Q_NCTX] = 0;             // becomes the escape cursor
+    }
+    uint32_t run = sh[0][threadIdx.x], is = base[0] + sh[1][threadIdx.x], ib = base[1] + sh[2][threadIdx.x];
+    for (uint32_t k = 0; k < PER; k++) {
+        const uint32_t v = cnt[lo + k];
+        cnt[lo + k] = run;
+        if (v) {
+            SfqSeg sg; sg.chunk = c; sg.start = run; sg.count = v; sg.flags = 0;
+            if (v >= SFQ_SEG_BIG) e2.segs[e2.seg_cap - 1 - ib++] = sg; else e2.segs[is++] = sg;
+        }
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_qlt_scatter(const SfqChunkMeta *__restrict__ metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, uint32_t nchunks) {
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (c >= nchunks) return;
+    const SfqChunkMeta *meta = &metas[c];
+    if (meta->status != SFQ_OK) return;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint16_t *qkey = e2.qkey + e2c[c].qoff;
+    const uint8_t *qb = e2.qb + e2c[c].qoff;
+    uint32_t *sorted = e2.sorted + e2c[c].qoff;
+    uint32_t *esorted = e2.esorted + e2c[c].eoff;
+    uint32_t *cur = e2.cnt + (size_t)c * SFQ_Q_CNT;
+    const uint32_t n = meta->nquals;
+    uint32_t ecur = 0;
+    for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        const bool active = p < n;
+        const uint32_t ctx = active ? qkey[p] : 0xffffffffu;
+        const uint32_t b = active ? qb[p] : 0u;
+        const unsigned peers = __match_any_sync(FULL, ctx);
+        const uint32_t rank = __popc(peers & lt);
+        uint32_t at = 0;
+        if (active && rank == 0) { at = sfq_ldcg32(cur + ctx); cur[ctx] = at + __popc(peers); }
+        at = __shfl_sync(FULL, at, __ffs(peers) - 1) + rank;
+        if (active) sorted[at] = p | ((b < 63u ? b : 63u) << 24);
+        const unsigned eb = __ballot_sync(FULL, active && b >= 63u);
+        if (active && b >= 63u) esorted[ecur + __popc(eb & lt)] = p | (b << 24);
+        ecur += __popc(eb);
+        __syncwarp();
+    }
+}
+
+// One thread per context segment (handed out dynamically, long ones first): the whole model lives in
+// shared memory for the lifetime of the segment.
+#define SFQ_QM_THREADS 128
+__global__ void __launch_bounds__(SFQ_QM_THREADS)
+k_qlt_model(const SfqChunkMeta *__restrict__ metas, SfqWorkspace ws, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, uint32_t chunk0) {
+    __shared__ uint32_t models[SFQ_QM_THREADS * SFQ_L64R_WORDS];
+    SfqL64Replay m;
+    m.w = models + threadIdx.x * SFQ_L64R_WORDS;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nsmall = e2.ctr[0], nbig = e2.ctr[1], total = nsmall + nbig;
+    bool have = false, done = false;
+    const uint32_t *src = nullptr;
+    uint64_t *dst = nullptr;
+    uint32_t p = 0, end = 0;
+    (void)chunk0;
+    for (;;) {
+        const unsigned need = __ballot_sync(FULL, !have && !done);
+        if (need) {
+            uint32_t first = 0;
+            if (lane == 0) first = atomicAdd(e2.ctr + 2, (uint32_t)__popc(need));
+            first = __shfl_sync(FULL, first, 0);
+            if (!have && !done) {
+                const uint32_t j = first + __popc(need & ((1u << lane) - 1u));
+                if (j >= total) done = true;
+                else {
+                    const SfqSeg sg = j < nbig ? e2.segs[e2.seg_cap - 1 - j] : e2.segs[j - nbig];
+                    const SfqEnc2Chunk ec = e2c[sg.chunk];
+                    if (sg.flags & 1u) {
+                        // escape symbols of the chunk through its 256-symbol model (qlts.cpp:124, power_ranger.hpp:93-106)
+                        if (metas[sg.chunk].status == SFQ_OK) {
+                            SfqPower ex; ex.m = ws.pw + ((size_t)sg.chunk * SFQ_PW_PER_CHUNK + SFQ_PW_QEX) * SFQ_PW_WORDS;
+                            SfqStepSink sink; sink.out = e2.esteps + ec.eoff;
+                            const uint32_t *es = e2.esorted + ec.eoff;
+                            for (uint32_t k = 0; k < sg.count; k++) ex.put(sink, es[k] >> 24);
+                        }
+                    } else {
+                        m.reset();
+                        src = e2.sorted + ec.qoff; dst = e2.qsteps + ec.qoff;
+                        p = sg.start; end = sg.start + sg.count;
+                        have = true;
+                    }
+                }
+            }
+        }
+        if (__all_sync(FULL, done)) break;
+        if (have) {
+            const uint32_t n = min(end - p, 8u);
+            for (uint32_t k = 0; k < n; k++) {
+                const uint32_t e = src[p + k];
+                const uint32_t b = e >> 24;
+                dst[e & 0xffffffu] = m.step(b, false);
+            }
+            p += n;
+            if (p == end) have = false;
+        }
+    }
+}
+
+// The escape flag of a position is known from the symbol alone; folding it in here keeps k_qlt_model's
+// step() free of it.
+__global__ void __launch_bounds__(256)
+k_qlt_mark_escapes(const SfqChunkMeta *__restrict__ metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, uint32_t nchunks) {
+    const uint32_t c = blockIdx.x;
+    if (c >= nchunks || metas[c].status != SFQ_OK || metas[c].extra_hi == 0) return;
+    const uint32_t *es = e2.esorted + e2c[c].eoff;
+    uint64_t *qs = e2.qsteps + e2c[c].qoff;
+    for (uint32_t k = threadIdx.x; k < metas[c].extra_hi; k += blockDim.x) qs[es[k] & 0xffffffu] |= 1ull << 61;
+}
+
+// ============================================================================ phase 2
+// kind: 0 = gen, 1 = qlt.  One thread per chunk-stream.
+__global__ void __launch_bounds__(32)
+k_rc_encode(SfqChunkMeta *metas, SfqArena *arenas, uint8_t *arena_buf, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c,
+            uint32_t nchunks, uint32_t lanes, int kind) {
+    const uint32_t c = blockIdx.x * lanes + threadIdx.x;
+    if (threadIdx.x >= lanes || c >= nchunks) return;
+    SfqChunkMeta *m = &metas[c];
+    if (m->status != SFQ_OK) return;
+    SfqArena *ar = &arenas[c];
+    bool ovf = false;
+    if (kind == 0)
+        sfq_rc_gen_chunk(e2.gsteps + e2c[c].goff, m->nbases, arena_buf + ar->off[SFQ_S_GEN], ar->cap[SFQ_S_GEN], &ar->size[SFQ_S_GEN], &ovf);
+    else
+        sfq_rc_qlt_chunk(e2.qsteps + e2c[c].qoff, e2.esteps + e2c[c].eoff, m->nquals, arena_buf + ar->off[SFQ_S_QLT],
+                         ar->cap[SFQ_S_QLT], &ar->size[SFQ_S_QLT], &ovf);
+    if (ovf) atomicCAS(&m->status, (uint32_t)SFQ_OK, (uint32_t)SFQ_E_CAP);
+}
+#endif  // __CUDACC__

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include "sfq_streams.cuh"
 #include "sfq_qlt_group.cuh"
+#include "sfq_encode2.cuh"
 #include "sfq_plan.cuh"
 #include "sfq_container.h"
 
@@ -130,13 +131,6 @@ __global__ void k_chunk_plan(const uint8_t *__restrict__ text, const uint64_t *_
     if (c >= nchunks) return;
     sfq_plan_chunk(text, ls, r0[c], r1[c], &metas[c]);
 }
-
-// Per-wave workspace of the coders: chunk w of the wave owns slice w of every table.
-struct SfqWorkspace {
-    uint8_t  *gtab;  uint64_t gtab_stride;  uint32_t hbits;     // base-context tables
-    uint32_t *qtab;  uint64_t qtab_words;   uint32_t cbits;     // quality-context tables (hashed)
-    uint32_t *pw;                                                // 256-symbol model pools
-};
 
 // One thread = one chunk-stream.  ROLE 0 = gen (+gen.Ns/Nn), 1 = qlt, 2 = rec (+rec.x, usr.*); the three
 // roles of a wave are separate kernels launched on three streams so they overlap on the device and

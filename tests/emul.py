@@ -23,6 +23,7 @@ def lib():
         L.sfq_emul_decompress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t),
                                           C.POINTER(C.c_uint32)]
         L.sfq_emul_free.argtypes = [C.c_void_p]
+        L.sfq_emul_set_two_phase.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -31,8 +32,9 @@ class EmulError(RuntimeError):
     pass
 
 
-def compress(data: bytes, level: int, chunk_bytes: int = 1 << 20) -> bytes:
+def compress(data: bytes, level: int, chunk_bytes: int = 1 << 20, two_phase: bool = False) -> bytes:
     out, n, st = C.POINTER(C.c_uint8)(), C.c_size_t(), C.c_uint32()
+    lib().sfq_emul_set_two_phase(1 if two_phase else 0)
     if lib().sfq_emul_compress(data, len(data), level, chunk_bytes, C.byref(out), C.byref(n), C.byref(st)):
         raise EmulError(f"status {st.value}")
     r = C.string_at(out, n.value)

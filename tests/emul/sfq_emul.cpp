@@ -6,6 +6,8 @@
 #include <vector>
 
 #include "../../slimfastq_b200/csrc/sfq_streams.cuh"
+#include "../../slimfastq_b200/csrc/sfq_encode2.cuh"
+#include <map>
 #include "../../slimfastq_b200/csrc/sfq_plan.cuh"
 #include "../../slimfastq_b200/csrc/sfq_container.h"
 #include "../../slimfastq_b200/csrc/sfq_layout.h"
@@ -19,6 +21,71 @@ static std::vector<uint8_t> padded(const uint8_t *p, size_t n) {
     std::vector<uint8_t> v(n + 64, 0);
     if (n) memcpy(v.data(), p, n);
     return v;
+}
+
+// The two-phase encoder's algorithm, run sequentially: coding steps of every symbol first (gen: table walk;
+// qlt: positions grouped by context, one replay model per context, escapes through the 256-symbol model),
+// then the coder chain over the steps.  Shares sfq_q_ctx_closed, SfqL64Replay, the step packing and
+// sfq_rc_*_chunk with the kernels; the warp choreography itself is checked on the GPU.
+static int g_two_phase = 0;
+extern "C" void sfq_emul_set_two_phase(int on) { g_two_phase = on; }
+
+static void emul_gen_two_phase(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *m, int level, void *gt, uint32_t hbits,
+                               uint8_t *arena, SfqArena *ar) {
+    SfqGenTable tab; tab.init(gt, hbits, level <= 1);
+    const uint32_t mask = sfq_gen_mask(level);
+    std::vector<uint32_t> steps;
+    for (uint32_t r = 0; r < m->nrec; r++) {
+        const SfqRecView v = sfq_rec_view(text, ls, m->line0, r, m->solid);
+        uint32_t last = 0x007616c7u;
+        for (uint32_t i = 0; i < v.llen; i++) {
+            uint32_t n = sfq_gencode(v.seq[i]);
+            if (n > 3) n = 0;
+            last &= mask;
+            uint32_t fv; const uint32_t slot = tab.find(last, fv);
+            const uint32_t f0 = fv & 0xff, f1 = (fv >> 8) & 0xff, f2 = (fv >> 16) & 0xff, f3 = fv >> 24;
+            steps.push_back(sfq_gstep_pack((n > 0 ? f0 : 0) + (n > 1 ? f1 : 0) + (n > 2 ? f2 : 0), (fv >> (8 * n)) & 0xff, f0 + f1 + f2 + f3));
+            tab.store(slot, last, sfq_b2_update(fv, n));
+            last = (last << 2) | n;
+        }
+    }
+    bool ovf = false;
+    sfq_rc_gen_chunk(steps.data(), (uint32_t)steps.size(), arena + ar->off[SFQ_S_GEN], ar->cap[SFQ_S_GEN], &ar->size[SFQ_S_GEN], &ovf);
+    if (ovf && m->status == SFQ_OK) m->status = SFQ_E_CAP;
+}
+
+static void emul_qlt_two_phase(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *m, int level, uint32_t *pw,
+                               uint8_t *arena, SfqArena *ar) {
+    std::vector<uint32_t> key, sym;
+    for (uint32_t r = 0; r < m->nrec; r++) {
+        const SfqRecView v = sfq_rec_view(text, ls, m->line0, r, m->solid);
+        uint32_t delta = 5;
+        for (uint32_t i = 0; i < v.qlen; i++) {
+            auto at = [&](int64_t k) -> uint32_t { return k < 0 ? 0u : (uint32_t)(uint8_t)(v.qual[k] - '!'); };
+            const uint32_t b1 = at((int64_t)i - 1), b2 = at((int64_t)i - 2), b3 = at((int64_t)i - 3);
+            if (i >= 1 && b2 > b1) delta += b2 - b1;
+            key.push_back(sfq_q_ctx_closed(level, i, b1, b2, b3, delta));
+            sym.push_back(at(i));
+        }
+    }
+    std::map<uint32_t, std::vector<uint32_t>> groups;
+    for (uint32_t p = 0; p < key.size(); p++) groups[key[p]].push_back(p);
+    std::vector<uint64_t> steps(key.size()), esteps;
+    for (auto &g : groups) {
+        uint32_t words[SFQ_L64R_WORDS];
+        SfqL64Replay mod; mod.w = words; mod.reset();
+        for (uint32_t p : g.second) steps[p] = mod.step(sym[p] < 63 ? sym[p] : 63, false);
+    }
+    uint32_t extra = 0;
+    for (uint32_t p = 0; p < key.size(); p++) if (sym[p] >= 63) extra++;
+    esteps.resize(extra + 1);
+    SfqPower ex; ex.m = pw + (size_t)SFQ_PW_QEX * SFQ_PW_WORDS;
+    SfqStepSink sink; sink.out = esteps.data();
+    for (uint32_t p = 0; p < key.size(); p++) if (sym[p] >= 63) { ex.put(sink, sym[p]); steps[p] |= 1ull << 61; }
+    bool ovf = false;
+    sfq_rc_qlt_chunk(steps.data(), esteps.data(), (uint32_t)steps.size(), arena + ar->off[SFQ_S_QLT], ar->cap[SFQ_S_QLT], &ar->size[SFQ_S_QLT], &ovf);
+    m->extra_hi = extra;
+    if (ovf && m->status == SFQ_OK) m->status = SFQ_E_CAP;
 }
 
 extern "C" int sfq_emul_compress(const uint8_t *text_in, size_t n, int level, uint64_t chunk_bytes,
@@ -53,6 +120,12 @@ extern "C" int sfq_emul_compress(const uint8_t *text_in, size_t n, int level, ui
             uint32_t *pw = (uint32_t *)calloc(1, sfq_pwpool_bytes());
             m.status = 0;
             sfq_gen_encode_chunk(text, ls.data(), &m, level, gt, hbits, pw, arena.data(), &ar);
+            if (g_two_phase) {      // gen stream and qlt stream again, the two-phase way, over fresh tables
+                void *gt2 = calloc(1, sfq_gtable_bytes(level, hbits));
+                emul_gen_two_phase(text, ls.data(), &m, level, gt2, hbits, arena.data(), &ar);
+                free(gt2);
+                emul_qlt_two_phase(text, ls.data(), &m, level, pw, arena.data(), &ar);
+            } else
             sfq_qlt_encode_chunk(text, ls.data(), &m, level, qt, pw, arena.data(), &ar);
             sfq_rec_encode_chunk(text, ls.data(), &m, pw, arena.data(), &ar);
             free(gt); free(qt); free(pw);

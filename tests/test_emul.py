@@ -37,3 +37,15 @@ def test_reference_samples(oracle, path):
         blob = emul.compress(data, level, chunk)
         check_container_against_oracle(oracle, data, blob, level)
         assert emul.decompress(blob) == oracle.decode(oracle.encode(data, level)) or chunk != 1 << 40
+
+
+def test_two_phase_encoder_algorithm(oracle):
+    """Coding steps first (per-context replay models), coder chain second: same bytes as the oracle."""
+    cases = [(synth.illumina(4000), 3), (synth.illumina(2500, bins8=True), 4), (synth.ont(30), 3), (synth.illumina(2500), 1),
+             (synth.illumina(2500), 2)]
+    cases += [(d, 3) for d in synth.edge_cases().values()]
+    for p in SAMPLES:
+        cases.append((open(p, "rb").read(), 3))
+    for data, level in cases:
+        blob = emul.compress(data, level, 1 << 19, two_phase=True)
+        check_container_against_oracle(oracle, data, blob, level)
