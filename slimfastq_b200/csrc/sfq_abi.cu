@@ -60,13 +60,14 @@ struct sfq_ctx {
     uint32_t max_resident = 0;
     uint32_t lanes = 4;                     // chunk-streams per gen/rec coder warp (SFQ_LANES)
     int sm_count = 148;
+    uint32_t rc_lanes = 8;                  // chunk-streams per warp of the coder-chain kernel (SFQ_RC_LANES)
     cudaEvent_t ev[EV_COUNT]{};
     std::vector<cudaEvent_t> wave_ev;       // 10 per wave: clear start, code start, code end, pack end, then start/end of gen, qlt, rec
     // device buffers (grow-only, reused across calls)
     DevBuf text, out, tiles, tile_prefix, lines, scalars, rec_begin, r0, r1, metas, arenas, arena_buf,
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
-           e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks;
+           e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff;
     bool serial_encoder = false;            // SFQ_ENC_SERIAL=1: single-pass coders (one chain per chunk-stream) for A/B runs
     HostBuf h_out, h_small;
     void release_all() {
@@ -74,7 +75,7 @@ struct sfq_ctx {
                          &arenas, &arena_buf, &blob_off, &gtab, &qtab, &pw, &dchunks, &bhdrs, &bases, &quals,
                          &hdrs, &rec_chunk, &t_llen, &t_qlen, &t_hlen, &t_pfg, &t_pfq, &t_boff, &t_qoff,
                          &t_hoff, &t_ooff, &e2_gsteps, &e2_qkey, &e2_qb, &e2_sorted, &e2_qsteps, &e2_cnt, &e2_esorted,
-                         &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks};
+                         &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks, &rec_qoff};
         for (DevBuf *b : all) b->release();
         h_out.release(); h_small.release();
     }
@@ -214,7 +215,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     CK(cudaMemcpyAsync(ctx->r0.p, r0.data(), nchunks * 8ull, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->r1.p, r1.data(), nchunks * 8ull, cudaMemcpyHostToDevice, s));
     SfqChunkMeta *d_metas = ctx->metas.as<SfqChunkMeta>();
-    k_chunk_plan<<<(nchunks + 63) / 64, 64, 0, s>>>(d_text, d_ls, ctx->r0.as<uint64_t>(), ctx->r1.as<uint64_t>(), d_metas, nchunks); LAUNCHED();
+    CK(ctx->rec_qoff.ensure(nrec_total * 4 + 64));
+    k_chunk_plan<<<(nchunks + 63) / 64, 64, 0, s>>>(d_text, d_ls, ctx->r0.as<uint64_t>(), ctx->r1.as<uint64_t>(), d_metas, nchunks, ctx->rec_qoff.as<uint32_t>()); LAUNCHED();
     std::vector<SfqChunkMeta> metas(nchunks);
     CK(cudaMemcpyAsync(metas.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[EV_PLAN], s));
@@ -281,8 +283,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         CK(ctx->arena_buf.ensure(wave_arena_max + 64));
         SfqEnc2Ws e2{};
         if (two_phase) {
-            CK(ctx->e2_gsteps.ensure(wave_nb * 4 + 64)); CK(ctx->e2_qkey.ensure(wave_nq * 2 + 64)); CK(ctx->e2_qb.ensure(wave_nq + 64));
-            CK(ctx->e2_sorted.ensure(wave_nq * 4 + 64)); CK(ctx->e2_qsteps.ensure(wave_nq * 8 + 64)); CK(ctx->e2_cnt.ensure((uint64_t)R * SFQ_Q_CNT * 4));
+            CK(ctx->e2_gsteps.ensure(wave_nb * 4 + 256)); CK(ctx->e2_qkey.ensure(wave_nq * 2 + 64)); CK(ctx->e2_qb.ensure(wave_nq + 64));
+            CK(ctx->e2_sorted.ensure(wave_nq * 4 + 64)); CK(ctx->e2_qsteps.ensure(wave_nq * 8 + 256)); CK(ctx->e2_cnt.ensure((uint64_t)R * SFQ_Q_CNT * 4));
             CK(ctx->e2_esorted.ensure(wave_ne * 4 + 64)); CK(ctx->e2_esteps.ensure(wave_ne * 8 + 64)); CK(ctx->e2_segs.ensure(wave_seg * sizeof(SfqSeg)));
             CK(ctx->e2_ctr.ensure(64)); CK(ctx->e2_chunks.ensure(nchunks * sizeof(SfqEnc2Chunk)));
             CK(cudaMemcpyAsync(ctx->e2_chunks.p, e2c.data(), nchunks * sizeof(SfqEnc2Chunk), cudaMemcpyHostToDevice, s));
@@ -316,7 +318,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
                 if (two_phase) {
                     k_gen_model<<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); LAUNCHED();
-                    k_rc_encode<<<(nc + 31) / 32, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, 32, 0); LAUNCHED();
+                    k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes); LAUNCHED();
                 } else {
                     k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
                 }
@@ -324,12 +326,14 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], ctx->side[0]));
                 if (two_phase) {
                     cudaStream_t q = ctx->side[0];
-                    k_qlt_keys<<<nwarp_blocks, 128, 0, q>>>(d_text, d_ls, d_metas + c0, e2, d_e2c, level, nc); LAUNCHED();
+                    uint32_t wave_max_nrec = 1;
+                    for (uint32_t c = c0; c < c0 + nc; c++) wave_max_nrec = std::max(wave_max_nrec, metas[c].nrec);
+                    k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc); LAUNCHED();
                     k_qlt_scan<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
                     k_qlt_scatter<<<nwarp_blocks, 128, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
                     k_qlt_model<<<ctx->sm_count * 4, SFQ_QM_THREADS, 0, q>>>(d_metas + c0, ws_at(ws, c0), e2, d_e2c, c0); LAUNCHED();
                     k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
-                    k_rc_encode<<<(nc + 31) / 32, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, 32, 1); LAUNCHED();
+                    k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes); LAUNCHED();
                 } else {
                     k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, ctx->side[0]>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
                 }
@@ -600,6 +604,7 @@ int sfq_create(sfq_ctx **out, int device) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
+    if (const char *e = getenv("SFQ_RC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->rc_lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_SERIAL")) ctx->serial_encoder = atoi(e) != 0;
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }

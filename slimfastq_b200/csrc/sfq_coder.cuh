@@ -107,6 +107,18 @@ struct SfqEnc {
             low <<= 8;
         }
     }
+    // encode() with the quotient r = range / totFreq supplied by the caller (reciprocal multiply)
+    SFQ_HD void encode_scaled(uint32_t cum, uint32_t freq, uint32_t r) {
+        low += (uint32_t)(cum * r);
+        range = r * freq;
+        while (range < SFQ_RC_TOP) {
+            if ((low ^ (low + range)) & (0xffULL << 56))
+                range = (((uint32_t)low) | (SFQ_RC_TOP - 1)) - (uint32_t)low;
+            out.put((uint8_t)(low >> 56));
+            range <<= 8;
+            low <<= 8;
+        }
+    }
     SFQ_HD void finish() {
         for (int i = 0; i < 8; i++) { out.put((uint8_t)(low >> 56)); low <<= 8; }
         out.flush();
@@ -385,7 +397,81 @@ struct SfqAModel {
     }
 };
 typedef SfqAModel<64, 6, 65472, 20> SfqLog64;
-typedef SfqAModel<256, 14, 32736, 256> SfqPower;
+
+// PowerRanger (power_ranger.hpp:36-131: 256 symbols, STEP 14, MAX_FREQ 32736) for one thread, in a
+// layout that needs no scan: the reference finds a symbol's slot and its cumulative frequency by
+// walking the slots (on average 128 of them for header text and number bytes); here an inverse map
+// gives the slot and per-16-slot group sums give the cumulative frequency in <= 15 + 15 additions.
+// Zeroed memory is the start state (symbols stored XOR slot index, positions XOR symbol).
+//   words   0..255  slots  [sym ^ index : 8 << 16 | freq : 16]
+//   words 256..319  inverse map, one byte per symbol: slot ^ symbol
+//   words 320..335  gsum[16]: sum of freq over slots 16g..16g+15
+//   word  336       total          word 337  count (power_ranger.hpp:43-45)
+struct SfqPower {
+    uint32_t *m;
+    SFQ_HD static uint32_t freq_of(uint32_t s) { return s & 0xffffu; }
+    SFQ_HD static uint32_t sym_of(uint32_t s, uint32_t i) { return ((s >> 16) & 0xffu) ^ (i & 0xffu); }
+    SFQ_HD static uint32_t pack(uint32_t sym, uint32_t i, uint32_t f) { return (((sym ^ i) & 0xffu) << 16) | f; }
+    SFQ_HD uint8_t *inv() const { return reinterpret_cast<uint8_t *>(m + 256); }
+    SFQ_HD uint32_t *gsum() const { return m + 320; }
+
+    // update_freq (power_ranger.hpp:68-86) for slot i holding `sym` with frequency f
+    SFQ_HD void update(uint32_t i, uint32_t f, uint32_t sym, uint32_t tot) {
+        if (f > 32736u - 14u) {
+            if (i == 0 && f + 256u > tot) return;
+            tot = 0;
+            for (uint32_t g = 0; g < 16; g++) {                    // normalize(): halve every slot
+                uint32_t gs = 0;
+                for (uint32_t k = 16 * g; k < 16 * g + 16; k++) { const uint32_t sk = m[k], fk = freq_of(sk) >> 1; m[k] = (sk & 0xffff0000u) | fk; gs += fk; }
+                gsum()[g] = gs;
+                tot += gs;
+            }
+            f = freq_of(m[i]);
+        }
+        f += 14u;
+        m[i] = pack(sym, i, f);
+        gsum()[i >> 4] += 14u;
+        m[336] = tot + 14u;
+        if (i == 0) return;                                        // `++count` is not evaluated for slot 0
+        const uint32_t count = (m[337] + 1u) & 0xffu;
+        m[337] = count;
+        if ((count & 0xfu) == 0) {
+            const uint32_t b = m[i - 1], fb = freq_of(b);
+            if (f > fb) {                                          // swap slots i and i-1
+                const uint32_t symb = sym_of(b, i - 1);
+                m[i] = pack(symb, i, fb);
+                m[i - 1] = pack(sym, i - 1, f);
+                inv()[sym] = (uint8_t)((i - 1) ^ sym);
+                inv()[symb] = (uint8_t)(i ^ symb);
+                if ((i & 15u) == 0) { gsum()[(i >> 4) - 1] += f - fb; gsum()[i >> 4] -= f - fb; }
+            }
+        }
+    }
+    template <class RC> SFQ_HD void put(RC &rc, uint32_t sym) {    // power_ranger.hpp:93-106
+        const uint32_t i = (uint32_t)inv()[sym] ^ sym, g = i >> 4;
+        const uint32_t f = freq_of(m[i]), tot = m[336];
+        uint32_t sumf = 0;
+        for (uint32_t j = 0; j < g; j++) sumf += gsum()[j];
+        for (uint32_t k = 16 * g; k < i; k++) sumf += freq_of(m[k]);
+        rc.encode(sumf + i, f + 1u, tot + 256u);
+        update(i, f, sym, tot);
+    }
+    SFQ_HD uint32_t get(SfqDec &rc) {                              // power_ranger.hpp:108-130
+        const uint32_t tot = m[336];
+        const uint32_t prob = rc.get_freq(tot + 256u);
+        uint32_t cum = 0, g = 0;
+        for (; g < 15; g++) { const uint32_t t = gsum()[g] + 16u; if (cum + t <= prob) cum += t; else break; }
+        uint32_t i = 16 * g, f;
+        for (;; i++) {
+            f = freq_of(m[i]);
+            if (i < 16 * g + 15 && cum + f + 1u <= prob) cum += f + 1u; else break;   // the last slot also catches a corrupt stream
+        }
+        const uint32_t sym = sym_of(m[i], i);
+        rc.decode(cum, f + 1u);
+        update(i, f, sym, tot);
+        return sym;
+    }
+};
 
 // PowerRangerU: variable-length u64 over 14 consecutive 256-symbol models (power_ranger.hpp:133-192)
 struct SfqPowerU {

@@ -47,7 +47,7 @@ enum {
 
 // Sizes of the per-chunk model pools.
 #define SFQ_L64_WORDS   64u            // one quality context  = 64 packed slots = 256 B
-#define SFQ_PW_WORDS    256u           // one 256-symbol model = 256 packed slots = 1 KiB
+#define SFQ_PW_WORDS    340u           // one 256-symbol model: 256 slots + inverse map + group sums (SfqPower)
 // 256-symbol model instances per chunk:
 //   header fields: 66 x (type, str, num[14])            recs.hpp:42-48
 //   7 exception streams x (num[14], str)                xfile.hpp:41-42
@@ -57,7 +57,7 @@ enum {
 #define SFQ_PW_X_BASE     (66u * 16u)
 #define SFQ_PW_PER_X      15u
 #define SFQ_PW_QEX        (SFQ_PW_X_BASE + 7u * SFQ_PW_PER_X)
-#define SFQ_PW_PER_CHUNK  (SFQ_PW_QEX + 1u)      // 1162 models = 1.13 MiB per resident chunk
+#define SFQ_PW_PER_CHUNK  (SFQ_PW_QEX + 1u)      // 1162 models = 1.5 MiB per resident chunk
 // exception-stream slot -> stream id
 #define SFQ_X_NS 0
 #define SFQ_X_NN 1

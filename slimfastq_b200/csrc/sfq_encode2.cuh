@@ -185,6 +185,7 @@ SFQ_HDN void sfq_rc_qlt_chunk(const uint64_t *steps, const uint64_t *esteps, uin
 __device__ __forceinline__ uint32_t sfq_ldcg32(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ uint64_t sfq_ldcg64(const uint64_t *p) { return __ldcg(reinterpret_cast<const unsigned long long *>(p)); }
 
+#define SFQ_GM_BATCH 8                 // windows whose text and table slots are requested together
 __global__ void __launch_bounds__(128)
 k_gen_model(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas,
             SfqArena *arenas, uint8_t *arena_buf, SfqWorkspace ws, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c,
@@ -217,98 +218,128 @@ k_gen_model(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, S
 
     for (uint32_t r = 0; r < nrec && status == SFQ_OK; r++) {
         const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+        if (r + 2 < nrec && lane < 4) sfq_prefetch(text + ls[line0 + 4ull * (r + 2)] + 128u * lane);   // the record after next
         uint32_t prev = 0x007616c7u;                                           // gens.cpp:139
-        for (uint32_t w0 = 0; w0 < v.llen; w0 += 32) {
-            const uint32_t i = w0 + lane;
-            const bool active = i < v.llen;
-            const uint8_t g = active ? v.seq[i] : (uint8_t)'A';
-            const uint8_t q = active ? (i < v.qlen ? v.qual[i] : (uint8_t)40) : (uint8_t)'I';   // gens.cpp:153
-            uint32_t n = sfq_gencode(g);
-            const bool bad_n = n == 4u;
-            const unsigned errb = __ballot_sync(FULL, n > 4u);
-            if (bad_n) n = 0;
-            const bool bad_q = q == '!';
-            unsigned excb = __ballot_sync(FULL, active && (bad_n || bad_q));
-            if (errb) {                  // the bases before the offending one still produce their exceptions; nothing is kept anyway
-                const int first = __ffs(errb) - 1;
-                status = SFQ_E_BASE; status_arg = __shfl_sync(FULL, (uint32_t)g, first);
-                break;
+        for (uint32_t w0 = 0; w0 < v.llen && status == SFQ_OK; w0 += 32 * SFQ_GM_BATCH) {
+            // ---- the batch's text: all loads in flight together
+            uint32_t gg[SFQ_GM_BATCH], qq[SFQ_GM_BATCH], ctxs[SFQ_GM_BATCH];
+#pragma unroll
+            for (int j = 0; j < SFQ_GM_BATCH; j++) {
+                const uint32_t i = w0 + 32u * j + lane;
+                const bool active = i < v.llen;
+                gg[j] = active ? v.seq[i] : (uint32_t)'A';
+                qq[j] = active ? (i < v.qlen ? v.qual[i] : 40u) : (uint32_t)'I';            // gens.cpp:153
             }
-            // ---- exception lists, in base order (gens.cpp:91-114); rare
-            while (excb && status == SFQ_OK) {
-                const int b = __ffs(excb) - 1;
-                excb &= excb - 1;
-                const bool bn = __shfl_sync(FULL, (int)bad_n, b) != 0, bq = __shfl_sync(FULL, (int)bad_q, b) != 0;
-                const uint32_t gb = __shfl_sync(FULL, (uint32_t)g, b);
-                const uint64_t genofs = (uint64_t)gbase + (uint32_t)b + 1u;
-                if (!bn) { if (lane == 0) xnn.put(genofs - nn_index); nn_index = genofs; }
-                else {
-                    if (!n_byte) n_byte = gb;
-                    if (gb != n_byte) { status = SFQ_E_NBYTE; status_arg = gb; break; }
-                    if (!bq) { if (lane == 0) xns.put(genofs - ns_index); ns_index = genofs; }
-                }
-            }
-            if (status != SFQ_OK) break;
-            // ---- context of every lane: inclusive packed history, 2 bits per base, newest lowest
-            uint32_t h = n, t;
-            t = __shfl_up_sync(FULL, h, 1); if (lane >= 1) h |= t << 2;
-            t = __shfl_up_sync(FULL, h, 2); if (lane >= 2) h |= t << 4;
-            t = __shfl_up_sync(FULL, h, 4); if (lane >= 4) h |= t << 8;
-            t = __shfl_up_sync(FULL, h, 8); if (lane >= 8) h |= t << 16;
-            t = __shfl_up_sync(FULL, h, 1);
-            const uint32_t ctx = ((lane < 16 ? prev << (2 * lane) : 0u) | (lane ? t : 0u)) & mask;
-            prev = __shfl_sync(FULL, h, 31);
-            // ---- lanes sharing a context form a group; its first lane finds (or claims) the slot
-            const unsigned peers = __match_any_sync(FULL, active ? ctx : 0xffffffffu);
-            const uint32_t rank = __popc(peers & lt), gsize = __popc(peers);
-            uint32_t slot = 0, fv = 0x03030303u;
-            bool full = false;
-            if (active && rank == 0) {
-                if (dense) { slot = ctx; fv = sfq_ldcg32(dtab + ctx) ^ 0x03030303u; }
-                else {
-                    const uint32_t key = ctx + 1u;
-                    uint32_t hh = (ctx * 2654435761u) >> (32 - hbits);
-                    for (uint32_t probes = 0;; probes++) {
-                        uint64_t k = sfq_ldcg64(slots + hh);
-                        if (k == 0) {
-                            k = atomicCAS(reinterpret_cast<unsigned long long *>(slots + hh), 0ull, ((unsigned long long)key << 32) | 0x03030303ull);
-                            if (k == 0) { used++; slot = hh; break; }
-                        }
-                        if ((uint32_t)(k >> 32) == key) { slot = hh; fv = (uint32_t)k; break; }
-                        if (probes >= hmask) { full = true; break; }
-                        hh = (hh + 1u) & hmask;
+            // ---- contexts of the batch (2 bits per base, newest lowest) and a prefetch of their home slots
+#pragma unroll
+            for (int j = 0; j < SFQ_GM_BATCH; j++) {
+                if (w0 + 32u * j < v.llen) {
+                    uint32_t n = sfq_gencode((uint8_t)gg[j]);
+                    if (n > 3u) n = 0;
+                    uint32_t h = n, t;
+                    t = __shfl_up_sync(FULL, h, 1); if (lane >= 1) h |= t << 2;
+                    t = __shfl_up_sync(FULL, h, 2); if (lane >= 2) h |= t << 4;
+                    t = __shfl_up_sync(FULL, h, 4); if (lane >= 4) h |= t << 8;
+                    t = __shfl_up_sync(FULL, h, 8); if (lane >= 8) h |= t << 16;
+                    t = __shfl_up_sync(FULL, h, 1);
+                    const uint32_t ctx = ((lane < 16 ? prev << (2 * lane) : 0u) | (lane ? t : 0u)) & mask;
+                    prev = __shfl_sync(FULL, h, 31);
+                    ctxs[j] = ctx;
+                    if (w0 + 32u * j + lane < v.llen) {
+                        if (dense) sfq_prefetch(dtab + ctx);
+                        else sfq_prefetch(slots + ((ctx * 2654435761u) >> (32 - hbits)));
                     }
                 }
             }
-            if (__any_sync(FULL, full)) { status = SFQ_E_TABLE; break; }
-            const int leader = __ffs(peers) - 1;
-            slot = __shfl_sync(FULL, slot, leader);
-            fv = __shfl_sync(FULL, fv, leader);
-            // ---- replay the group in lane order
-            const uint32_t maxrank = __reduce_max_sync(FULL, active ? rank : 0u);
-            uint32_t step = 0;
-            for (uint32_t rr = 0; rr <= maxrank; rr++) {
-                if (rank == rr) {
-                    const uint32_t f0 = fv & 0xff, f1 = (fv >> 8) & 0xff, f2 = (fv >> 16) & 0xff, f3 = fv >> 24;
-                    const uint32_t cum = (n > 0 ? f0 : 0) + (n > 1 ? f1 : 0) + (n > 2 ? f2 : 0);
-                    step = sfq_gstep_pack(cum, (fv >> (8 * n)) & 0xffu, f0 + f1 + f2 + f3);
-                    fv = sfq_b2_update(fv, n);
-                }
-                if (rr < maxrank) {
-                    const int src = __fns(peers, 0, rr + 1);                   // lane holding rank rr of my group
-                    const uint32_t nv = __shfl_sync(FULL, fv, src < 0 ? 0 : src);
-                    if (rank > rr) fv = nv;
+            // ---- window by window: exceptions, table slots, replay
+#pragma unroll
+            for (int j = 0; j < SFQ_GM_BATCH; j++) {
+                const uint32_t wj = w0 + 32u * j;
+                if (wj < v.llen && status == SFQ_OK) {
+                    const bool active = wj + lane < v.llen;
+                    const uint32_t g = gg[j], ctx = ctxs[j];
+                    uint32_t n = sfq_gencode((uint8_t)g);
+                    const bool bad_n = n == 4u;
+                    const unsigned errb = __ballot_sync(FULL, n > 4u);
+                    if (bad_n) n = 0;
+                    const bool bad_q = qq[j] == (uint32_t)'!';
+                    unsigned excb = __ballot_sync(FULL, active && (bad_n || bad_q));
+                    if (errb) {
+                        status = SFQ_E_BASE; status_arg = __shfl_sync(FULL, g, __ffs(errb) - 1);
+                    }
+                    // exception lists, in base order (gens.cpp:91-114); rare
+                    while (excb && status == SFQ_OK) {
+                        const int b = __ffs(excb) - 1;
+                        excb &= excb - 1;
+                        const bool bn = __shfl_sync(FULL, (int)bad_n, b) != 0, bq = __shfl_sync(FULL, (int)bad_q, b) != 0;
+                        const uint32_t gb = __shfl_sync(FULL, g, b);
+                        const uint64_t genofs = (uint64_t)gbase + (uint32_t)b + 1u;
+                        if (!bn) { if (lane == 0) xnn.put(genofs - nn_index); nn_index = genofs; }
+                        else {
+                            if (!n_byte) n_byte = gb;
+                            if (gb != n_byte) { status = SFQ_E_NBYTE; status_arg = gb; break; }
+                            if (!bq) { if (lane == 0) xns.put(genofs - ns_index); ns_index = genofs; }
+                        }
+                    }
+                    if (status == SFQ_OK) {
+                        // lanes sharing a context form a group; its first lane finds (or claims) the slot
+                        const unsigned peers = __match_any_sync(FULL, active ? ctx : 0xffffffffu);
+                        const uint32_t rank = __popc(peers & lt), gsize = __popc(peers);
+                        uint32_t slot = 0, fv = 0x03030303u;
+                        bool need = active && rank == 0, full = false;
+                        if (dense) { if (need) { slot = ctx; fv = sfq_ldcg32(dtab + ctx) ^ 0x03030303u; } }
+                        else {
+                            const uint32_t key = ctx + 1u;
+                            uint32_t hh = (ctx * 2654435761u) >> (32 - hbits), probes = 0;
+                            while (__any_sync(FULL, need)) {
+                                bool claim = false;
+                                if (need) {
+                                    const uint64_t k = sfq_ldcg64(slots + hh);
+                                    if ((uint32_t)(k >> 32) == key) { slot = hh; fv = (uint32_t)k; need = false; }
+                                    else if (k == 0) claim = true;
+                                    else { hh = (hh + 1u) & hmask; if (++probes > hmask) { full = true; need = false; } }
+                                }
+                                // two contexts of the window may want the same empty slot: the lower lane takes it
+                                const unsigned cl = __match_any_sync(FULL, claim ? hh : (0x80000000u | lane));
+                                if (claim) {
+                                    if ((cl & lt) == 0) { slots[hh] = ((uint64_t)key << 32) | 0x03030303ull; slot = hh; used++; need = false; }
+                                    else { hh = (hh + 1u) & hmask; probes++; }
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        if (__any_sync(FULL, full)) status = SFQ_E_TABLE;
+                        const int leader = __ffs(peers) - 1;
+                        slot = __shfl_sync(FULL, slot, leader);
+                        fv = __shfl_sync(FULL, fv, leader);
+                        // replay the group in lane order
+                        const uint32_t maxrank = __reduce_max_sync(FULL, active ? rank : 0u);
+                        uint32_t step = 0;
+                        for (uint32_t rr = 0; rr <= maxrank; rr++) {
+                            if (rank == rr) {
+                                const uint32_t f0 = fv & 0xff, f1 = (fv >> 8) & 0xff, f2 = (fv >> 16) & 0xff, f3 = fv >> 24;
+                                const uint32_t cum = (n > 0 ? f0 : 0) + (n > 1 ? f1 : 0) + (n > 2 ? f2 : 0);
+                                step = sfq_gstep_pack(cum, (fv >> (8 * n)) & 0xffu, f0 + f1 + f2 + f3);
+                                fv = sfq_b2_update(fv, n);
+                            }
+                            if (rr < maxrank) {
+                                const int src = __fns(peers, 0, rr + 1);       // lane holding rank rr of my group
+                                const uint32_t nv = __shfl_sync(FULL, fv, src < 0 ? 0 : src);
+                                if (rank > rr) fv = nv;
+                            }
+                        }
+                        if (active && status == SFQ_OK) {
+                            gsteps[gbase + lane] = step;
+                            if (rank + 1 == gsize) {
+                                if (dense) dtab[slot] = fv ^ 0x03030303u;
+                                else slots[slot] = ((uint64_t)(ctx + 1u) << 32) | fv;
+                            }
+                        }
+                        gbase += min(32u, v.llen - wj);
+                        __syncwarp();
+                    }
                 }
             }
-            if (active) {
-                gsteps[gbase + lane] = step;
-                if (rank + 1 == gsize) {
-                    if (dense) dtab[slot] = fv ^ 0x03030303u;
-                    else slots[slot] = ((uint64_t)(ctx + 1u) << 32) | fv;
-                }
-            }
-            gbase += min(32u, v.llen - w0);
-            __syncwarp();
         }
     }
     used = __reduce_add_sync(FULL, used);
@@ -353,23 +384,29 @@ struct SfqQWin {
     }
 };
 
+// Contexts and the per-context histogram do not depend on any order: a CTA takes SFQ_QK_RECS records of
+// one chunk (blockIdx.y), a warp one record at a time; counts go out as fire-and-forget atomics.
+#define SFQ_QK_RECS 64
 __global__ void __launch_bounds__(128)
 k_qlt_keys(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas,
-           SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, int level, uint32_t nchunks) {
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31u;
+           const uint32_t *__restrict__ rec_qoff, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, int level, uint32_t nchunks) {
+    const uint32_t c = blockIdx.y;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (c >= nchunks) return;
     const SfqChunkMeta *meta = &metas[c];
     if (meta->status != SFQ_OK) return;
     const unsigned FULL = 0xffffffffu;
     const uint32_t solid = meta->solid, nrec = meta->nrec;
     const uint64_t line0 = meta->line0;
+    const uint32_t *qoffs = rec_qoff + line0 / 4;
     uint16_t *qkey = e2.qkey + e2c[c].qoff;
     uint8_t *qb = e2.qb + e2c[c].qoff;
     uint32_t *cnt = e2.cnt + (size_t)c * SFQ_Q_CNT;
-    uint32_t qbase = 0, nesc = 0;
-    for (uint32_t r = 0; r < nrec; r++) {
+    const uint32_t r_end = min(nrec, (blockIdx.x + 1u) * SFQ_QK_RECS);
+    uint32_t nesc = 0;
+    for (uint32_t r = blockIdx.x * SFQ_QK_RECS + warp; r < r_end; r += 4) {
         const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+        const uint32_t qbase = qoffs[r];
         SfqQWin win; win.reset();
         for (uint32_t w0 = 0; w0 < v.qlen; w0 += 32) {
             const uint32_t i = w0 + lane;
@@ -379,15 +416,13 @@ k_qlt_keys(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, Sf
             nesc += __popc(__ballot_sync(FULL, active && b >= 63u));
             const unsigned peers = __match_any_sync(FULL, active ? ctx : 0xffffffffu);
             if (active) {
-                qkey[qbase + lane] = (uint16_t)ctx;
-                qb[qbase + lane] = (uint8_t)b;
-                if ((peers & ((1u << lane) - 1u)) == 0) cnt[ctx] = sfq_ldcg32(cnt + ctx) + __popc(peers);
+                qkey[qbase + i] = (uint16_t)ctx;
+                qb[qbase + i] = (uint8_t)b;
+                if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(cnt + ctx, (uint32_t)__popc(peers));
             }
-            qbase += min(32u, v.qlen - w0);
-            __syncwarp();
         }
     }
-    if (lane == 0) cnt[SFQ_Q_NCTX] = nesc;
+    if (lane == 0 && nesc) atomicAdd(cnt + SFQ_Q_NCTX, nesc);
 }
 
 // One CTA per chunk: histogram -> cursors (in place) + the segment list.
@@ -397,11 +432,11 @@ k_qlt_scan(SfqChunkMeta *metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e
     SfqChunkMeta *meta = &metas[c];
     if (meta->status != SFQ_OK) return;
     uint32_t *cnt = e2.cnt + (size_t)c * SFQ_Q_CNT;
+    // thread t owns contexts t, t + 256, ...: coalesced, and the order of the segments does not matter
     constexpr uint32_t PER = SFQ_Q_NCTX / 256;
-    const uint32_t lo = threadIdx.x * PER;
     uint32_t s = 0, ks = 0, kb = 0;
     for (uint32_t k = 0; k < PER; k++) {
-        const uint32_t v = cnt[lo + k];
+        const uint32_t v = cnt[k * 256 + threadIdx.x];
         s += v;
         if (v >= SFQ_SEG_BIG) kb++; else if (v) ks++;
     }
@@ -434,8 +469,8 @@ k_qlt_scan(SfqChunkMeta *metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e
     }
     uint32_t run = sh[0][threadIdx.x], is = base[0] + sh[1][threadIdx.x], ib = base[1] + sh[2][threadIdx.x];
     for (uint32_t k = 0; k < PER; k++) {
-        const uint32_t v = cnt[lo + k];
-        cnt[lo + k] = run;
+        const uint32_t v = cnt[k * 256 + threadIdx.x];
+        cnt[k * 256 + threadIdx.x] = run;
         if (v) {
             SfqSeg sg; sg.chunk = c; sg.start = run; sg.count = v; sg.flags = 0;
             if (v >= SFQ_SEG_BIG) e2.segs[e2.seg_cap - 1 - ib++] = sg; else e2.segs[is++] = sg;
@@ -444,6 +479,8 @@ k_qlt_scan(SfqChunkMeta *metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e
     }
 }
 
+// Stable counting sort: positions must reach their segment in order, so one warp walks the chunk;
+// keys and cursors of eight windows are requested together to keep the walk off the HBM latency.
 __global__ void __launch_bounds__(128)
 k_qlt_scatter(const SfqChunkMeta *__restrict__ metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, uint32_t nchunks) {
     const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -460,21 +497,35 @@ k_qlt_scatter(const SfqChunkMeta *__restrict__ metas, SfqEnc2Ws e2, const SfqEnc
     uint32_t *cur = e2.cnt + (size_t)c * SFQ_Q_CNT;
     const uint32_t n = meta->nquals;
     uint32_t ecur = 0;
-    for (uint32_t p0 = 0; p0 < n; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        const bool active = p < n;
-        const uint32_t ctx = active ? qkey[p] : 0xffffffffu;
-        const uint32_t b = active ? qb[p] : 0u;
-        const unsigned peers = __match_any_sync(FULL, ctx);
-        const uint32_t rank = __popc(peers & lt);
-        uint32_t at = 0;
-        if (active && rank == 0) { at = sfq_ldcg32(cur + ctx); cur[ctx] = at + __popc(peers); }
-        at = __shfl_sync(FULL, at, __ffs(peers) - 1) + rank;
-        if (active) sorted[at] = p | ((b < 63u ? b : 63u) << 24);
-        const unsigned eb = __ballot_sync(FULL, active && b >= 63u);
-        if (active && b >= 63u) esorted[ecur + __popc(eb & lt)] = p | (b << 24);
-        ecur += __popc(eb);
-        __syncwarp();
+    constexpr int B = 8;
+    for (uint32_t p0 = 0; p0 < n; p0 += 32 * B) {
+        uint32_t keys[B], bs[B];
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            const uint32_t p = p0 + 32u * j + lane;
+            keys[j] = p < n ? (uint32_t)qkey[p] : 0xffffffffu;
+            bs[j] = p < n ? (uint32_t)qb[p] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < B; j++) if (keys[j] != 0xffffffffu) sfq_prefetch(cur + keys[j]);
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            const uint32_t p = p0 + 32u * j + lane;
+            if (p0 + 32u * j < n) {
+                const bool active = p < n;
+                const uint32_t ctx = keys[j], b = bs[j];
+                const unsigned peers = __match_any_sync(FULL, ctx);
+                const uint32_t rank = __popc(peers & lt);
+                uint32_t at = 0;
+                if (active && rank == 0) { at = sfq_ldcg32(cur + ctx); cur[ctx] = at + __popc(peers); }
+                at = __shfl_sync(FULL, at, __ffs(peers) - 1) + rank;
+                if (active) sorted[at] = p | ((b < 63u ? b : 63u) << 24);
+                const unsigned eb = __ballot_sync(FULL, active && b >= 63u);
+                if (active && b >= 63u) esorted[ecur + __popc(eb & lt)] = p | (b << 24);
+                ecur += __popc(eb);
+                __syncwarp();
+            }
+        }
     }
 }
 
@@ -549,21 +600,89 @@ k_qlt_mark_escapes(const SfqChunkMeta *__restrict__ metas, SfqEnc2Ws e2, const S
 }
 
 // ============================================================================ phase 2
-// kind: 0 = gen, 1 = qlt.  One thread per chunk-stream.
+// One thread per chunk-stream; kind 0 = gen, 1 = qlt.  The steps of a stream are read 16 bytes at a
+// time through a ring of four registers, four loads ahead of the coder (the stores of the coder's
+// output may alias, so the compiler will not hoist loads by itself), and range / totFreq is a
+// multiply by a reciprocal: a 1021-entry table in shared memory for the 4-symbol model
+// (totFreq <= 1020), computed off the dependency chain for the 64-symbol model.
+__device__ __forceinline__ uint32_t sfq_div_by(uint32_t n, uint32_t d, uint32_t inv) {   // inv = floor(2^32 / d), d >= 2
+    const uint32_t q = __umulhi(n, inv);
+    return q + ((n - q * d) >= d ? 1u : 0u);
+}
+__device__ __forceinline__ uint32_t sfq_recip32(uint32_t d) {                            // floor(2^32 / d), d >= 2
+    const uint32_t q = 0xffffffffu / d;
+    return q + ((0xffffffffu - q * d) == d - 1u ? 1u : 0u);
+}
+template <int KIND>
 __global__ void __launch_bounds__(32)
 k_rc_encode(SfqChunkMeta *metas, SfqArena *arenas, uint8_t *arena_buf, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c,
-            uint32_t nchunks, uint32_t lanes, int kind) {
+            uint32_t nchunks, uint32_t lanes) {
+    __shared__ uint32_t lut[1024];
+    if (KIND == 0) {
+        for (uint32_t t = threadIdx.x; t < 1024; t += 32) lut[t] = t < 2 ? 0xffffffffu : sfq_recip32(t);
+        __syncwarp();
+    }
     const uint32_t c = blockIdx.x * lanes + threadIdx.x;
     if (threadIdx.x >= lanes || c >= nchunks) return;
     SfqChunkMeta *m = &metas[c];
     if (m->status != SFQ_OK) return;
     SfqArena *ar = &arenas[c];
-    bool ovf = false;
-    if (kind == 0)
-        sfq_rc_gen_chunk(e2.gsteps + e2c[c].goff, m->nbases, arena_buf + ar->off[SFQ_S_GEN], ar->cap[SFQ_S_GEN], &ar->size[SFQ_S_GEN], &ovf);
-    else
-        sfq_rc_qlt_chunk(e2.qsteps + e2c[c].qoff, e2.esteps + e2c[c].eoff, m->nquals, arena_buf + ar->off[SFQ_S_QLT],
-                         ar->cap[SFQ_S_QLT], &ar->size[SFQ_S_QLT], &ovf);
-    if (ovf) atomicCAS(&m->status, (uint32_t)SFQ_OK, (uint32_t)SFQ_E_CAP);
+    const int sid = KIND == 0 ? SFQ_S_GEN : SFQ_S_QLT;
+    SfqEnc rc;
+    rc.start(arena_buf + ar->off[sid], ar->cap[sid]);
+    if (KIND == 0) {
+        const uint32_t n = m->nbases;
+        const uint4 *p = reinterpret_cast<const uint4 *>(e2.gsteps + e2c[c].goff);
+        uint4 b0 = p[0], b1 = p[1], b2 = p[2], b3 = p[3];
+        auto block = [&](const uint4 &b, uint32_t first) {
+            const uint32_t s[4] = {b.x, b.y, b.z, b.w};
+            uint32_t inv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) inv[j] = lut[s[j] >> 18];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (first + j < n) {
+                    const uint32_t tot = s[j] >> 18;
+                    rc.encode_scaled(s[j] & 1023u, (s[j] >> 10) & 255u, sfq_div_by(rc.range, tot, inv[j]));
+                }
+        };
+        for (uint32_t i = 0; i < n; i += 16) {
+            const uint32_t k = i >> 2;
+            block(b0, i);      b0 = p[k + 4];
+            block(b1, i + 4);  b1 = p[k + 5];
+            block(b2, i + 8);  b2 = p[k + 6];
+            block(b3, i + 12); b3 = p[k + 7];
+        }
+    } else {
+        const uint32_t n = m->nquals;
+        const uint4 *p = reinterpret_cast<const uint4 *>(e2.qsteps + e2c[c].qoff);
+        const uint64_t *es = e2.esteps + e2c[c].eoff;
+        uint4 b0 = p[0], b1 = p[1], b2 = p[2], b3 = p[3];
+        auto block = [&](const uint4 &b, uint32_t first) {
+            const uint64_t s[2] = {(uint64_t)b.x | ((uint64_t)b.y << 32), (uint64_t)b.z | ((uint64_t)b.w << 32)};
+            uint32_t tot[2], inv[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) { tot[j] = (uint32_t)(s[j] >> 39) & 0x3fffffu; if (tot[j] < 64u) tot[j] = 64u; inv[j] = sfq_recip32(tot[j]); }   // tot >= 64 in every real step; the clamp only guards the read-ahead padding
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                if (first + j < n) {
+                    rc.encode_scaled((uint32_t)s[j] & 0x3fffffu, (uint32_t)(s[j] >> 22) & 0x1ffffu, sfq_div_by(rc.range, tot[j], inv[j]));
+                    if (s[j] >> 61) {                                           // qlts.cpp:120-125
+                        const uint64_t x = *es++;
+                        rc.encode((uint32_t)x & 0xffffffu, (uint32_t)(x >> 24) & 0xffffu, (uint32_t)(x >> 40));
+                    }
+                }
+        };
+        for (uint32_t i = 0; i < n; i += 8) {
+            const uint32_t k = i >> 1;
+            block(b0, i);     b0 = p[k + 4];
+            block(b1, i + 2); b1 = p[k + 5];
+            block(b2, i + 4); b2 = p[k + 6];
+            block(b3, i + 6); b3 = p[k + 7];
+        }
+    }
+    rc.finish();
+    ar->size[sid] = rc.out.n;
+    if (rc.out.overflow()) atomicCAS(&m->status, (uint32_t)SFQ_OK, (uint32_t)SFQ_E_CAP);
 }
 #endif  // __CUDACC__

@@ -15,7 +15,8 @@ SFQ_HD uint64_t sfq_first_record_at(const uint64_t *ls, uint64_t nrec_total, uin
 }
 
 // Fills `m` for the chunk made of records [r0, r1).  nrec == 0 chunks are left empty (text_len 0).
-SFQ_HDN void sfq_plan_chunk(const uint8_t *text, const uint64_t *ls, uint64_t r0, uint64_t r1, SfqChunkMeta *m) {
+// `rec_qoff` (may be null): rec_qoff[r - r0] = index of record r's first coded quality within the chunk.
+SFQ_HDN void sfq_plan_chunk(const uint8_t *text, const uint64_t *ls, uint64_t r0, uint64_t r1, SfqChunkMeta *m, uint32_t *rec_qoff = nullptr) {
     m->line0 = 4 * r0;
     m->text_off = ls[4 * r0];
     m->text_len = ls[4 * r1] - ls[4 * r0];
@@ -62,6 +63,7 @@ SFQ_HDN void sfq_plan_chunk(const uint8_t *text, const uint64_t *ls, uint64_t r0
         if (solid && (sl == 0 || ql == 0)) { status = SFQ_E_TRUNC; arg = recno; break; }
         if (hl - 1 >= SFQ_MAX_ID_LLEN - 1 || pl - 1 >= SFQ_MAX_ID_LLEN - 1 ||
             sl - solid >= SFQ_MAX_GN_LLEN - 1 || ql - solid >= SFQ_MAX_GN_LLEN - 1) { status = SFQ_E_OVERSIZE; arg = recno; break; }
+        if (rec_qoff) rec_qoff[r - r0] = (uint32_t)nq;
         nh += hl - 1;
         nb += sl - solid;
         nq += ql - solid;
