@@ -298,7 +298,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         CK(cudaMemcpyAsync(d_scal, h_small, 24, cudaMemcpyHostToDevice, s));
         SfqWorkspace ws;
         ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
-        ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.cbits = cbits; ws.pw = ctx->pw.as<uint32_t>();
+        ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.cbits = level <= 1 ? 4096u : 1u << cbits; ws.pw = ctx->pw.as<uint32_t>();
         for (uint32_t w = 0; w < nwaves; w++) {
             const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 0], s));
@@ -472,11 +472,11 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
     uint64_t *h_total = ctx->h_small.as<uint64_t>();
     st.retries = 0;
     for (uint32_t grow = 0;; grow++) {
-        const uint32_t hbits = sfq_gen_hbits(max_level, have_hints ? max_g : max_bases, grow);
-        uint32_t cbits = have_hints ? std::max(10u, sfq_ceil_log2(2 * max_q + 16)) + grow : sfq_q_cbits(max_level, grow);
-        if (cbits > 16) cbits = 16;
-        const uint64_t gstride = std::max(sfq_gtable_bytes(max_level, hbits), sfq_gtable_bytes(1, 18));
-        const uint64_t qbytes = std::max(sfq_qhash_bytes(max_level, cbits), sfq_qhash_bytes(1, 12)), pbytes = sfq_pwpool_bytes();
+        const uint32_t hbits = sfq_gen_nbuckets(max_level, have_hints ? max_g : max_bases, grow);     // buckets of the decoder's table
+        const uint32_t qent = sfq_q_entries(max_level, have_hints ? max_q : 65536, grow);
+        const uint32_t cbits = qent;
+        const uint64_t gstride = std::max(sfq_gbuckets_bytes(max_level, hbits), sfq_gbuckets_bytes(1, 1));
+        const uint64_t qbytes = (uint64_t)std::max(qent, 4096u) * SFQ_L64_WORDS * 4, pbytes = sfq_pwpool_bytes();
         const uint32_t R = pick_resident(ctx, nchunks, gstride + qbytes + pbytes + 4096, ctx->gtab.cap + ctx->qtab.cap + ctx->pw.cap);
         CK(ctx->gtab.ensure(R * gstride)); CK(ctx->qtab.ensure(R * qbytes)); CK(ctx->pw.ensure(R * pbytes));
         nwaves = (nchunks + R - 1) / R;
@@ -485,6 +485,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         SfqWorkspace ws;
         ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
         ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.cbits = cbits; ws.pw = ctx->pw.as<uint32_t>();
+        CK(cudaMemsetAsync(ctx->bases.p, 0, nb + 16, s));           // exception markers are ORed into the decoded bases
         for (uint32_t w = 0; w < nwaves; w++) {
             const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 0], s));
@@ -492,7 +493,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
             CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
             CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
-            k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, nc); LAUNCHED();
+            k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, ctx->bases.as<uint8_t>(), nc); LAUNCHED();
             {
                 const unsigned nb = (nc + ctx->lanes - 1) / ctx->lanes;
                 uint8_t *pb = ctx->bases.as<uint8_t>(), *pq = ctx->quals.as<uint8_t>(), *ph = ctx->hdrs.as<uint8_t>();

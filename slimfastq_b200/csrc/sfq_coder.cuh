@@ -46,6 +46,14 @@ SFQ_HD void sfq_prefetch(const void *p) {
 #endif
 }
 
+SFQ_HD void sfq_prefetch_l1(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // ------------------------------------------------------------------ byte sink / source
 // Output bytes are gathered in a 64-bit register and stored 8 at a time (the arena sub-ranges are
 // 16-byte aligned and their capacities multiples of 8).

@@ -107,7 +107,7 @@ struct SfqArena {
 // Per-wave workspace of the coders: chunk w of the wave owns slice w of every table.
 struct SfqWorkspace {
     uint8_t  *gtab;  uint64_t gtab_stride;  uint32_t hbits;     // base-context tables
-    uint32_t *qtab;  uint64_t qtab_words;   uint32_t cbits;     // quality-context tables (hashed)
+    uint32_t *qtab;  uint64_t qtab_words;   uint32_t cbits;     // quality-context tables (hashed); cbits = ENTRIES of one table
     uint32_t *pw;                                                // 256-symbol model pools
 };
 

@@ -638,11 +638,11 @@ k_rc_encode(SfqChunkMeta *metas, SfqArena *arenas, uint8_t *arena_buf, SfqEnc2Ws
             const uint32_t s[4] = {b.x, b.y, b.z, b.w};
             uint32_t inv[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) inv[j] = lut[s[j] >> 18];
+            for (int j = 0; j < 4; j++) inv[j] = lut[(s[j] >> 18) & 1023u];     // (the read-ahead past the stream's end sees arbitrary words)
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (first + j < n) {
-                    const uint32_t tot = s[j] >> 18;
+                    const uint32_t tot = (s[j] >> 18) & 1023u;
                     rc.encode_scaled(s[j] & 1023u, (s[j] >> 10) & 255u, sfq_div_by(rc.range, tot, inv[j]));
                 }
         };

@@ -16,6 +16,13 @@ static inline uint32_t sfq_q_cbits(int level, uint32_t grow) {
     uint32_t b = (level == 2 ? 15u : 14u) + grow;
     return b > 16 ? 16 : b;
 }
+// Decoder-side quality-context hash: entries for a load factor <= 2/3 at `contexts` visited contexts
+// (recorded in the blob header), or the direct table when that would be as large.
+static inline uint32_t sfq_q_entries(int level, uint64_t contexts, uint32_t grow) {
+    if (level <= 1) return 4096;
+    uint64_t e = (contexts + (contexts >> 1) + 64) << grow;
+    return (uint32_t)(e >= 65536 ? 65536 : e);
+}
 static inline uint64_t sfq_qhash_bytes(int level, uint32_t cbits) { return (level <= 1 ? 4096ull : (1ull << cbits)) * SFQ_L64_WORDS * 4; }
 // Base-context table.  Level 1: direct 2^18 x u32.  Levels 2-4: open-addressing hash of 64-bit
 // slots sized for a load factor <= 0.5 at `max_bases` insertions, never larger than the dense table
@@ -27,6 +34,17 @@ static inline uint32_t sfq_gen_hbits(int level, uint64_t max_bases, uint32_t gro
 }
 static inline uint64_t sfq_gtable_bytes(int level, uint32_t hbits) {
     return level <= 1 ? (1ull << 18) * 4 : (1ull << hbits) * 8;
+}
+// Decoder-side base-context table (SfqGenBuckets): buckets of four 64-bit slots, sized for a load
+// factor <= 2/3 at `contexts` distinct contexts (the blob header records how many a chunk touched).
+static inline uint32_t sfq_gen_nbuckets(int level, uint64_t contexts, uint32_t grow) {
+    if (level <= 1) return 1;
+    uint64_t slots = (contexts + (contexts >> 1) + 64) << grow;
+    uint64_t nb = (slots + 3) / 4;
+    return (uint32_t)(nb > 0x7fffffffull ? 0x7fffffffull : nb);
+}
+static inline uint64_t sfq_gbuckets_bytes(int level, uint32_t nbuckets) {
+    return level <= 1 ? (1ull << 18) * 4 : (uint64_t)nbuckets * 32;
 }
 static inline uint64_t sfq_pwpool_bytes() { return (uint64_t)SFQ_PW_PER_CHUNK * SFQ_PW_WORDS * 4; }
 

@@ -24,9 +24,9 @@
 // "occupied" in bit 7 of slot 5's aux byte; all of them live in lane 0's sector).
 struct SfqQTable {
     uint32_t *base;
-    uint32_t cbits, used, dense;
-    __device__ __forceinline__ void init(uint32_t *mem, uint32_t bits, bool is_dense) { base = mem; cbits = bits; used = 0; dense = is_dense; }
-    __device__ __forceinline__ uint32_t home(uint32_t ctx) const { return dense ? ctx : (ctx * 2654435761u) >> (32 - cbits); }
+    uint32_t nent, used, dense;          // nent = entries of the hash (any size, not only powers of two)
+    __device__ __forceinline__ void init(uint32_t *mem, uint32_t entries, bool is_dense) { base = mem; nent = entries; used = 0; dense = is_dense; }
+    __device__ __forceinline__ uint32_t home(uint32_t ctx) const { return dense ? ctx : __umulhi(ctx * 2654435761u, nent); }
     __device__ __forceinline__ void prefetch(uint32_t ctx, uint32_t lane) const { sfq_prefetch(base + (size_t)home(ctx) * 64 + lane * SFQ_QS); }
 };
 
@@ -83,7 +83,6 @@ struct SfqQGroup {
     // Finds (or claims) the model of `ctx`, leaves it loaded.  False = table full.
     __device__ __forceinline__ bool locate(SfqQTable &t, uint32_t ctx) {
         if (t.dense) { load(t.base + (size_t)ctx * 64); return true; }
-        const uint32_t mask = (1u << t.cbits) - 1u;
         uint32_t h = t.home(ctx);
         for (;;) {
             load(t.base + (size_t)h * 64);
@@ -91,7 +90,7 @@ struct SfqQGroup {
             const uint32_t key = bcast((w[6] >> 24) | ((w[7] >> 24) << 8), 0);
             if (a5 & 0x80u) { if (key == ctx) return true; }
             else {
-                if (t.used + 1u >= mask) return false;
+                if (t.used + 1u >= t.nent) return false;
                 t.used++;
                 if (lane == 0) {
                     w[5] |= 0x80000000u;
@@ -100,7 +99,7 @@ struct SfqQGroup {
                 }
                 return true;      // lane 0 is stored by every update, which persists the claim
             }
-            h = (h + 1u) & mask;
+            h = h + 1u == t.nent ? 0u : h + 1u;
         }
     }
 
@@ -223,14 +222,14 @@ struct SfqQGroup {
 
 // One group of SFQ_QG lanes per chunk.
 __device__ __forceinline__ void sfq_qlt_encode_group(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *meta, int level,
-                                                     uint32_t *qtable, uint32_t cbits, uint32_t *pwpool, uint8_t *arena,
+                                                     uint32_t *qtable, uint32_t nent, uint32_t *pwpool, uint8_t *arena,
                                                      SfqArena *ar, SfqQGroup &g) {
     SfqEnc rc;
     rc.start(arena + ar->off[SFQ_S_QLT], ar->cap[SFQ_S_QLT]);
     rc.out.mute = (g.lane != 0);
     SfqPower ex; ex.m = pwpool + (size_t)SFQ_PW_QEX * SFQ_PW_WORDS;
     SfqQTable tab;
-    tab.init(qtable, cbits, level <= 1 || cbits >= 16);
+    tab.init(qtable, nent, level <= 1 || nent >= 65536u);
     const uint32_t solid = meta->solid;
     uint32_t extra_hi = 0;
     bool full = false;
@@ -269,13 +268,13 @@ __device__ __forceinline__ void sfq_qlt_encode_group(const uint8_t *text, const 
 }
 
 __device__ __forceinline__ void sfq_qlt_decode_group(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
-                                                     SfqChunkMeta *meta, int level, uint32_t *qtable, uint32_t cbits, uint32_t *pwpool,
+                                                     SfqChunkMeta *meta, int level, uint32_t *qtable, uint32_t nent, uint32_t *pwpool,
                                                      const uint32_t *qlen_tab, const uint64_t *qoff_tab, uint8_t *quals, SfqQGroup &g) {
     SfqDec rc;
     rc.start(in + soff[SFQ_S_QLT], ssize[SFQ_S_QLT]);
     SfqPower ex; ex.m = pwpool + (size_t)SFQ_PW_QEX * SFQ_PW_WORDS;
     SfqQTable tab;
-    tab.init(qtable, cbits, level <= 1 || cbits >= 16);
+    tab.init(qtable, nent, level <= 1 || nent >= 65536u);
     bool full = false;
     for (uint32_t r = 0; r < meta->nrec && !full; r++) {
         const uint32_t qlen = qlen_tab[r];

@@ -158,42 +158,236 @@ SFQ_HDN void sfq_gen_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
 // qualities, which another thread is producing concurrently, so it is applied afterwards by the
 // assemble kernel: positions taken from gen.Nn (a real base under a '!' quality) are flagged with
 // bit 7 here so the rule skips them; gen.Ns positions get the N byte right away.
-SFQ_HDN void sfq_gen_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
-                                  SfqChunkMeta *meta, int level, void *table_mem, uint32_t hbits,
-                                  uint32_t *pwpool, const uint32_t *llen_tab, const uint64_t *boff_tab,
-                                  uint8_t *bases) {
-    SfqDec rc;
-    rc.start(in + soff[SFQ_S_GEN], ssize[SFQ_S_GEN]);
-    SfqXLoad xns, xnn;
-    xns.init(pwpool, SFQ_X_NS, in + soff[SFQ_S_GEN_NS], ssize[SFQ_S_GEN_NS]);
-    xnn.init(pwpool, SFQ_X_NN, in + soff[SFQ_S_GEN_NN], ssize[SFQ_S_GEN_NN]);
-    SfqGenTable tab;
-    tab.init(table_mem, hbits, level <= 1);
-    const uint32_t mask = sfq_gen_mask(level);
-    const uint8_t n_byte = meta->n_byte ? meta->n_byte : (uint8_t)'N';          // gens.cpp:169
-    const uint8_t a0 = meta->solid ? '0' : 'A', a1 = meta->solid ? '1' : 'C',
-                  a2 = meta->solid ? '2' : 'G', a3 = meta->solid ? '3' : 'T';   // gens.cpp:173-178
-    uint64_t genofs = 0;
-    uint64_t ns_index = xns.get(), nn_index = xnn.get();                        // gens.cpp:188-189
-    uint32_t status = SFQ_OK;
-    for (uint32_t r = 0; r < meta->nrec && status == SFQ_OK; r++) {
+//
+// This loop is one serial chain of ~440 k steps per chunk, so it is written for few instructions and
+// one memory round trip per base:
+//   * contexts live in buckets of four 64-bit slots (one 32-byte sector): a lookup is one sector load
+//     (two 16-byte loads), key compare and first-empty search in registers;
+//   * range / totFreq (coder.hpp:84) multiplies by a reciprocal from a 1021-entry table (totFreq <= 1020);
+//   * the symbol search compares `code` with cumFreq * range instead of dividing code by range
+//     (coder.hpp:85, base2_ranger.hpp:91-98): floor(code / r) < c  <=>  code < c * r;
+//   * the two exception lists are watched through one 32-bit "next exception" position.
+SFQ_HD uint32_t sfq_umulhi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+// floor(2^32 / d) for d >= 2
+SFQ_HD uint32_t sfq_recip_u32(uint32_t d) {
+    const uint32_t q = 0xffffffffu / d;
+    return q + ((0xffffffffu - q * d) == d - 1u ? 1u : 0u);
+}
+// floor(n / d) from inv = floor(2^32 / d)
+SFQ_HD uint32_t sfq_div_recip(uint32_t n, uint32_t d, uint32_t inv) {
+    const uint32_t q = sfq_umulhi(n, inv);
+    return q + ((n - q * d) >= d ? 1u : 0u);
+}
+#define SFQ_B2_LUT 1024u               // reciprocals of totFreq 0..1023 (entries 0,1 unused)
+SFQ_HD void sfq_b2_lut_fill(uint32_t *lut, uint32_t first, uint32_t step) {
+    for (uint32_t t = first; t < SFQ_B2_LUT; t += step) lut[t] = t < 2 ? 0xffffffffu : sfq_recip_u32(t);
+}
+
+// Decoder-side base-context table: `nb` buckets of 4 slots, slot = (ctx+1) << 32 | freq[4].
+// A context's home bucket is chosen by its PARENT (ctx >> 2, i.e. without the newest base): the bucket
+// of base i+1 then depends only on the context of base i, so it can be requested from memory before
+// base i is decoded and the table's HBM latency overlaps the coder arithmetic of the previous base.
+// (Level 1 keeps the direct 2^18 x u32 table, stored ^0x03030303.)
+struct SfqGenBuckets {
+    uint64_t *slots;
+    uint32_t nb, used, dense;
+    SFQ_HD void init(void *mem, uint32_t nbuckets, bool is_dense) { slots = (uint64_t *)mem; nb = nbuckets; used = 0; dense = is_dense; }
+    SFQ_HD uint32_t home(uint32_t ctx) const { return sfq_umulhi((ctx >> 2) * 2654435761u, nb); }
+    // home bucket of whichever context follows `ctx` (mask = context mask of the level)
+    SFQ_HD uint32_t next_home(uint32_t ctx, uint32_t mask) const { return sfq_umulhi((ctx & (mask >> 2)) * 2654435761u, nb); }
+};
+SFQ_HD void sfq_ld_bucket(const uint64_t *p, uint32_t (&k)[4], uint32_t (&v)[4]) {
+#if defined(__CUDA_ARCH__)
+    const uint4 a = *reinterpret_cast<const uint4 *>(p), b = *reinterpret_cast<const uint4 *>(p + 2);
+    v[0] = a.x; k[0] = a.y; v[1] = a.z; k[1] = a.w; v[2] = b.x; k[2] = b.y; v[3] = b.z; k[3] = b.w;
+#else
+    for (int j = 0; j < 4; j++) { v[j] = (uint32_t)p[j]; k[j] = (uint32_t)(p[j] >> 32); }
+#endif
+}
+// Looks for `key` among the four slots held in registers: true if it is there or a slot is free
+// (j = slot index, fv = its frequencies or the start state); slots fill front to back.
+SFQ_HD bool sfq_bucket_pick(const uint32_t (&k)[4], const uint32_t (&v)[4], uint32_t key, uint32_t &j, uint32_t &fv, bool &hit) {
+    const bool m0 = k[0] == key, m1 = k[1] == key, m2 = k[2] == key, m3 = k[3] == key;
+    hit = m0 | m1 | m2 | m3;
+    const uint32_t nfree = (k[0] == 0) + (k[1] == 0) + (k[2] == 0) + (k[3] == 0);
+    j = hit ? (m0 ? 0u : m1 ? 1u : m2 ? 2u : 3u) : 4u - nfree;
+    fv = m0 ? v[0] : m1 ? v[1] : m2 ? v[2] : m3 ? v[3] : 0x03030303u;
+    return hit | (nfree != 0);
+}
+// Byte source of a decoder: aligned 8-byte loads, one word ahead of the coder so that a refill never
+// waits on memory; bytes past the end read as 0 (filer.hpp:94-97).
+struct SfqByteSrc {
+    const uint8_t *p;      // address of the word after `ahead`
+    const uint8_t *end;
+    uint64_t word, ahead;
+    uint32_t left;         // unread bytes in `word`
+    SFQ_HD uint64_t fetch() {
+        uint64_t w = 0;
+        if (p + 8 <= end) w = *reinterpret_cast<const uint64_t *>(p);
+        else for (int k = 0; k < 8; k++) if (p + k < end) w |= (uint64_t)p[k] << (8 * k);
+        p += 8;
+        return w;
+    }
+    // the stream starts at any byte offset; loads are aligned, so the first word is entered part-way
+    SFQ_HD void start(const uint8_t *buf, uint32_t size) {
+        end = buf + size;
+        const uint32_t mis = (uint32_t)((uintptr_t)buf & 7u);
+        p = buf - mis;
+        word = 0;
+        for (uint32_t k = mis; k < 8; k++) if (p + k < end) word |= (uint64_t)p[k] << (8 * k);
+        word >>= 8 * mis;
+        p += 8;
+        left = 8 - mis;
+        ahead = fetch();
+    }
+    SFQ_HD uint32_t next() {
+        if (left == 0) { word = ahead; ahead = fetch(); left = 8; }
+        const uint32_t c = (uint32_t)word & 0xffu;
+        word >>= 8;
+        left--;
+        return c;
+    }
+};
+
+// The two exception lists of the base stream (gen.Ns: an N whose quality is not '!'; gen.Nn: a real base
+// under a '!' quality; gens.cpp:91-114, 188-189, 244-247) are sparse, so they are read before the bases
+// are decoded and their positions marked in the chunk's (zeroed) base plane: 0xFF = N byte, 0x80 = keep the
+// decoded base even under a '!' quality.  The base decoder merges the marker; its hot loop then holds no
+// calls.  Where both lists name a position the reference's first test (gen.Nn) wins.
+#define SFQ_MARK_NS 0xFFu
+#define SFQ_MARK_NN 0x80u
+SFQ_HDN void sfq_gen_mark_exceptions(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
+                                     const SfqChunkMeta *meta, uint32_t *pwpool, uint8_t *plane) {
+    const uint64_t nb = meta->nbases;
+    for (int pass = 0; pass < 2; pass++) {
+        SfqXLoad x;
+        if (pass == 0) x.init(pwpool, SFQ_X_NS, in + soff[SFQ_S_GEN_NS], ssize[SFQ_S_GEN_NS]);
+        else x.init(pwpool, SFQ_X_NN, in + soff[SFQ_S_GEN_NN], ssize[SFQ_S_GEN_NN]);
+        uint64_t index = 0;
+        for (;;) {
+            const uint64_t d = x.get();
+            if (d == 0) break;                       // terminator, or an absent stream (xfile.cpp:90-93)
+            const uint64_t nxt = index + d;
+            if (nxt <= index || nxt > nb) break;     // never reached by the reference's running base count
+            index = nxt;
+            plane[index - 1] = pass == 0 ? (uint8_t)SFQ_MARK_NS : (uint8_t)SFQ_MARK_NN;
+        }
+    }
+}
+
+template <bool DENSE>
+SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_t mask, uint32_t alpha, uint8_t n_byte,
+                                    const SfqChunkMeta *meta, const uint32_t *llen_tab,
+                                    const uint64_t *boff_tab, uint8_t *bases, const uint32_t *lut) {
+    uint32_t *dtab = reinterpret_cast<uint32_t *>(tab.slots);
+    uint64_t low = 0, code = 0;
+    uint32_t range = 0xFFFFFFFFu;
+    for (int i = 0; i < 8; i++) code = (code << 8) | src.next();               // coder.hpp:44-48
+    const uint32_t nrec = meta->nrec;
+    for (uint32_t r = 0; r < nrec; r++) {
         const uint32_t llen = llen_tab[r];
         uint8_t *g = bases + boff_tab[r];
         uint32_t last = 0x007616c7u;
+        uint32_t bk = DENSE ? 0u : tab.home(last & mask), bkn = 0;
+        uint32_t k[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0}, kn[4] = {0, 0, 0, 0}, vn[4] = {0, 0, 0, 0};
+        uint32_t pj = 4, pkey = 0, pfv = 0;     // slot of the current bucket written after it was loaded (4 = none)
+        if (!DENSE && llen) sfq_ld_bucket(tab.slots + 4ull * bk, k, v);
         for (uint32_t i = 0; i < llen; i++) {
-            last &= mask;
-            uint32_t fv, b;
-            const uint32_t slot = tab.find(last, fv);
-            if (slot == 0xFFFFFFFFu) { status = SFQ_E_TABLE; break; }
-            tab.store(slot, last, sfq_b2_get(fv, rc, b));
+            const uint32_t ctx = last & mask;
+            uint32_t fv;
+            uint64_t *slot = nullptr;
+            if (DENSE) fv = dtab[ctx] ^ 0x03030303u;
+            else {
+                // the bucket was requested before the previous base stored its slot: if that store went into
+                // this very bucket, the registers are one update behind
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) if (q == pj) { k[q] = pkey; v[q] = pfv; }
+                uint32_t j; bool hit;
+                if (sfq_bucket_pick(k, v, ctx + 1u, j, fv, hit)) slot = tab.slots + 4ull * bk + j;
+                else {                      // home bucket full of other contexts: walk on (rare)
+                    uint32_t b2 = bk;
+                    for (uint32_t probes = 0; !slot && probes < tab.nb; probes++) {
+                        b2 = b2 + 1u == tab.nb ? 0u : b2 + 1u;
+                        uint32_t k2[4], v2[4];
+                        sfq_ld_bucket(tab.slots + 4ull * b2, k2, v2);
+                        if (sfq_bucket_pick(k2, v2, ctx + 1u, j, fv, hit)) slot = tab.slots + 4ull * b2 + j;
+                    }
+                    if (!slot) return SFQ_E_TABLE;
+                }
+                tab.used += hit ? 0u : 1u;
+                // the bucket of the next base does not depend on what this base decodes to: request it now,
+                // use it in the next iteration
+                bkn = tab.next_home(ctx, mask);
+                sfq_ld_bucket(tab.slots + 4ull * bkn, kn, vn);
+            }
+            const uint32_t f0 = fv & 0xff, f1 = (fv >> 8) & 0xff, f2 = (fv >> 16) & 0xff, f3 = fv >> 24;
+            const uint32_t tot = f0 + f1 + f2 + f3;
+            const uint32_t rr = sfq_div_recip(range, tot, lut[tot]);            // GetFreq: range /= tot
+            uint32_t b, cr, f;
+            if ((code >> 32) == 0) {
+                const uint32_t c32 = (uint32_t)code;
+                const uint32_t c1 = f0 * rr, c2 = c1 + f1 * rr, c3 = c2 + f2 * rr;
+                const bool g1 = c32 >= c1, g2 = c32 >= c2, g3 = c32 >= c3;
+                b = (uint32_t)g1 + (uint32_t)g2 + (uint32_t)g3;
+                cr = g3 ? c3 : g2 ? c2 : g1 ? c1 : 0u;
+                f = g3 ? f3 : g2 ? f2 : g1 ? f1 : f0;
+            } else {                          // only a corrupt stream: behave like the reference's 64-bit divide
+                const uint32_t prob = (uint32_t)(code / rr);
+                if (prob < f0) { b = 0; cr = 0; f = f0; }
+                else if (prob < f0 + f1) { b = 1; cr = f0 * rr; f = f1; }
+                else if (prob < f0 + f1 + f2) { b = 2; cr = (f0 + f1) * rr; f = f2; }
+                else { b = 3; cr = (f0 + f1 + f2) * rr; f = f3; }
+            }
+            low += cr;                         // Decode (coder.hpp:88-102)
+            code -= cr;
+            range = rr * f;
+            while (range < SFQ_RC_TOP) {
+                if ((low ^ (low + range)) & (0xffULL << 56))
+                    range = (((uint32_t)low) | (SFQ_RC_TOP - 1)) - (uint32_t)low;
+                code = (code << 8) | src.next();
+                range <<= 8;
+                low <<= 8;
+            }
+            fv = sfq_b2_update(fv, b);
+            if (DENSE) dtab[ctx] = fv ^ 0x03030303u;
+            else {
+                *slot = ((uint64_t)(ctx + 1u) << 32) | fv;
+                const uint32_t sidx = (uint32_t)(slot - tab.slots);
+                pj = (sidx >> 2) == bkn ? (sidx & 3u) : 4u; pkey = ctx + 1u; pfv = fv;
+                bk = bkn;
+#pragma unroll
+                for (int q = 0; q < 4; q++) { k[q] = kn[q]; v[q] = vn[q]; }
+            }
             last = (last << 2) + b;
-            uint8_t c = b == 0 ? a0 : b == 1 ? a1 : b == 2 ? a2 : a3;
-            genofs++;
-            if (nn_index == genofs) { nn_index += xnn.get(); c |= 0x80; }
-            else if (ns_index == genofs) { ns_index += xns.get(); c = n_byte; }
-            g[i] = c;
+            const uint32_t mark = g[i];         // sfq_gen_mark_exceptions (gens.cpp:244-247)
+            const uint32_t c = (alpha >> (8 * b)) & 0xffu;
+            g[i] = (uint8_t)(mark == SFQ_MARK_NS ? (uint32_t)n_byte : (c | mark));
         }
     }
+    return SFQ_OK;
+}
+
+SFQ_HDN void sfq_gen_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
+                                  SfqChunkMeta *meta, int level, void *table_mem, uint32_t nbuckets,
+                                  uint32_t *pwpool, const uint32_t *llen_tab, const uint64_t *boff_tab,
+                                  uint8_t *bases, const uint32_t *lut) {
+    SfqByteSrc src;
+    src.start(in + soff[SFQ_S_GEN], ssize[SFQ_S_GEN]);
+    (void)pwpool;
+    SfqGenBuckets tab;
+    tab.init(table_mem, nbuckets, level <= 1);
+    const uint32_t mask = sfq_gen_mask(level);
+    const uint8_t n_byte = meta->n_byte ? meta->n_byte : (uint8_t)'N';          // gens.cpp:169
+    const uint32_t alpha = meta->solid ? 0x33323130u : 0x54474341u;             // "0123" / "ACGT", gens.cpp:173-178
+    const uint32_t status = level <= 1
+        ? sfq_gen_decode_loop<true>(src, tab, mask, alpha, n_byte, meta, llen_tab, boff_tab, bases, lut)
+        : sfq_gen_decode_loop<false>(src, tab, mask, alpha, n_byte, meta, llen_tab, boff_tab, bases, lut);
     if (status != SFQ_OK && meta->status == SFQ_OK) meta->status = status;
 }
 

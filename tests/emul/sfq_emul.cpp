@@ -173,10 +173,12 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **ou
         uint64_t soff[SFQ_NSTREAMS]; uint32_t ssize[SFQ_NSTREAMS];
         uint64_t o = off + sizeof b + b.rec_first_len;
         for (int k = 0; k < SFQ_NSTREAMS; k++) { soff[k] = o; ssize[k] = b.ssize[k]; o += b.ssize[k]; }
-        uint32_t hbits = sfq_gen_hbits(level, m.nbases, 0);
-        void *gt = calloc(1, sfq_gtable_bytes(level, hbits));
+        uint32_t hbits = sfq_gen_nbuckets(level, b.g_used ? b.g_used : m.nbases, 0);
+        void *gt = calloc(1, sfq_gbuckets_bytes(level, hbits));
         uint32_t *qt = (uint32_t *)calloc(1, sfq_qtable_bytes(level));
         uint32_t *pw = (uint32_t *)calloc(1, sfq_pwpool_bytes());
+        static uint32_t lut[SFQ_B2_LUT];
+        sfq_b2_lut_fill(lut, 0, 1);
         std::vector<uint32_t> llen(m.nrec), qlen(m.nrec), hlen(m.nrec);
         std::vector<uint8_t> pfg(m.nrec), pfq(m.nrec);
         std::vector<uint64_t> boff(m.nrec), qoff(m.nrec), hoff(m.nrec);
@@ -185,7 +187,8 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **ou
         uint64_t nb = 0, nq = 0;
         for (uint32_t r = 0; r < m.nrec; r++) { boff[r] = nb; qoff[r] = nq; nb += llen[r]; nq += qlen[r]; }
         std::vector<uint8_t> bases(nb + 1), quals(nq + 1), hdrs((size_t)SFQ_HDR_PLANE(&m));
-        sfq_gen_decode_chunk(sfq, ssize, soff, &m, level, gt, hbits, pw, llen.data(), boff.data(), bases.data());
+        sfq_gen_mark_exceptions(sfq, ssize, soff, &m, pw, bases.data());
+        sfq_gen_decode_chunk(sfq, ssize, soff, &m, level, gt, hbits, pw, llen.data(), boff.data(), bases.data(), lut);
         sfq_qlt_decode_chunk(sfq, ssize, soff, &m, level, qt, pw, qlen.data(), qoff.data(), quals.data());
         sfq_rec_decode_chunk(sfq, ssize, soff, &m, pw, sfq + off + sizeof b, b.rec_first_len, hdrs.data(),
                              hdrs.size(), hlen.data(), hoff.data());
