@@ -485,7 +485,6 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         SfqWorkspace ws;
         ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
         ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.cbits = cbits; ws.pw = ctx->pw.as<uint32_t>();
-        CK(cudaMemsetAsync(ctx->bases.p, 0, nb + 16, s));           // exception markers are ORed into the decoded bases
         for (uint32_t w = 0; w < nwaves; w++) {
             const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 0], s));
@@ -493,7 +492,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
             CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
             CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
-            k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, ctx->bases.as<uint8_t>(), nc); LAUNCHED();
+            k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, nc); LAUNCHED();
             {
                 const unsigned nb = (nc + ctx->lanes - 1) / ctx->lanes;
                 uint8_t *pb = ctx->bases.as<uint8_t>(), *pq = ctx->quals.as<uint8_t>(), *ph = ctx->hdrs.as<uint8_t>();
@@ -502,6 +501,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 CK(cudaStreamWaitEvent(ctx->side[1], ctx->fork_ev, 0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
                 k_decode<0><<<nb, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
+                k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], ctx->side[0]));
                 k_decode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, ctx->side[0]>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();

@@ -240,7 +240,7 @@ struct SfqRecTables {
 
 __global__ void __launch_bounds__(32)
 k_decode_usr(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
-             SfqWorkspace ws, SfqRecTables t, uint8_t *bases, uint32_t nchunks) {
+             SfqWorkspace ws, SfqRecTables t, uint32_t nchunks) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     const SfqDecChunk &d = dc[c];
@@ -253,7 +253,17 @@ k_decode_usr(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
         t.boff[d.rec_base + r] = b; t.qoff[d.rec_base + r] = q;
         b += t.llen[d.rec_base + r]; q += t.qlen[d.rec_base + r];
     }
-    if (m->status == SFQ_OK) sfq_gen_mark_exceptions(in, d.ssize, d.soff, m, pw, bases + d.base_plane);
+}
+
+// After the base decoder of a wave: apply gen.Ns / gen.Nn to the decoded base planes (one thread per chunk).
+__global__ void __launch_bounds__(32)
+k_gen_exceptions(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ metas,
+                 SfqWorkspace ws, uint8_t *bases, uint32_t nchunks) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks || metas[c].status != SFQ_OK) return;
+    const SfqDecChunk &d = dc[c];
+    if (d.ssize[SFQ_S_GEN_NS] == 0 && d.ssize[SFQ_S_GEN_NN] == 0) return;
+    sfq_gen_apply_exceptions(in, d.ssize, d.soff, &metas[c], ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS, bases + d.base_plane);
 }
 
 template <int ROLE>
@@ -261,6 +271,7 @@ __global__ void __launch_bounds__(32)
 k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
          SfqWorkspace ws, SfqRecTables t, uint8_t *bases, uint8_t *quals, uint8_t *hdrs, uint32_t nchunks, uint32_t lanes) {
     __shared__ uint32_t lut[ROLE == 0 ? SFQ_B2_LUT : 1];       // reciprocals of the 4-symbol model's totals
+    __shared__ uint4 cells[ROLE == 0 ? 64 : 1];                // bucket look-ahead, two 16-byte cells per thread
     if (ROLE == 0) { sfq_b2_lut_fill(lut, threadIdx.x, 32); __syncthreads(); }
     if (ROLE == 1) {
         const uint32_t c = blockIdx.x * (32 / SFQ_QG) + threadIdx.x / SFQ_QG;
@@ -278,9 +289,12 @@ k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, Sfq
     SfqChunkMeta *m = &metas[c];
     if (m->status != SFQ_OK) return;
     uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
-    if (ROLE == 0)
+    if (ROLE == 0) {
+        SfqStage stage;
+        stage.cell0 = &cells[threadIdx.x]; stage.cell1 = &cells[32 + threadIdx.x];
         sfq_gen_decode_chunk(in, d.ssize, d.soff, m, d.level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw,
-                             t.llen + d.rec_base, t.boff + d.rec_base, bases, lut);
+                             t.llen + d.rec_base, t.boff + d.rec_base, bases, lut, stage);
+    }
     else {
         sfq_rec_decode_chunk(in, d.ssize, d.soff, m, pw, in + d.rec_first_off, d.rec_first_len,
                              hdrs + d.hdr_plane, SFQ_HDR_PLANE(m), t.hlen + d.rec_base, t.hoff + d.rec_base);

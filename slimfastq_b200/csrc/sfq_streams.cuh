@@ -220,6 +220,34 @@ SFQ_HD bool sfq_bucket_pick(const uint32_t (&k)[4], const uint32_t (&v)[4], uint
     fv = m0 ? v[0] : m1 ? v[1] : m2 ? v[2] : m3 ? v[3] : 0x03030303u;
     return hit | (nfree != 0);
 }
+// Look-ahead of one bucket.  On the device the 32 bytes travel global -> shared with cp.async: that
+// copy is not tracked by the register scoreboard, so it stays in flight across the divergent branches of
+// the coder's renormalisation loop (a plain early load is waited for at the first such branch) and is
+// only collected when the next base needs it.  `slot` = this thread's two 16-byte cells in shared memory.
+struct SfqStage {
+    void *cell0 = nullptr, *cell1 = nullptr;
+    SFQ_HD void request(const uint64_t *bucket) const {
+#if defined(__CUDA_ARCH__)
+        const unsigned a0 = (unsigned)__cvta_generic_to_shared(cell0), a1 = (unsigned)__cvta_generic_to_shared(cell1);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a0), "l"(bucket));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a1), "l"(bucket + 2));
+        asm volatile("cp.async.commit_group;");
+#else
+        (void)bucket;
+#endif
+    }
+    SFQ_HD void collect(const uint64_t *bucket, uint32_t (&k)[4], uint32_t (&v)[4]) const {
+#if defined(__CUDA_ARCH__)
+        (void)bucket;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const uint4 a = *reinterpret_cast<const uint4 *>(cell0), b = *reinterpret_cast<const uint4 *>(cell1);
+        v[0] = a.x; k[0] = a.y; v[1] = a.z; k[1] = a.w; v[2] = b.x; k[2] = b.y; v[3] = b.z; k[3] = b.w;
+#else
+        sfq_ld_bucket(bucket, k, v);
+#endif
+    }
+};
+
 // Byte source of a decoder: aligned 8-byte loads, one word ahead of the coder so that a refill never
 // waits on memory; bytes past the end read as 0 (filer.hpp:94-97).
 struct SfqByteSrc {
@@ -247,7 +275,10 @@ struct SfqByteSrc {
         ahead = fetch();
     }
     SFQ_HD uint32_t next() {
-        if (left == 0) { word = ahead; ahead = fetch(); left = 8; }
+        if (left == 0) {
+            word = ahead; ahead = fetch(); left = 8;
+            if (((uintptr_t)p & 127u) == 0 && p + 256 <= end) sfq_prefetch_l1(p + 128);     // the stream is read once, front to back
+        }
         const uint32_t c = (uint32_t)word & 0xffu;
         word >>= 8;
         left--;
@@ -256,19 +287,18 @@ struct SfqByteSrc {
 };
 
 // The two exception lists of the base stream (gen.Ns: an N whose quality is not '!'; gen.Nn: a real base
-// under a '!' quality; gens.cpp:91-114, 188-189, 244-247) are sparse, so they are read before the bases
-// are decoded and their positions marked in the chunk's (zeroed) base plane: 0xFF = N byte, 0x80 = keep the
-// decoded base even under a '!' quality.  The base decoder merges the marker; its hot loop then holds no
-// calls.  Where both lists name a position the reference's first test (gen.Nn) wins.
-#define SFQ_MARK_NS 0xFFu
-#define SFQ_MARK_NN 0x80u
-SFQ_HDN void sfq_gen_mark_exceptions(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
-                                     const SfqChunkMeta *meta, uint32_t *pwpool, uint8_t *plane) {
+// under a '!' quality; gens.cpp:91-114, 188-189, 244-247) are sparse, so they are applied to the chunk's
+// decoded base plane afterwards instead of being polled once per base: gen.Nn positions get bit 7 set
+// (the assemble kernel's "quality '!' means N" rule skips them), gen.Ns positions get the N byte.
+// Where both lists name a position the reference's first test (gen.Nn) wins, hence gen.Nn goes first.
+SFQ_HDN void sfq_gen_apply_exceptions(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
+                                      const SfqChunkMeta *meta, uint32_t *pwpool, uint8_t *plane) {
     const uint64_t nb = meta->nbases;
+    const uint8_t n_byte = meta->n_byte ? meta->n_byte : (uint8_t)'N';          // gens.cpp:169
     for (int pass = 0; pass < 2; pass++) {
         SfqXLoad x;
-        if (pass == 0) x.init(pwpool, SFQ_X_NS, in + soff[SFQ_S_GEN_NS], ssize[SFQ_S_GEN_NS]);
-        else x.init(pwpool, SFQ_X_NN, in + soff[SFQ_S_GEN_NN], ssize[SFQ_S_GEN_NN]);
+        if (pass == 0) x.init(pwpool, SFQ_X_NN, in + soff[SFQ_S_GEN_NN], ssize[SFQ_S_GEN_NN]);
+        else x.init(pwpool, SFQ_X_NS, in + soff[SFQ_S_GEN_NS], ssize[SFQ_S_GEN_NS]);
         uint64_t index = 0;
         for (;;) {
             const uint64_t d = x.get();
@@ -276,15 +306,17 @@ SFQ_HDN void sfq_gen_mark_exceptions(const uint8_t *in, const uint32_t *ssize, c
             const uint64_t nxt = index + d;
             if (nxt <= index || nxt > nb) break;     // never reached by the reference's running base count
             index = nxt;
-            plane[index - 1] = pass == 0 ? (uint8_t)SFQ_MARK_NS : (uint8_t)SFQ_MARK_NN;
+            uint8_t *c = plane + (index - 1);
+            if (pass == 0) *c |= 0x80u;
+            else if (!(*c & 0x80u)) *c = n_byte;
         }
     }
 }
 
 template <bool DENSE>
-SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_t mask, uint32_t alpha, uint8_t n_byte,
+SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_t mask, uint32_t alpha,
                                     const SfqChunkMeta *meta, const uint32_t *llen_tab,
-                                    const uint64_t *boff_tab, uint8_t *bases, const uint32_t *lut) {
+                                    const uint64_t *boff_tab, uint8_t *bases, const uint32_t *lut, SfqStage stage) {
     uint32_t *dtab = reinterpret_cast<uint32_t *>(tab.slots);
     uint64_t low = 0, code = 0;
     uint32_t range = 0xFFFFFFFFu;
@@ -295,9 +327,9 @@ SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_
         uint8_t *g = bases + boff_tab[r];
         uint32_t last = 0x007616c7u;
         uint32_t bk = DENSE ? 0u : tab.home(last & mask), bkn = 0;
-        uint32_t k[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0}, kn[4] = {0, 0, 0, 0}, vn[4] = {0, 0, 0, 0};
+        uint32_t k[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
         uint32_t pj = 4, pkey = 0, pfv = 0;     // slot of the current bucket written after it was loaded (4 = none)
-        if (!DENSE && llen) sfq_ld_bucket(tab.slots + 4ull * bk, k, v);
+        if (!DENSE && llen) stage.request(tab.slots + 4ull * bk);
         for (uint32_t i = 0; i < llen; i++) {
             const uint32_t ctx = last & mask;
             uint32_t fv;
@@ -306,6 +338,7 @@ SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_
             else {
                 // the bucket was requested before the previous base stored its slot: if that store went into
                 // this very bucket, the registers are one update behind
+                stage.collect(tab.slots + 4ull * bk, k, v);
 #pragma unroll
                 for (uint32_t q = 0; q < 4; q++) if (q == pj) { k[q] = pkey; v[q] = pfv; }
                 uint32_t j; bool hit;
@@ -324,7 +357,7 @@ SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_
                 // the bucket of the next base does not depend on what this base decodes to: request it now,
                 // use it in the next iteration
                 bkn = tab.next_home(ctx, mask);
-                sfq_ld_bucket(tab.slots + 4ull * bkn, kn, vn);
+                if (i + 1 < llen) stage.request(tab.slots + 4ull * bkn);      // (never two copies in flight into the same cells)
             }
             const uint32_t f0 = fv & 0xff, f1 = (fv >> 8) & 0xff, f2 = (fv >> 16) & 0xff, f3 = fv >> 24;
             const uint32_t tot = f0 + f1 + f2 + f3;
@@ -361,13 +394,9 @@ SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_
                 const uint32_t sidx = (uint32_t)(slot - tab.slots);
                 pj = (sidx >> 2) == bkn ? (sidx & 3u) : 4u; pkey = ctx + 1u; pfv = fv;
                 bk = bkn;
-#pragma unroll
-                for (int q = 0; q < 4; q++) { k[q] = kn[q]; v[q] = vn[q]; }
             }
             last = (last << 2) + b;
-            const uint32_t mark = g[i];         // sfq_gen_mark_exceptions (gens.cpp:244-247)
-            const uint32_t c = (alpha >> (8 * b)) & 0xffu;
-            g[i] = (uint8_t)(mark == SFQ_MARK_NS ? (uint32_t)n_byte : (c | mark));
+            g[i] = (uint8_t)(alpha >> (8 * b));  // exceptions: sfq_gen_apply_exceptions, afterwards
         }
     }
     return SFQ_OK;
@@ -376,18 +405,17 @@ SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_
 SFQ_HDN void sfq_gen_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
                                   SfqChunkMeta *meta, int level, void *table_mem, uint32_t nbuckets,
                                   uint32_t *pwpool, const uint32_t *llen_tab, const uint64_t *boff_tab,
-                                  uint8_t *bases, const uint32_t *lut) {
+                                  uint8_t *bases, const uint32_t *lut, SfqStage stage) {
     SfqByteSrc src;
     src.start(in + soff[SFQ_S_GEN], ssize[SFQ_S_GEN]);
     (void)pwpool;
     SfqGenBuckets tab;
     tab.init(table_mem, nbuckets, level <= 1);
     const uint32_t mask = sfq_gen_mask(level);
-    const uint8_t n_byte = meta->n_byte ? meta->n_byte : (uint8_t)'N';          // gens.cpp:169
     const uint32_t alpha = meta->solid ? 0x33323130u : 0x54474341u;             // "0123" / "ACGT", gens.cpp:173-178
     const uint32_t status = level <= 1
-        ? sfq_gen_decode_loop<true>(src, tab, mask, alpha, n_byte, meta, llen_tab, boff_tab, bases, lut)
-        : sfq_gen_decode_loop<false>(src, tab, mask, alpha, n_byte, meta, llen_tab, boff_tab, bases, lut);
+        ? sfq_gen_decode_loop<true>(src, tab, mask, alpha, meta, llen_tab, boff_tab, bases, lut, stage)
+        : sfq_gen_decode_loop<false>(src, tab, mask, alpha, meta, llen_tab, boff_tab, bases, lut, stage);
     if (status != SFQ_OK && meta->status == SFQ_OK) meta->status = status;
 }
 

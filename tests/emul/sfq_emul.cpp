@@ -187,8 +187,8 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **ou
         uint64_t nb = 0, nq = 0;
         for (uint32_t r = 0; r < m.nrec; r++) { boff[r] = nb; qoff[r] = nq; nb += llen[r]; nq += qlen[r]; }
         std::vector<uint8_t> bases(nb + 1), quals(nq + 1), hdrs((size_t)SFQ_HDR_PLANE(&m));
-        sfq_gen_mark_exceptions(sfq, ssize, soff, &m, pw, bases.data());
-        sfq_gen_decode_chunk(sfq, ssize, soff, &m, level, gt, hbits, pw, llen.data(), boff.data(), bases.data(), lut);
+        sfq_gen_decode_chunk(sfq, ssize, soff, &m, level, gt, hbits, pw, llen.data(), boff.data(), bases.data(), lut, SfqStage());
+        sfq_gen_apply_exceptions(sfq, ssize, soff, &m, pw, bases.data());
         sfq_qlt_decode_chunk(sfq, ssize, soff, &m, level, qt, pw, qlen.data(), qoff.data(), quals.data());
         sfq_rec_decode_chunk(sfq, ssize, soff, &m, pw, sfq + off + sizeof b, b.rec_first_len, hdrs.data(),
                              hdrs.size(), hlen.data(), hoff.data());

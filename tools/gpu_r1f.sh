@@ -11,4 +11,4 @@ except Exception as e:
 PY
 }
 run base A=1
-KERN=k_decode SKIP=0 COUNT=3 TAG=r1f GB=0.25 bash tools/gpu_ncu_sections.sh 2>&1 | tail -2
+KERN=k_decode SKIP=0 COUNT=3 TAG=r1g GB=0.25 CHUNK=131072 bash tools/gpu_ncu_sections.sh 2>&1 | tail -2
