@@ -19,15 +19,22 @@ namespace {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool view = false;                      // a sub-range of ctx->scratch: not owned
     cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        if (bytes <= cap && !view) return cudaSuccess;
+        if (p && !view) cudaFree(p);
+        p = nullptr; cap = 0; view = false;
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e == cudaSuccess) cap = bytes;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; cap = 0; view = false; }
+    // the next `bytes` of `pool` from *off (256-byte aligned); the caller has sized the pool
+    void carve(const DevBuf &pool, size_t bytes, size_t *off) {
+        if (p && !view) cudaFree(p);
+        p = static_cast<uint8_t *>(pool.p) + *off; cap = bytes; view = true;
+        *off += (bytes + 255) & ~(size_t)255;
+    }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 struct HostBuf {
@@ -64,10 +71,18 @@ struct sfq_ctx {
     cudaEvent_t ev[EV_COUNT]{};
     std::vector<cudaEvent_t> wave_ev;       // 10 per wave: clear start, code start, code end, pack end, then start/end of gen, qlt, rec
     // device buffers (grow-only, reused across calls)
+    // One arena for everything a call needs only while it runs and that scales with the resident chunks or
+    // the input: compress carves its stream arenas and coding-step arrays from it, decompress its planes,
+    // per-record tables and quality tables.  Alternating calls reuse the same memory instead of each keeping
+    // a private set alive (which would halve the chunks that fit in one wave).
+    DevBuf scratch;
     DevBuf text, out, tiles, tile_prefix, lines, scalars, rec_begin, r0, r1, metas, arenas, arena_buf,
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
            e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff;
+    bool qdec_octets = true;                // SFQ_QDEC=0: the first (sub-warp mask) quality decoder, for A/B runs
+    bool serial_roles = false;              // SFQ_SERIAL_ROLES=1: gen, qlt, rec kernels of a wave one after another (diagnosis)
+    uint32_t qgpw = 2;                      // quality-decoder groups (chunks) per warp (SFQ_QGPW: 1, 2 or 4)
     bool serial_encoder = false;            // SFQ_ENC_SERIAL=1: single-pass coders (one chain per chunk-stream) for A/B runs
     HostBuf h_out, h_small;
     void release_all() {
@@ -77,22 +92,27 @@ struct sfq_ctx {
                          &t_hoff, &t_ooff, &e2_gsteps, &e2_qkey, &e2_qb, &e2_sorted, &e2_qsteps, &e2_cnt, &e2_esorted,
                          &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks, &rec_qoff};
         for (DevBuf *b : all) b->release();
+        scratch.release();
         h_out.release(); h_small.release();
     }
 };
 
 namespace {
 
+void release_workspace(sfq_ctx *ctx) {
+    DevBuf *views[] = {&ctx->arena_buf, &ctx->qtab, &ctx->bases, &ctx->quals, &ctx->hdrs, &ctx->t_llen, &ctx->t_qlen, &ctx->t_hlen,
+                       &ctx->t_pfg, &ctx->t_pfq, &ctx->t_boff, &ctx->t_qoff, &ctx->t_hoff, &ctx->t_ooff,
+                       &ctx->e2_gsteps, &ctx->e2_qkey, &ctx->e2_qb, &ctx->e2_sorted, &ctx->e2_qsteps, &ctx->e2_cnt,
+                       &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs};
+    for (DevBuf *d : views) d->release();
+    ctx->scratch.release(); ctx->gtab.release(); ctx->pw.release();
+}
 // Large caller-facing buffers win over the cached coder workspace: on OOM drop it and retry.
 cudaError_t ensure_big(sfq_ctx *ctx, DevBuf &b, size_t bytes) {
     cudaError_t e = b.ensure(bytes);
     if (e != cudaErrorMemoryAllocation) return e;
     cudaGetLastError();
-    ctx->gtab.release(); ctx->qtab.release(); ctx->pw.release(); ctx->arena_buf.release();
-    ctx->bases.release(); ctx->quals.release(); ctx->hdrs.release();
-    DevBuf *e2[] = {&ctx->e2_gsteps, &ctx->e2_qkey, &ctx->e2_qb, &ctx->e2_sorted, &ctx->e2_qsteps, &ctx->e2_cnt,
-                    &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs};
-    for (DevBuf *d : e2) d->release();
+    release_workspace(ctx);
     return b.ensure(bytes);
 }
 
@@ -133,10 +153,11 @@ int status_to_error(sfq_ctx *ctx, const SfqChunkMeta &m, uint64_t chunk, uint64_
 }
 
 // How many chunks can have their model tables resident at once.
-uint32_t pick_resident(sfq_ctx *ctx, uint64_t nchunks, uint64_t per_chunk, uint64_t already_have) {
+uint32_t pick_resident(sfq_ctx *ctx, uint64_t nchunks, uint64_t per_chunk, uint64_t already_have, uint64_t fixed = 0) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     uint64_t budget = (uint64_t)((double)(free_b + already_have) * 0.85);
+    budget = budget > fixed ? budget - fixed : 0;
     uint64_t r = budget / per_chunk;
     if (r < 1) r = 1;
     if (ctx->max_resident && r > ctx->max_resident) r = ctx->max_resident;
@@ -167,6 +188,7 @@ int ensure_wave_events(sfq_ctx *ctx, size_t waves) {
 int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level, uint64_t chunk_bytes,
                        uint8_t *d_out, size_t out_cap, size_t *out_n) {
     cudaStream_t s = ctx->stream;
+    cudaStream_t side0 = ctx->serial_roles ? s : ctx->side[0], side1 = ctx->serial_roles ? s : ctx->side[1];
     sfq_stats &st = ctx->st;
     level = level > 4 ? 4 : level < 1 ? 1 : level;                    // range_level, config.cpp:231-236
     if (!chunk_bytes) chunk_bytes = 1ull << 20;
@@ -258,12 +280,9 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         // two-phase encoder: no quality-model table in global memory, but the coding steps of every symbol
         const uint64_t e2_per_chunk = 4 * max_nb + 15 * max_nq + SFQ_Q_CNT * 4ull + 16 * seg_cap(max_nq) + 12 * esc_cap(max_nq) + 256;
         const uint64_t per_chunk = gstride + pbytes + max_arena + 4096 + (two_phase ? e2_per_chunk : qbytes);
-        const uint64_t have_now = ctx->gtab.cap + ctx->qtab.cap + ctx->pw.cap + ctx->arena_buf.cap + ctx->e2_gsteps.cap + ctx->e2_qkey.cap +
-                                  ctx->e2_qb.cap + ctx->e2_sorted.cap + ctx->e2_qsteps.cap + ctx->e2_cnt.cap + ctx->e2_esorted.cap +
-                                  ctx->e2_esteps.cap + ctx->e2_segs.cap;
+        const uint64_t have_now = ctx->gtab.cap + ctx->pw.cap + ctx->scratch.cap;
         const uint32_t R = pick_resident(ctx, nchunks, per_chunk, have_now);
         CK(ctx->gtab.ensure(R * gstride)); CK(ctx->pw.ensure(R * pbytes));
-        if (!two_phase) CK(ctx->qtab.ensure(R * qbytes));
         const uint32_t nwaves = (nchunks + R - 1) / R;
         if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
         st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * per_chunk;
@@ -280,12 +299,20 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             wave_arena_max = std::max(wave_arena_max, o);
             wave_nb = std::max(wave_nb, gb); wave_nq = std::max(wave_nq, qb); wave_ne = std::max(wave_ne, eb); wave_seg = std::max(wave_seg, sg);
         }
-        CK(ctx->arena_buf.ensure(wave_arena_max + 64));
         SfqEnc2Ws e2{};
+        {   // everything wave-sized comes out of the shared scratch arena
+            const size_t sz[] = {wave_arena_max + 64, wave_nb * 4 + 256, wave_nq * 2 + 64, wave_nq + 64, wave_nq * 4 + 64, wave_nq * 8 + 256,
+                                 (size_t)R * SFQ_Q_CNT * 4, wave_ne * 4 + 64, wave_ne * 8 + 64, wave_seg * sizeof(SfqSeg), (size_t)R * qbytes};
+            DevBuf *bufs[] = {&ctx->arena_buf, &ctx->e2_gsteps, &ctx->e2_qkey, &ctx->e2_qb, &ctx->e2_sorted, &ctx->e2_qsteps,
+                              &ctx->e2_cnt, &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs, &ctx->qtab};
+            const int first = 0, last = two_phase ? 10 : 11;
+            size_t total = 0;
+            for (int k = first; k < last; k++) if (two_phase || k == 0 || k == 10) total += (sz[k] + 255) & ~(size_t)255;
+            CK(ctx->scratch.ensure(total));
+            size_t off = 0;
+            for (int k = first; k < last; k++) if (two_phase || k == 0 || k == 10) bufs[k]->carve(ctx->scratch, sz[k], &off);
+        }
         if (two_phase) {
-            CK(ctx->e2_gsteps.ensure(wave_nb * 4 + 256)); CK(ctx->e2_qkey.ensure(wave_nq * 2 + 64)); CK(ctx->e2_qb.ensure(wave_nq + 64));
-            CK(ctx->e2_sorted.ensure(wave_nq * 4 + 64)); CK(ctx->e2_qsteps.ensure(wave_nq * 8 + 256)); CK(ctx->e2_cnt.ensure((uint64_t)R * SFQ_Q_CNT * 4));
-            CK(ctx->e2_esorted.ensure(wave_ne * 4 + 64)); CK(ctx->e2_esteps.ensure(wave_ne * 8 + 64)); CK(ctx->e2_segs.ensure(wave_seg * sizeof(SfqSeg)));
             CK(ctx->e2_ctr.ensure(64)); CK(ctx->e2_chunks.ensure(nchunks * sizeof(SfqEnc2Chunk)));
             CK(cudaMemcpyAsync(ctx->e2_chunks.p, e2c.data(), nchunks * sizeof(SfqEnc2Chunk), cudaMemcpyHostToDevice, s));
             e2.gsteps = ctx->e2_gsteps.as<uint32_t>(); e2.qkey = ctx->e2_qkey.as<uint16_t>(); e2.qb = ctx->e2_qb.as<uint8_t>();
@@ -313,8 +340,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 const SfqEnc2Chunk *d_e2c = ctx->e2_chunks.as<SfqEnc2Chunk>() + c0;
                 uint8_t *abuf = ctx->arena_buf.as<uint8_t>();
                 CK(cudaEventRecord(ctx->fork_ev, s));
-                CK(cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0));
-                CK(cudaStreamWaitEvent(ctx->side[1], ctx->fork_ev, 0));
+                CK(cudaStreamWaitEvent(side0, ctx->fork_ev, 0));
+                CK(cudaStreamWaitEvent(side1, ctx->fork_ev, 0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
                 if (two_phase) {
                     k_gen_model<<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); LAUNCHED();
@@ -323,9 +350,9 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], ctx->side[0]));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
                 if (two_phase) {
-                    cudaStream_t q = ctx->side[0];
+                    cudaStream_t q = side0;
                     uint32_t wave_max_nrec = 1;
                     for (uint32_t c = c0; c < c0 + nc; c++) wave_max_nrec = std::max(wave_max_nrec, metas[c].nrec);
                     k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc); LAUNCHED();
@@ -335,14 +362,14 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
                     k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes); LAUNCHED();
                 } else {
-                    k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, ctx->side[0]>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
+                    k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, side0>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
                 }
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], ctx->side[0]));
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], ctx->side[1]));
-                k_encode<2><<<nb, 32, 0, ctx->side[1]>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], ctx->side[1]));
-                CK(cudaEventRecord(ctx->join_ev[0], ctx->side[0]));
-                CK(cudaEventRecord(ctx->join_ev[1], ctx->side[1]));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
+                k_encode<2><<<nb, 32, 0, side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
+                CK(cudaEventRecord(ctx->join_ev[0], side0));
+                CK(cudaEventRecord(ctx->join_ev[1], side1));
                 CK(cudaStreamWaitEvent(s, ctx->join_ev[0], 0));
                 CK(cudaStreamWaitEvent(s, ctx->join_ev[1], 0));
             }
@@ -403,6 +430,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                          const std::vector<uint64_t> &index, const std::vector<SfqBlobHeader> &blobs,
                          uint8_t *d_out, size_t out_cap, size_t *out_n) {
     cudaStream_t s = ctx->stream;
+    cudaStream_t side0 = ctx->serial_roles ? s : ctx->side[0], side1 = ctx->serial_roles ? s : ctx->side[1];
     sfq_stats &st = ctx->st;
     const uint32_t nchunks = (uint32_t)fh.nchunks;
     std::vector<SfqChunkMeta> metas(nchunks);
@@ -441,11 +469,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
 
     CK(ctx->metas.ensure(nchunks * sizeof(SfqChunkMeta)));
     CK(ctx->dchunks.ensure(nchunks * sizeof(SfqDecChunk)));
-    CK(ensure_big(ctx, ctx->bases, nb + 16)); CK(ensure_big(ctx, ctx->quals, nq + 16)); CK(ensure_big(ctx, ctx->hdrs, nh + 16));
     CK(ctx->rec_chunk.ensure(nrec * 4));
-    CK(ctx->t_llen.ensure(nrec * 4)); CK(ctx->t_qlen.ensure(nrec * 4)); CK(ctx->t_hlen.ensure(nrec * 4));
-    CK(ctx->t_pfg.ensure(nrec)); CK(ctx->t_pfq.ensure(nrec));
-    CK(ctx->t_boff.ensure(nrec * 8)); CK(ctx->t_qoff.ensure(nrec * 8)); CK(ctx->t_hoff.ensure(nrec * 8)); CK(ctx->t_ooff.ensure(nrec * 8));
     std::vector<uint32_t> rec_chunk(nrec);
     for (uint32_t c = 0; c < nchunks; c++) std::fill(rec_chunk.begin() + dcs[c].rec_base, rec_chunk.begin() + dcs[c].rec_base + metas[c].nrec, c);
     SfqChunkMeta *d_metas = ctx->metas.as<SfqChunkMeta>();
@@ -453,10 +477,13 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
     CK(cudaMemcpyAsync(d_metas, metas.data(), nchunks * sizeof(SfqChunkMeta), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_dcs, dcs.data(), nchunks * sizeof(SfqDecChunk), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->rec_chunk.p, rec_chunk.data(), nrec * 4, cudaMemcpyHostToDevice, s));
-    SfqRecTables t;
-    t.llen = ctx->t_llen.as<uint32_t>(); t.qlen = ctx->t_qlen.as<uint32_t>(); t.hlen = ctx->t_hlen.as<uint32_t>();
-    t.pfg = ctx->t_pfg.as<uint8_t>(); t.pfq = ctx->t_pfq.as<uint8_t>();
-    t.boff = ctx->t_boff.as<uint64_t>(); t.qoff = ctx->t_qoff.as<uint64_t>(); t.hoff = ctx->t_hoff.as<uint64_t>(); t.ooff = ctx->t_ooff.as<uint64_t>();
+    // planes and per-record tables: carved from the scratch arena together with the quality tables (below)
+    const size_t fixed_sz[] = {nb + 16, nq + 16, nh + 16, nrec * 4, nrec * 4, nrec * 4, nrec, nrec, nrec * 8, nrec * 8, nrec * 8, nrec * 8};
+    DevBuf *fixed_buf[] = {&ctx->bases, &ctx->quals, &ctx->hdrs, &ctx->t_llen, &ctx->t_qlen, &ctx->t_hlen, &ctx->t_pfg, &ctx->t_pfq,
+                           &ctx->t_boff, &ctx->t_qoff, &ctx->t_hoff, &ctx->t_ooff};
+    size_t fixed_total = 0;
+    for (size_t v : fixed_sz) fixed_total += (v + 255) & ~(size_t)255;
+    SfqRecTables t{};
     CK(cudaEventRecord(ctx->ev[EV_PLAN], s));
 
     // all chunks of a container share one table geometry, sized from the blobs' context counts; a table
@@ -477,8 +504,19 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         const uint32_t cbits = qent;
         const uint64_t gstride = std::max(sfq_gbuckets_bytes(max_level, hbits), sfq_gbuckets_bytes(1, 1));
         const uint64_t qbytes = (uint64_t)std::max(qent, 4096u) * SFQ_L64_WORDS * 4, pbytes = sfq_pwpool_bytes();
-        const uint32_t R = pick_resident(ctx, nchunks, gstride + qbytes + pbytes + 4096, ctx->gtab.cap + ctx->qtab.cap + ctx->pw.cap);
-        CK(ctx->gtab.ensure(R * gstride)); CK(ctx->qtab.ensure(R * qbytes)); CK(ctx->pw.ensure(R * pbytes));
+        const uint32_t R = pick_resident(ctx, nchunks, gstride + qbytes + pbytes + 4096, ctx->gtab.cap + ctx->pw.cap + ctx->scratch.cap, fixed_total);
+        {
+            cudaError_t e = ctx->scratch.ensure(fixed_total + (size_t)R * qbytes + 256);
+            if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); release_workspace(ctx); e = ctx->scratch.ensure(fixed_total + (size_t)R * qbytes + 256); }
+            CK(e);
+            size_t off = 0;
+            for (int k = 0; k < 12; k++) fixed_buf[k]->carve(ctx->scratch, fixed_sz[k], &off);
+            ctx->qtab.carve(ctx->scratch, (size_t)R * qbytes, &off);
+            t.llen = ctx->t_llen.as<uint32_t>(); t.qlen = ctx->t_qlen.as<uint32_t>(); t.hlen = ctx->t_hlen.as<uint32_t>();
+            t.pfg = ctx->t_pfg.as<uint8_t>(); t.pfq = ctx->t_pfq.as<uint8_t>();
+            t.boff = ctx->t_boff.as<uint64_t>(); t.qoff = ctx->t_qoff.as<uint64_t>(); t.hoff = ctx->t_hoff.as<uint64_t>(); t.ooff = ctx->t_ooff.as<uint64_t>();
+        }
+        CK(ctx->gtab.ensure(R * gstride)); CK(ctx->pw.ensure(R * pbytes));
         nwaves = (nchunks + R - 1) / R;
         if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
         st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * (gstride + qbytes + pbytes);
@@ -497,20 +535,23 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 const unsigned nb = (nc + ctx->lanes - 1) / ctx->lanes;
                 uint8_t *pb = ctx->bases.as<uint8_t>(), *pq = ctx->quals.as<uint8_t>(), *ph = ctx->hdrs.as<uint8_t>();
                 CK(cudaEventRecord(ctx->fork_ev, s));
-                CK(cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0));
-                CK(cudaStreamWaitEvent(ctx->side[1], ctx->fork_ev, 0));
+                CK(cudaStreamWaitEvent(side0, ctx->fork_ev, 0));
+                CK(cudaStreamWaitEvent(side1, ctx->fork_ev, 0));
+                // the quality decoder is the longest chain of the three: it goes first (and on the high-priority
+                // stream) so that its warps are all resident from the start; gen and rec fill in around it
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
+                if (ctx->qdec_octets) { k_qlt_decode4<<<(nc + 4 * SFQ_QD_WARPS - 1) / (4 * SFQ_QD_WARPS), 32 * SFQ_QD_WARPS, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc); LAUNCHED(); }
+                else { k_decode<1><<<(nc + 2 * ctx->qgpw - 1) / (2 * ctx->qgpw), 64, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->qgpw); LAUNCHED(); }
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
                 k_decode<0><<<nb, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
                 k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], ctx->side[0]));
-                k_decode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, ctx->side[0]>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], ctx->side[0]));
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], ctx->side[1]));
-                k_decode<2><<<nb, 32, 0, ctx->side[1]>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], ctx->side[1]));
-                CK(cudaEventRecord(ctx->join_ev[0], ctx->side[0]));
-                CK(cudaEventRecord(ctx->join_ev[1], ctx->side[1]));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
+                k_decode<2><<<nb, 32, 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
+                CK(cudaEventRecord(ctx->join_ev[0], side0));
+                CK(cudaEventRecord(ctx->join_ev[1], side1));
                 CK(cudaStreamWaitEvent(s, ctx->join_ev[0], 0));
                 CK(cudaStreamWaitEvent(s, ctx->join_ev[1], 0));
             }
@@ -607,10 +648,15 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_RC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->rc_lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_SERIAL")) ctx->serial_encoder = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_QDEC")) ctx->qdec_octets = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_SERIAL_ROLES")) ctx->serial_roles = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_QGPW")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ctx->qgpw = (uint32_t)v; }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (int k = 0; k < 2; k++)
-        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess ||
+        if (cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, k == 0 ? prio_hi : prio_lo) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     *out = ctx;

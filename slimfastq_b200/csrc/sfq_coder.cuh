@@ -464,7 +464,7 @@ struct SfqPower {
         rc.encode(sumf + i, f + 1u, tot + 256u);
         update(i, f, sym, tot);
     }
-    SFQ_HD uint32_t get(SfqDec &rc) {                              // power_ranger.hpp:108-130
+    template <class RC> SFQ_HD uint32_t get(RC &rc) {              // power_ranger.hpp:108-130
         const uint32_t tot = m[336];
         const uint32_t prob = rc.get_freq(tot + 256u);
         uint32_t cum = 0, g = 0;

@@ -565,7 +565,7 @@ k_qlt_model(const SfqChunkMeta *__restrict__ metas, SfqWorkspace ws, SfqEnc2Ws e
                             const uint32_t *es = e2.esorted + ec.eoff;
                             for (uint32_t k = 0; k < sg.count; k++) ex.put(sink, es[k] >> 24);
                         }
-                    } else {
+                    } else if (metas[sg.chunk].status == SFQ_OK) {     // (a chunk that overflowed its escape list was not scattered)
                         m.reset();
                         src = e2.sorted + ec.qoff; dst = e2.qsteps + ec.qoff;
                         p = sg.start; end = sg.start + sg.count;

@@ -238,6 +238,8 @@ struct SfqRecTables {
     uint64_t *boff, *qoff, *hoff, *ooff;
 };
 
+#include "sfq_qlt_dec.cuh"
+
 __global__ void __launch_bounds__(32)
 k_decode_usr(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
              SfqWorkspace ws, SfqRecTables t, uint32_t nchunks) {
@@ -267,18 +269,21 @@ k_gen_exceptions(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__
 }
 
 template <int ROLE>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(ROLE == 1 ? 64 : 32)
 k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
          SfqWorkspace ws, SfqRecTables t, uint8_t *bases, uint8_t *quals, uint8_t *hdrs, uint32_t nchunks, uint32_t lanes) {
     __shared__ uint32_t lut[ROLE == 0 ? SFQ_B2_LUT : 1];       // reciprocals of the 4-symbol model's totals
     __shared__ uint4 cells[ROLE == 0 ? 64 : 1];                // bucket look-ahead, two 16-byte cells per thread
     if (ROLE == 0) { sfq_b2_lut_fill(lut, threadIdx.x, 32); __syncthreads(); }
     if (ROLE == 1) {
-        const uint32_t c = blockIdx.x * (32 / SFQ_QG) + threadIdx.x / SFQ_QG;
-        if (c >= nchunks || metas[c].status != SFQ_OK) return;
+        // `lanes` = groups (chunks) per warp: fewer groups per warp means fewer groups waiting on each
+        // other's divergent branches and memory round trips (the chain is latency-bound, lanes are cheap)
+        const uint32_t gw = (threadIdx.x & 31u) / SFQ_QG;
+        const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes + gw;
+        if (gw >= lanes || c >= nchunks || metas[c].status != SFQ_OK) return;
         const SfqDecChunk &d = dc[c];
         SfqQGroup g;
-        g.lane = threadIdx.x % SFQ_QG; g.gbase = threadIdx.x & ~(SFQ_QG - 1u); g.gmask = ((1u << SFQ_QG) - 1u) << g.gbase;
+        g.lane = threadIdx.x % SFQ_QG; g.gbase = threadIdx.x & 31u & ~(SFQ_QG - 1u); g.gmask = ((1u << SFQ_QG) - 1u) << g.gbase;
         sfq_qlt_decode_group(in, d.ssize, d.soff, &metas[c], d.level, ws.qtab + (size_t)c * ws.qtab_words, ws.cbits,
                              ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS, t.qlen + d.rec_base, t.qoff + d.rec_base, quals, g);
         return;

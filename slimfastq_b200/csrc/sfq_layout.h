@@ -16,11 +16,12 @@ static inline uint32_t sfq_q_cbits(int level, uint32_t grow) {
     uint32_t b = (level == 2 ? 15u : 14u) + grow;
     return b > 16 ? 16 : b;
 }
-// Decoder-side quality-context hash: entries for a load factor <= 2/3 at `contexts` visited contexts
-// (recorded in the blob header), or the direct table when that would be as large.
+// Decoder-side quality-context hash: entries for a load factor <= 1/2 at `contexts` visited contexts
+// (recorded in the blob header; every extra probe is a memory round trip on the decoder's serial chain),
+// or the direct table when that would be as large.
 static inline uint32_t sfq_q_entries(int level, uint64_t contexts, uint32_t grow) {
     if (level <= 1) return 4096;
-    uint64_t e = (contexts + (contexts >> 1) + 64) << grow;
+    uint64_t e = (2 * contexts + 64) << grow;
     return (uint32_t)(e >= 65536 ? 65536 : e);
 }
 static inline uint64_t sfq_qhash_bytes(int level, uint32_t cbits) { return (level <= 1 ? 4096ull : (1ull << cbits)) * SFQ_L64_WORDS * 4; }
@@ -40,8 +41,8 @@ static inline uint64_t sfq_gtable_bytes(int level, uint32_t hbits) {
 static inline uint32_t sfq_gen_nbuckets(int level, uint64_t contexts, uint32_t grow) {
     if (level <= 1) return 1;
     uint64_t slots = (contexts + (contexts >> 1) + 64) << grow;
-    uint64_t nb = (slots + 3) / 4;
-    return (uint32_t)(nb > 0x7fffffffull ? 0x7fffffffull : nb);
+    uint64_t nb = ((slots + 15) / 16) * 4;                      // whole 128-byte lines of four buckets
+    return (uint32_t)(nb > 0x7ffffffcull ? 0x7ffffffcull : nb);
 }
 static inline uint64_t sfq_gbuckets_bytes(int level, uint32_t nbuckets) {
     return level <= 1 ? (1ull << 18) * 4 : (uint64_t)nbuckets * 32;

@@ -189,18 +189,27 @@ SFQ_HD void sfq_b2_lut_fill(uint32_t *lut, uint32_t first, uint32_t step) {
     for (uint32_t t = first; t < SFQ_B2_LUT; t += step) lut[t] = t < 2 ? 0xffffffffu : sfq_recip_u32(t);
 }
 
-// Decoder-side base-context table: `nb` buckets of 4 slots, slot = (ctx+1) << 32 | freq[4].
-// A context's home bucket is chosen by its PARENT (ctx >> 2, i.e. without the newest base): the bucket
-// of base i+1 then depends only on the context of base i, so it can be requested from memory before
-// base i is decoded and the table's HBM latency overlaps the coder arithmetic of the previous base.
+// Decoder-side base-context table: `nb` buckets of 4 slots (nb a multiple of 4), slot = (ctx+1) << 32 | freq[4];
+// four consecutive buckets share one 128-byte line.
+// The LINE of a context is chosen by its grandparent (ctx >> 4, i.e. without the two newest bases) and the
+// bucket inside the line by the older of those two bases: the line of base i+2 and the bucket of base i+1
+// therefore depend only on the context of base i.  While base i is being decoded the line of base i+2 is
+// prefetched into L2 and the bucket of base i+1 is copied to shared memory, so the table's HBM latency is
+// spread over two links of the chain and the bucket copy itself is an L2 hit.
 // (Level 1 keeps the direct 2^18 x u32 table, stored ^0x03030303.)
 struct SfqGenBuckets {
     uint64_t *slots;
-    uint32_t nb, used, dense;
-    SFQ_HD void init(void *mem, uint32_t nbuckets, bool is_dense) { slots = (uint64_t *)mem; nb = nbuckets; used = 0; dense = is_dense; }
-    SFQ_HD uint32_t home(uint32_t ctx) const { return sfq_umulhi((ctx >> 2) * 2654435761u, nb); }
+    uint32_t nb, nl, used, dense;
+    SFQ_HD void init(void *mem, uint32_t nbuckets, bool is_dense) { slots = (uint64_t *)mem; nb = nbuckets & ~3u; nl = nb >> 2; used = 0; dense = is_dense; }
+    SFQ_HD uint32_t home(uint32_t ctx) const { return 4u * sfq_umulhi((ctx >> 4) * 2654435761u, nl) + ((ctx >> 2) & 3u); }
     // home bucket of whichever context follows `ctx` (mask = context mask of the level)
-    SFQ_HD uint32_t next_home(uint32_t ctx, uint32_t mask) const { return sfq_umulhi((ctx & (mask >> 2)) * 2654435761u, nb); }
+    SFQ_HD uint32_t next_home(uint32_t ctx, uint32_t mask) const { return 4u * sfq_umulhi(((ctx >> 2) & (mask >> 4)) * 2654435761u, nl) + (ctx & 3u); }
+    // line of whichever context comes two bases after `ctx`
+    SFQ_HD uint32_t line_after2(uint32_t ctx, uint32_t mask) const { return sfq_umulhi((ctx & (mask >> 4)) * 2654435761u, nl); }
+    SFQ_HD void prefetch_line(uint32_t line) const {
+        const uint64_t *p = slots + 16ull * line;
+        sfq_prefetch(p); sfq_prefetch(p + 4); sfq_prefetch(p + 8); sfq_prefetch(p + 12);
+    }
 };
 SFQ_HD void sfq_ld_bucket(const uint64_t *p, uint32_t (&k)[4], uint32_t (&v)[4]) {
 #if defined(__CUDA_ARCH__)
@@ -329,7 +338,10 @@ SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_
         uint32_t bk = DENSE ? 0u : tab.home(last & mask), bkn = 0;
         uint32_t k[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
         uint32_t pj = 4, pkey = 0, pfv = 0;     // slot of the current bucket written after it was loaded (4 = none)
-        if (!DENSE && llen) stage.request(tab.slots + 4ull * bk);
+        if (!DENSE && llen) {
+            stage.request(tab.slots + 4ull * bk);
+            if (llen > 1) tab.prefetch_line(tab.next_home(last & mask, mask) >> 2);
+        }
         for (uint32_t i = 0; i < llen; i++) {
             const uint32_t ctx = last & mask;
             uint32_t fv;
@@ -358,6 +370,7 @@ SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_
                 // use it in the next iteration
                 bkn = tab.next_home(ctx, mask);
                 if (i + 1 < llen) stage.request(tab.slots + 4ull * bkn);      // (never two copies in flight into the same cells)
+                if (i + 2 < llen) tab.prefetch_line(tab.line_after2(ctx, mask));
             }
             const uint32_t f0 = fv & 0xff, f1 = (fv >> 8) & 0xff, f2 = (fv >> 16) & 0xff, f3 = fv >> 24;
             const uint32_t tot = f0 + f1 + f2 + f3;
