@@ -234,14 +234,14 @@ def main():
     sampler.start()
     t_c = t_d = 0.0
     launches = 0
-    code_ms_c = code_ms_d = scan_ms = 0.0
+    code_ms_c = code_ms_d = scan_ms = qd_ms = 0.0
     waves_c = waves_d = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         csz, sc, sd = step_device()
         t_c += sc["ms_total"]; t_d += sd["ms_total"]
         launches += sc["kernel_launches"] + sd["kernel_launches"]
-        code_ms_c += sc["ms_code"]; code_ms_d += sd["ms_code"]; scan_ms += sc["ms_scan"]
+        code_ms_c += sc["ms_code"]; code_ms_d += sd["ms_code"]; scan_ms += sc["ms_scan"]; qd_ms += sd["ms_qlt"]
         waves_c += sc["waves"]; waves_d += sd["waves"]
     barrier()
     wall = time.perf_counter() - t0
@@ -315,13 +315,27 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         K_ = args.steps
         value = 2 * tot_bytes * K_ / (dev_ms_max / 1e3) / 1e9
-        # dominant kernel = the coder (k_encode + k_decode launches); algorithmic bytes per launch:
-        # planes in (bases + qualities + headers) + streams out, and the mirror image for decode
+        # Dominant kernel = the quality decoder (k_qlt_decode4, the longest launch of a step).  Algorithmic bytes
+        # per launch: one byte out per quality + the qlt stream bytes in.  Its duration is
+        # measured with CUDA events on the stream it is launched on (sfq_stats.ms_qlt of the decompress call).
         plane_bytes = sc["nbases"] + sc["nquals"] + (n - sc["nbases"] - sc["nquals"] - 6 * sc["nrecords"])
-        alg_per_step = 2 * (plane_bytes + sc["stream_bytes"])
         code_ms = code_ms_c + code_ms_d
-        achieved = alg_per_step * K_ / (code_ms / 1e3) / 1e9
+        qd_bytes = sd["nquals"] + sd["qlt_stream_bytes"]
+        achieved = qd_bytes * K_ / (qd_ms / 1e3) / 1e9
         symbols = sc["nbases"] + sc["nquals"]
+        hdr_bytes = n - sc["nbases"] - sc["nquals"] - 6 * sc["nrecords"]
+
+        def gbps(nbytes, ms):
+            return round(nbytes / (ms / 1e3) / 1e9, 3) if ms > 0 else None
+
+        coder_kernels = {   # every coder kernel group of one step against its own algorithmic bytes (last step's timings)
+            "compress_gen (k_gen_model + k_rc_encode<0>)": gbps(sc["nbases"] + sc["gen_stream_bytes"], sc["ms_gen"]),
+            "compress_qlt (k_qlt_keys/scan/scatter/model + k_rc_encode<1>)": gbps(sc["nquals"] + sc["qlt_stream_bytes"], sc["ms_qlt"]),
+            "compress_rec (k_encode<2>)": gbps(hdr_bytes, sc["ms_rec"]),
+            "decompress_gen (k_decode<0>)": gbps(sd["nbases"] + sd["gen_stream_bytes"], sd["ms_gen"]),
+            "decompress_qlt (k_qlt_decode4)": gbps(sd["nquals"] + sd["qlt_stream_bytes"], sd["ms_qlt"]),
+            "decompress_rec (k_decode<2>)": gbps(hdr_bytes, sd["ms_rec"]),
+        }
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": args.warmup,
             "ms_per_step": round(dev_ms_max / K_, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -335,14 +349,19 @@ def main():
             "wall_s_per_step": round(wall_max / K_, 4),
             "clocks": clocks,
             "gpu_launches": int(launches_sum),
-            "roofline": {"bound": "hbm", "kernel": "k_encode+k_decode (adaptive range coders, 1 thread per chunk-stream)",
+            "roofline": {"bound": "hbm", "kernel": "k_qlt_decode4 (quality decoder: 4 chunks per warp, 8 lanes per chunk)",
                          "achieved": round(achieved, 3), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 6),
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "launch_ms_avg": round(code_ms / max(1, waves_c + waves_d), 3),
-                         "note": "latency-bound serial chains, not bandwidth-bound: see chain"},
-            "chain": {"symbols_per_chunk_stream": round(symbols / 2 / max(1, sc["nchunks"])), "resident_chunks": sc["resident_chunks"],
-                      "waves": sc["waves"], "encode_ns_per_symbol": round(code_ms_c / K_ * 1e6 / (symbols / 2 / sc["nchunks"]) / sc["waves"], 2),
-                      "decode_ns_per_symbol": round(code_ms_d / K_ * 1e6 / (symbols / 2 / sc["nchunks"]) / max(1, sd["waves"]), 2)},
+                         "traffic": None, "traffic_note": "profiles/: dram bytes per decoded quality from the ncu --set full capture (smaller input; a 10 GB launch cannot be replayed)",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "algorithmic_bytes_per_launch": int(qd_bytes / max(1, sd["waves"])),
+                         "launch_ms_avg": round(qd_ms / K_ / max(1, sd["waves"]), 3),
+                         "note": "a serial adaptive-coder chain per chunk: bound by issue slots and dependent latency, not by HBM (see chain and DESIGN.md section 3)"},
+            "coder_kernels_GBps": coder_kernels,
+            "chain": {"symbols_per_chunk_stream": round(symbols / 2 / max(1, sc["nchunks"])),
+                      "compress": {"resident_chunks": sc["resident_chunks"], "waves": sc["waves"],
+                                   "ns_per_symbol_per_wave": round(code_ms_c / K_ * 1e6 / (symbols / 2 / sc["nchunks"]) / max(1, sc["waves"]), 2)},
+                      "decompress": {"resident_chunks": sd["resident_chunks"], "waves": sd["waves"],
+                                     "ns_per_symbol_per_wave": round(code_ms_d / K_ * 1e6 / (symbols / 2 / sc["nchunks"]) / max(1, sd["waves"]), 2)}},
             "roofline_scan": {"bound": "hbm", "kernel": "k_count_newlines+k_scan_tiles+k_fill_lines", "achieved": round((n + 8 * 4 * sc["nrecords"]) * K_ / (scan_ms / 1e3) / 1e9, 2),
                               "peak": hbm_peak, "unit": "GB/s", "frac": round((n + 32 * sc["nrecords"]) * K_ / (scan_ms / 1e3) / 1e9 / hbm_peak, 4)},
             "phases_ms_per_step": {"c_scan": round(scan_ms / K_, 3), "c_code": round(code_ms_c / K_, 3), "d_code": round(code_ms_d / K_, 3),

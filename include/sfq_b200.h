@@ -66,6 +66,8 @@ typedef struct sfq_stats {
     uint64_t workspace_bytes;     /* model tables resident per wave                           */
     float ms_gen, ms_qlt, ms_rec; /* the three coder kernels of a wave run concurrently; each   */
                                   /* one's own duration, summed over waves                      */
+    uint64_t gen_stream_bytes;    /* bytes of the `gen` streams (bases)                         */
+    uint64_t qlt_stream_bytes;    /* bytes of the `qlt` streams (qualities)                     */
 } sfq_stats;
 
 /* Create a context on CUDA device `device` (-1 = current).  Fails if no device is usable. */

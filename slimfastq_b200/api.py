@@ -31,6 +31,7 @@ class Stats(C.Structure):
         ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_scan", C.c_float),
         ("ms_plan", C.c_float), ("ms_clear", C.c_float), ("ms_code", C.c_float), ("ms_pack", C.c_float),
         ("workspace_bytes", C.c_uint64), ("ms_gen", C.c_float), ("ms_qlt", C.c_float), ("ms_rec", C.c_float),
+        ("gen_stream_bytes", C.c_uint64), ("qlt_stream_bytes", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -65,7 +65,7 @@ struct sfq_ctx {
     std::string err;
     sfq_stats st{};
     uint32_t max_resident = 0;
-    uint32_t lanes = 4;                     // chunk-streams per gen/rec coder warp (SFQ_LANES)
+    uint32_t lanes = 0;                     // chunk-streams per gen/rec coder warp (SFQ_LANES); 0 = by wave size
     int sm_count = 148;
     uint32_t rc_lanes = 8;                  // chunk-streams per warp of the coder-chain kernel (SFQ_RC_LANES)
     cudaEvent_t ev[EV_COUNT]{};
@@ -169,6 +169,11 @@ uint32_t pick_resident(sfq_ctx *ctx, uint64_t nchunks, uint64_t per_chunk, uint6
     r = (nchunks + nw - 1) / nw;
     return (uint32_t)r;
 }
+
+// Chunk-streams per warp of the thread-per-chunk coders: few when the wave is small (the chains are then
+// latency-bound and a lane's slow path stalls fewer neighbours), more when it is large (issue slots are
+// then the scarce resource and a fuller warp spends fewer of them per symbol).
+uint32_t pick_lanes(const sfq_ctx *ctx, uint32_t nc) { return ctx->lanes ? ctx->lanes : nc >= 2048u ? 8u : 4u; }
 
 // kernels index the per-chunk pools by the chunk's position in the wave
 SfqWorkspace ws_at(const SfqWorkspace &ws, uint32_t) { return ws; }
@@ -335,7 +340,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
             {   // fork: gen on the main stream, qlt and rec beside it; join before packing
-                const unsigned nb = (nc + ctx->lanes - 1) / ctx->lanes;
+                const uint32_t lanes = pick_lanes(ctx, nc);
+                const unsigned nb = (nc + lanes - 1) / lanes;
                 const unsigned nwarp_blocks = (nc * 32u + 127u) / 128u;       // one warp per chunk, 4 warps per CTA
                 const SfqEnc2Chunk *d_e2c = ctx->e2_chunks.as<SfqEnc2Chunk>() + c0;
                 uint8_t *abuf = ctx->arena_buf.as<uint8_t>();
@@ -347,7 +353,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     k_gen_model<<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); LAUNCHED();
                     k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes); LAUNCHED();
                 } else {
-                    k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
+                    k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
@@ -362,11 +368,11 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
                     k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes); LAUNCHED();
                 } else {
-                    k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, side0>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
+                    k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, side0>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
-                k_encode<2><<<nb, 32, 0, side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, ctx->lanes); LAUNCHED();
+                k_encode<2><<<nb, 32, 0, side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
                 CK(cudaEventRecord(ctx->join_ev[1], side1));
@@ -416,8 +422,11 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     CK(cudaEventRecord(ctx->ev[EV_CODE_END], s));
     CK(cudaStreamSynchronize(s));
     *out_n = index_off + nchunks * 8ull;
-    st.stream_bytes = 0;
-    for (uint32_t c = 0; c < nchunks; c++) for (int k = 0; k < SFQ_NSTREAMS; k++) st.stream_bytes += arenas[c].size[k];
+    st.stream_bytes = 0; st.gen_stream_bytes = 0; st.qlt_stream_bytes = 0;
+    for (uint32_t c = 0; c < nchunks; c++) {
+        for (int k = 0; k < SFQ_NSTREAMS; k++) st.stream_bytes += arenas[c].size[k];
+        st.gen_stream_bytes += arenas[c].size[SFQ_S_GEN]; st.qlt_stream_bytes += arenas[c].size[SFQ_S_QLT];
+    }
     st.in_bytes = n; st.out_bytes = *out_n;
     st.ms_scan = ev_ms(ctx->ev[EV_H2D], ctx->ev[EV_SCAN]);
     st.ms_plan = ev_ms(ctx->ev[EV_SCAN], ctx->ev[EV_PLAN]);
@@ -437,7 +446,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
     std::vector<SfqDecChunk> dcs(nchunks);
     uint64_t nrec = 0, nb = 0, nq = 0, nh = 0, no = 0, max_bases = 0;
     int max_level = 1;
-    st.stream_bytes = 0;
+    st.stream_bytes = 0; st.gen_stream_bytes = 0; st.qlt_stream_bytes = 0;
     for (uint32_t c = 0; c < nchunks; c++) {
         const SfqBlobHeader &b = blobs[c];
         const uint64_t off = index[c];
@@ -452,6 +461,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         uint64_t o = off + sizeof(SfqBlobHeader);
         d.rec_first_off = o; d.rec_first_len = b.rec_first_len; o += b.rec_first_len;
         for (int k = 0; k < SFQ_NSTREAMS; k++) { d.soff[k] = o; d.ssize[k] = b.ssize[k]; o += b.ssize[k]; st.stream_bytes += b.ssize[k]; }
+        st.gen_stream_bytes += b.ssize[SFQ_S_GEN]; st.qlt_stream_bytes += b.ssize[SFQ_S_QLT];
         d.level = (int32_t)b.level;
         d.rec_base = nrec; d.base_plane = nb; d.qual_plane = nq; d.hdr_plane = nh;
         nrec += b.nrec; nb += b.nbases; nq += b.nquals; nh += SFQ_HDR_PLANE(&m); no += b.out_len;
@@ -532,7 +542,8 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
             k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, nc); LAUNCHED();
             {
-                const unsigned nb = (nc + ctx->lanes - 1) / ctx->lanes;
+                const uint32_t lanes = pick_lanes(ctx, nc);
+                const unsigned nb = (nc + lanes - 1) / lanes;
                 uint8_t *pb = ctx->bases.as<uint8_t>(), *pq = ctx->quals.as<uint8_t>(), *ph = ctx->hdrs.as<uint8_t>();
                 CK(cudaEventRecord(ctx->fork_ev, s));
                 CK(cudaStreamWaitEvent(side0, ctx->fork_ev, 0));
@@ -544,11 +555,11 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 else { k_decode<1><<<(nc + 2 * ctx->qgpw - 1) / (2 * ctx->qgpw), 64, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->qgpw); LAUNCHED(); }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
-                k_decode<0><<<nb, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
+                k_decode<0><<<nb, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
                 k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
-                k_decode<2><<<nb, 32, 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->lanes); LAUNCHED();
+                k_decode<2><<<nb, 32, 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
                 CK(cudaEventRecord(ctx->join_ev[1], side1));

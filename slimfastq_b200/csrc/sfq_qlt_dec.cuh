@@ -11,8 +11,8 @@
 //   words 0..3   freq[8L .. 8L+7]            (u16 each)
 //   words 4..5   symbol of slot 8L+k XOR (8L+k), one byte each  -> zeroed memory is the reference's start state
 //   word  6      total (bits 0..21) | count (bits 24..31), replicated in every lane
-//   word  7      sum of freq over the slots of lanes < L (bits 0..21); in lane 0 instead: hash key (bits 0..15)
-//                and the occupied flag (bit 16)
+//   word  7      sum of freq over the slots of lanes < L; in lane 0 (whose sum is 0 by definition) the hash key.
+//                An entry is occupied once its total is non-zero - every update adds to it
 // so a lane needs nothing from its neighbours to place `code` among its eight cumulative frequencies: one
 // division (range / total), eight multiply-compares, one ballot to pick the lane, two shuffles to broadcast
 // the slot.  range / totFreq and the search "largest cum with cum * r <= code" replace the reference's
@@ -105,28 +105,32 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
     if (live) live = metas[c].status == SFQ_OK;
     const bool valid = live;
 
-    uint32_t nrec = 0, nent = 1;
-    int level = 3;
+    uint32_t nrec = 0, nent = 1, level = 3;
     bool dense = true;
     uint32_t *tab = ws.qtab, *pwq = ws.pw;
     const uint32_t *qlen_tab = t.qlen;
+    uint8_t *oplane = quals;
     SfqQdCoder rc;
-    SfqQdSink out;
     rc.idle();
-    out.start(quals);
     if (live) {
         const SfqDecChunk &d = dc[c];
         nrec = metas[c].nrec;
-        level = d.level;
+        level = (uint32_t)d.level;
         nent = ws.cbits;
-        dense = level <= 1 || nent >= 65536u;
+        dense = level <= 1u || nent >= 65536u;
         tab = ws.qtab + (size_t)c * ws.qtab_words;
         pwq = ws.pw + ((size_t)c * SFQ_PW_PER_CHUNK + SFQ_PW_QEX) * SFQ_PW_WORDS;
         qlen_tab = t.qlen + d.rec_base;
         rc.start(in + d.soff[SFQ_S_QLT], d.ssize[SFQ_S_QLT]);
-        out.start(quals + d.qual_plane);
+        oplane = quals + d.qual_plane;
     }
-    uint8_t *const out_first = out.p;
+    tab += l8 * 8u;                                             // this lane's 32 bytes of every entry
+    // decoded qualities of a chunk are contiguous in the plane: eight bytes are gathered in two registers and
+    // stored as one aligned word; `opos` counts from the aligned address at or below the chunk's first byte
+    uint8_t *const obase = (uint8_t *)((uintptr_t)oplane & ~(uintptr_t)7);
+    const uint32_t ohead = (uint32_t)((uintptr_t)oplane & 7u);
+    uint32_t opos = ohead, alo = 0, ahi = 0;
+    const uint32_t lmask = level <= 1u ? 0xfffu : 0xffffu;
 
     // record cursor: r = record, i = position inside it; empty records are skipped
     uint32_t r = 0, i = 0, qlen = 0;
@@ -142,34 +146,41 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
     }
     SFQ_QD_OPEN(live)
 
-    SfqQCtx cs;
-    cs.reset();
+    // context state (qlts.hpp:52-74, qlts.cpp:109-134): `last` for levels 1-2; previous / one-before symbols
+    // and the running drop sum for levels 3-4
+    uint32_t last = 0, p1 = 0, p2 = 0, dl = 5;
     uint32_t ctx = 0, h = 0, used = 0;
     bool full = false;
     SfqQdModel m;
     m.f0 = m.f1 = m.f2 = m.f3 = m.f4 = m.f5 = m.f6 = m.f7 = 0; m.sx = m.sy = m.hdr = m.excl = 0;
-    if (live) sfq_qd_load(m, tab + (size_t)h * 64u + l8 * 8u);
+    uint4 na = make_uint4(0, 0, 0, 0), nb = make_uint4(0, 0, 0, 0);      // the next model, as loaded
+    if (live) { na = __ldcg(reinterpret_cast<const uint4 *>(tab)); nb = __ldcg(reinterpret_cast<const uint4 *>(tab + 4)); }
+    bool fresh = live;                                                    // na/nb hold a model not yet unpacked
     bool chk = live && !dense;
 
     while (__any_sync(FULL, live)) {
+        if (fresh) {
+            m.f0 = na.x & 0xffffu; m.f1 = na.x >> 16; m.f2 = na.y & 0xffffu; m.f3 = na.y >> 16;
+            m.f4 = na.z & 0xffffu; m.f5 = na.z >> 16; m.f6 = na.w & 0xffffu; m.f7 = na.w >> 16;
+            m.sx = nb.x; m.sy = nb.y; m.hdr = nb.z; m.excl = nb.w;
+        }
         // ---------------------------------------------------------------- the entry of `ctx` (hash probe)
+        // An entry is in use once its total is non-zero (every update adds to it, and every lane holds the
+        // total); lane 0 keeps the 16-bit key in its otherwise unused prefix word.
         if (__any_sync(FULL, chk)) {
             uint32_t probes = 0;
             for (;;) {
-                bool bad = false, claim = false;
-                if (chk && l8 == 0) {
-                    if (!((m.excl >> 16) & 1u)) claim = true;
-                    else if ((m.excl & 0xffffu) != ctx) bad = true;
-                }
-                const unsigned vb = __ballot_sync(FULL, bad), vc = __ballot_sync(FULL, claim);
-                if ((vc >> osh) & 1u) {                                   // first visit of this context in the chunk
+                const bool occ = (m.hdr & 0x3fffffu) != 0u;
+                const unsigned vb = __ballot_sync(FULL, chk && occ && l8 == 0 && m.excl != ctx);
+                const bool bad = (vb >> osh) & 1u;
+                if (chk && !occ) {                                        // first visit of this context in the chunk
                     if (used + 1u >= nent) { full = true; live = false; }
-                    else { used++; if (l8 == 0) m.excl = ctx | 0x10000u; }
+                    else { used++; if (l8 == 0) m.excl = ctx; }
                     chk = false;
-                } else if ((vb >> osh) & 1u) {                            // somebody else's entry: walk on
+                } else if (chk && bad) {                                  // somebody else's entry: walk on
                     h = h + 1u == nent ? 0u : h + 1u;
                     if (++probes > nent) { full = true; live = false; chk = false; }
-                    else sfq_qd_load(m, tab + (size_t)h * 64u + l8 * 8u);
+                    else sfq_qd_load(m, tab + (size_t)h * 64u);
                 } else chk = false;
                 if (!vb) break;
             }
@@ -179,25 +190,27 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
         // ---------------------------------------------------------------- Log64Ranger::get (log64_ranger.hpp:114-138)
         const uint32_t tot = m.hdr & 0x3fffffu, count = m.hdr >> 24;
         const uint32_t rr = rc.range / (tot + 64u);
-        const uint32_t e0 = (l8 ? (m.excl & 0x3fffffu) : 0u) + 8u * l8;
+        const uint32_t e0 = (l8 ? m.excl : 0u) + 8u * l8;
         const uint32_t c0 = e0 + m.f0 + 1u, c1 = c0 + m.f1 + 1u, c2 = c1 + m.f2 + 1u, c3 = c2 + m.f3 + 1u,
                        c4 = c3 + m.f4 + 1u, c5 = c4 + m.f5 + 1u, c6 = c5 + m.f6 + 1u, c7 = c6 + m.f7 + 1u;
-        const bool hi = (uint32_t)(rc.code >> 32) != 0u;                    // only a corrupt stream
-        const uint32_t code32 = (uint32_t)rc.code;
-        const bool g0 = hi || code32 >= c0 * rr, g1 = hi || code32 >= c1 * rr, g2 = hi || code32 >= c2 * rr, g3 = hi || code32 >= c3 * rr,
-                   g4 = hi || code32 >= c4 * rr, g5 = hi || code32 >= c5 * rr, g6 = hi || code32 >= c6 * rr, g7 = hi || code32 >= c7 * rr;
-        const uint32_t nle = (uint32_t)g0 + g1 + g2 + g3 + g4 + g5 + g6 + g7;
-        const unsigned sel = (__ballot_sync(FULL, nle < 8u) >> osh) & 0xffu;
+        // (a corrupt stream can leave code >= 2^32: every comparison below is then true, as with the reference's 64-bit quotient)
+        const uint32_t code32 = (uint32_t)(rc.code >> 32) ? 0xffffffffu : (uint32_t)rc.code;
+        const unsigned sel = (__ballot_sync(FULL, code32 < c7 * rr) >> osh) & 0xffu;
         const uint32_t hl = sel ? (uint32_t)(__ffs(sel) - 1) : 7u;          // no lane: corrupt stream, last slot
-        uint32_t hk = sel ? nle : 7u;                                       // (meaningful in lane hl)
-        uint32_t cb = g6 ? c6 : g5 ? c5 : g4 ? c4 : g3 ? c3 : g2 ? c2 : g1 ? c1 : g0 ? c0 : e0;
-        const uint32_t fs = g6 ? m.f7 : g5 ? m.f6 : g4 ? m.f5 : g3 ? m.f4 : g2 ? m.f3 : g1 ? m.f2 : g0 ? m.f1 : m.f0;
-        uint32_t pack;
-        {
-            const uint64_t s64 = ((uint64_t)m.sy << 32) | m.sx;
-            const uint32_t k = hk & 7u;
-            const uint32_t sb = (uint32_t)(s64 >> (8u * k)) & 0xffu;
-            pack = fs | ((sb ^ (8u * l8 + k)) << 16) | (k << 24);
+        uint32_t cb, hk, pack;
+        {   // binary search of code among this lane's thresholds c0..c6 (meaningful in lane hl)
+            const bool g3 = code32 >= c3 * rr;
+            const uint32_t cm = g3 ? c5 : c1;
+            uint32_t lo = g3 ? c3 : e0, hi = g3 ? c7 : c3;
+            const bool g2 = code32 >= cm * rr;
+            const uint32_t cq = g3 ? (g2 ? c6 : c4) : (g2 ? c2 : c0);
+            lo = g2 ? cm : lo; hi = g2 ? hi : cm;
+            const bool g1 = code32 >= cq * rr;
+            lo = g1 ? cq : lo; hi = g1 ? hi : cq;
+            hk = (g3 ? 4u : 0u) + (g2 ? 2u : 0u) + (g1 ? 1u : 0u);
+            const uint32_t sb = __byte_perm(m.sx, m.sy, hk) & 0xffu;
+            cb = lo;
+            pack = (hi - lo - 1u) | ((sb ^ (8u * l8 + hk)) << 16) | (hk << 24);
         }
         cb = __shfl_sync(FULL, cb, hl, 8);                                   // the chosen slot, from its lane
         pack = __shfl_sync(FULL, pack, hl, 8);
@@ -209,11 +222,11 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
             rc.code -= tt;
             rc.range = rr * (f + 1u);
         }
-        {   // renormalise: n whole bytes at once unless the carry guard (coder.hpp:95-96) could fire
+        {   // renormalise: n whole bytes at once.  The carry guard (coder.hpp:95-96) can only fire when bits
+            // 32..39 of low are all ones (for any of the n byte steps); then take the reference's loop.
             const uint32_t n = act ? (uint32_t)__clz((int)rc.range) >> 3 : 0u;
-            const uint32_t l32 = (uint32_t)(rc.low >> 32) & 0xffffffu, l24 = (uint32_t)(rc.low >> 24) & 0xffffffu, l16 = (uint32_t)(rc.low >> 16) & 0xffffffu;
-            const bool risky = act && n && (l32 == 0xffffffu || (n > 1u && l24 == 0xffffffu) || (n > 2u && l16 == 0xffffffu));
-            if (n && !risky) {
+            const bool risky = n != 0u && ((uint32_t)(rc.low >> 32) & 0xffu) == 0xffu;
+            if (n != 0u && !risky) {
                 const uint32_t v = sfq_src_take(rc.src, n);
                 rc.code = (rc.code << (8u * n)) | v;
                 rc.range <<= 8u * n;
@@ -239,32 +252,42 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
 
         // ---------------------------------------------------------------- output, next position, next context
         if (act) {
-            const uint32_t k = (uint32_t)((uintptr_t)out.p & 7u);
-            out.acc |= (uint64_t)((b + 33u) & 0xffu) << (8u * k);
-            out.p++;
+            const uint32_t k = opos & 7u;
+            const uint32_t v = ((b + 33u) & 0xffu) << (8u * (k & 3u));
+            if (k & 4u) ahi |= v; else alo |= v;
+            opos++;
             if (k == 7u) {
                 if (l8 == 0) {
-                    if (out.p - 8 >= out_first) *reinterpret_cast<uint64_t *>(out.p - 8) = out.acc;
-                    else for (uint8_t *q = out_first; q < out.p; q++) *q = (uint8_t)(out.acc >> (8u * (uint32_t)((uintptr_t)q & 7u)));
+                    if (opos - 8u >= ohead) *reinterpret_cast<uint2 *>(obase + (opos - 8u)) = make_uint2(alo, ahi);
+                    else for (uint32_t q = ohead; q < 8u; q++) obase[q] = (uint8_t)((q & 4u ? ahi : alo) >> (8u * (q & 3u)));
                 }
-                out.acc = 0;
+                alo = 0; ahi = 0;
             }
             i++;
         }
         const bool endrec = act && i == qlen;
-        if (endrec) { cs.reset(); r++; }
-        else sfq_q_next(cs, level, (uint8_t)b);
+        {   // qlts.hpp:52-74; b is not clamped when it feeds the context
+            const uint32_t b8 = b & 0xffu;
+            const uint32_t l12 = (b8 | (last << 6)) & lmask;
+            dl += p1 > b8 ? p1 - b8 : 0u;
+            const uint32_t d3 = dl >> 3;
+            const uint32_t l3 = (b8 | ((p1 > p2 ? p1 : p2) << 6) | ((p1 == p2 ? 1u : 0u) << 12) | ((d3 < 7u ? d3 : 7u) << 13)) & 0xffffu;
+            p2 = p1; p1 = b8;
+            last = level >= 3u ? l3 : l12;
+            if (endrec) { last = 0; p1 = 0; p2 = 0; dl = 5; r++; }
+        }
         SFQ_QD_OPEN(endrec)
-        const uint32_t nctx = cs.last;
+        const uint32_t nctx = last;
 
         // ---------------------------------------------------------------- request the next model before updating this one
-        const bool ld = live && nctx != ctx;
+        fresh = live && nctx != ctx;
         uint32_t hn = h;
-        SfqQdModel mn = m;
-        if (ld) {
+        if (fresh) {
             hn = dense ? nctx : __umulhi(nctx * 2654435761u, nent);
             if (!dense && hn == h) hn = h + 1u == nent ? 0u : h + 1u;       // entry h is ours (key = ctx): skip it unseen, its store is still pending
-            sfq_qd_load(mn, tab + (size_t)hn * 64u + l8 * 8u);
+            const uint32_t *e = tab + (size_t)hn * 64u;
+            na = __ldcg(reinterpret_cast<const uint4 *>(e));
+            nb = __ldcg(reinterpret_cast<const uint4 *>(e + 4));
         }
 
         // ---------------------------------------------------------------- update_freq (log64_ranger.hpp:69-87)
@@ -290,14 +313,15 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
             }
         }
         const bool upd = act && !skip;
+        const bool mine = upd && l8 == hl;
         if (upd) {
             fn += 6u;
             tot2 += 6u;
-            if (l8 == hl) {
-                m.f0 = hk == 0u ? fn : m.f0; m.f1 = hk == 1u ? fn : m.f1; m.f2 = hk == 2u ? fn : m.f2; m.f3 = hk == 3u ? fn : m.f3;
-                m.f4 = hk == 4u ? fn : m.f4; m.f5 = hk == 5u ? fn : m.f5; m.f6 = hk == 6u ? fn : m.f6; m.f7 = hk == 7u ? fn : m.f7;
-            }
             if (l8 > hl) m.excl += 6u;
+        }
+        if (mine) {
+            m.f0 = hk == 0u ? fn : m.f0; m.f1 = hk == 1u ? fn : m.f1; m.f2 = hk == 2u ? fn : m.f2; m.f3 = hk == 3u ? fn : m.f3;
+            m.f4 = hk == 4u ? fn : m.f4; m.f5 = hk == 5u ? fn : m.f5; m.f6 = hk == 6u ? fn : m.f6; m.f7 = hk == 7u ? fn : m.f7;
         }
         uint32_t cnt2 = count;
         const bool cand = upd && slot != 0u;                                 // `++count` is not evaluated for slot 0
@@ -328,7 +352,7 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
                         m.excl += fn - fprev;                                 // (hl >= 1 here: lane 0's word keeps the key)
                     } else {
                         const uint32_t k1 = hk - 1u;
-                        m.f0 = k1 == 0u ? fn : hk == 0u ? fprev : m.f0; m.f1 = k1 == 1u ? fn : hk == 1u ? fprev : m.f1;
+                        m.f0 = k1 == 0u ? fn : m.f0;                            m.f1 = k1 == 1u ? fn : hk == 1u ? fprev : m.f1;
                         m.f2 = k1 == 2u ? fn : hk == 2u ? fprev : m.f2; m.f3 = k1 == 3u ? fn : hk == 3u ? fprev : m.f3;
                         m.f4 = k1 == 4u ? fn : hk == 4u ? fprev : m.f4; m.f5 = k1 == 5u ? fn : hk == 5u ? fprev : m.f5;
                         m.f6 = k1 == 6u ? fn : hk == 6u ? fprev : m.f6; m.f7 = hk == 7u ? fprev : m.f7;
@@ -346,22 +370,19 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
         }
         if (act) {
             m.hdr = tot2 | (cnt2 << 24);
-            uint32_t *e = tab + (size_t)h * 64u + l8 * 8u;
-            if (wide) { sfq_qd_store_freqs(m, e); sfq_qd_store_tail(m, e); }
-            else {
-                if (l8 == hl && upd) sfq_qd_store_freqs(m, e);
-                sfq_qd_store_hdr(m, e);
-            }
+            uint32_t *e = tab + (size_t)h * 64u;
+            if (wide || mine) sfq_qd_store_freqs(m, e);
+            if (wide) sfq_qd_store_tail(m, e); else sfq_qd_store_hdr(m, e);
         }
-        if (ld) { m = mn; h = hn; ctx = nctx; chk = !dense; }
+        if (fresh) { h = hn; ctx = nctx; chk = !dense; }
     }
 #undef SFQ_QD_OPEN
 #undef SFQ_QD_BC32
 #undef SFQ_QD_BC64
     if (valid && l8 == 0) {
         // the last partial word
-        uint8_t *w = (uint8_t *)((uintptr_t)out.p & ~(uintptr_t)7);
-        for (uint8_t *q = w < out_first ? out_first : w; q < out.p; q++) *q = (uint8_t)(out.acc >> (8u * (uint32_t)((uintptr_t)q & 7u)));
+        const uint32_t w0 = opos & ~7u;
+        for (uint32_t q = w0 < ohead ? ohead : w0; q < opos; q++) obase[q] = (uint8_t)((q & 4u ? ahi : alo) >> (8u * (q & 3u)));
         if (full && metas[c].status == SFQ_OK) metas[c].status = SFQ_E_TABLE;
     }
 }
