@@ -102,6 +102,23 @@ int sfq_decompressed_size(const uint8_t *sfq, size_t n, uint64_t *out_n, int *le
 
 int sfq_get_stats(const sfq_ctx *ctx, sfq_stats *st);
 
+/* ---- interchange with the reference's own file format -----------------------
+ * The reference writes an 8 KiB-page WORM container (filer.cpp:41-303); one file = one set of streams,
+ * i.e. exactly one chunk of this library's container.  These are host-side format conversions: no
+ * coding happens here and no CUDA device is needed.
+ *   sfq_export_reference   single-chunk container (compress with chunk_bytes >= file size) -> a file the
+ *                          unmodified reference binary decodes (stands where FilerSave / Config::init
+ *                          wrote the pages, filer.cpp:166-242, config.cpp:330-349,382-386)
+ *   sfq_import_reference   reference-written file -> single-chunk container for sfq_decompress (stands
+ *                          where FilerLoad / Config::load_info read them, filer.cpp:246-303, config.cpp:87-107).
+ *                          The file must carry orig.size (absent only when the reference read stdin). */
+int    sfq_is_reference_file(const uint8_t *p, size_t n);
+size_t sfq_export_reference_bound(const uint8_t *sfq, size_t n);
+int    sfq_export_reference(const uint8_t *sfq, size_t n, const char *orig_filename,
+                            uint8_t *out, size_t out_cap, size_t *out_n);
+size_t sfq_import_reference_bound(size_t n);
+int    sfq_import_reference(const uint8_t *ref, size_t n, uint8_t *out, size_t out_cap, size_t *out_n);
+
 #ifdef __cplusplus
 }
 #endif

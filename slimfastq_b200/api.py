@@ -42,6 +42,8 @@ EXPORTS = [
     "sfq_create", "sfq_destroy", "sfq_last_error", "sfq_version", "sfq_set_max_resident", "sfq_host_alloc",
     "sfq_host_free", "sfq_compress", "sfq_compress_device", "sfq_compress_bound", "sfq_decompress",
     "sfq_decompress_device", "sfq_decompressed_size", "sfq_get_stats",
+    "sfq_is_reference_file", "sfq_export_reference_bound", "sfq_export_reference",
+    "sfq_import_reference_bound", "sfq_import_reference",
 ]
 
 _lib = None
@@ -70,6 +72,11 @@ def load_library():
     L.sfq_decompress_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]; L.sfq_decompress_device.restype = C.c_int
     L.sfq_decompressed_size.argtypes = [vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]; L.sfq_decompressed_size.restype = C.c_int
     L.sfq_get_stats.argtypes = [vp, C.POINTER(Stats)]; L.sfq_get_stats.restype = C.c_int
+    L.sfq_is_reference_file.argtypes = [vp, sz]; L.sfq_is_reference_file.restype = C.c_int
+    L.sfq_export_reference_bound.argtypes = [vp, sz]; L.sfq_export_reference_bound.restype = sz
+    L.sfq_export_reference.argtypes = [vp, sz, C.c_char_p, vp, sz, C.POINTER(sz)]; L.sfq_export_reference.restype = C.c_int
+    L.sfq_import_reference_bound.argtypes = [sz]; L.sfq_import_reference_bound.restype = sz
+    L.sfq_import_reference.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]; L.sfq_import_reference.restype = C.c_int
     _lib = L
     return L
 
@@ -168,6 +175,37 @@ def decompressed_size(sfq: bytes) -> tuple[int, int]:
     if rc:
         raise SfqError(rc, "not a b200 chunked .sfq container")
     return n.value, lv.value
+
+
+# ---------------------------------------------------------------------------- the reference's own file format
+# Host-side format conversions (no coding, no GPU): see include/sfq_b200.h.
+def is_reference_file(blob: bytes) -> bool:
+    return bool(load_library().sfq_is_reference_file(C.cast(C.c_char_p(blob), C.c_void_p), len(blob)))
+
+
+def export_reference(sfq: bytes, orig_filename: str = "") -> bytes:
+    """Single-chunk container -> a file the unmodified reference binary decodes."""
+    L = load_library()
+    src = C.cast(C.c_char_p(sfq), C.c_void_p)
+    cap = L.sfq_export_reference_bound(src, len(sfq))
+    out = C.create_string_buffer(cap)
+    on = C.c_size_t()
+    rc = L.sfq_export_reference(src, len(sfq), orig_filename.encode(), C.cast(out, C.c_void_p), cap, C.byref(on))
+    if rc:
+        raise SfqError(rc, "cannot export: not a single-chunk b200 container")
+    return out.raw[:on.value]
+
+
+def import_reference(ref: bytes) -> bytes:
+    """Reference-written .sfq file -> single-chunk container for Codec.decompress."""
+    L = load_library()
+    cap = L.sfq_import_reference_bound(len(ref))
+    out = C.create_string_buffer(cap)
+    on = C.c_size_t()
+    rc = L.sfq_import_reference(C.cast(C.c_char_p(ref), C.c_void_p), len(ref), C.cast(out, C.c_void_p), cap, C.byref(on))
+    if rc:
+        raise SfqError(rc, "cannot import: not a reference .sfq file, or one without orig.size / with oversized-record streams")
+    return out.raw[:on.value]
 
 
 # ---------------------------------------------------------------------------- sharding (multi-GPU)

@@ -13,6 +13,7 @@
 #include "../../include/sfq_b200.h"
 #include "sfq_kernels.cuh"
 #include "sfq_layout.h"
+#include "sfq_worm.h"
 
 namespace {
 
@@ -80,6 +81,7 @@ struct sfq_ctx {
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
            e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff;
+    int gen_ahead2 = -1;                    // SFQ_GEN_AHEAD2=0/1: base decoder's two-ahead line prefetch (default on)
     bool qdec_octets = true;                // SFQ_QDEC=0: the first (sub-warp mask) quality decoder, for A/B runs
     bool serial_roles = false;              // SFQ_SERIAL_ROLES=1: gen, qlt, rec kernels of a wave one after another (diagnosis)
     uint32_t qgpw = 2;                      // quality-decoder groups (chunks) per warp (SFQ_QGPW: 1, 2 or 4)
@@ -328,7 +330,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         CK(cudaMemcpyAsync(d_arenas, arenas.data(), nchunks * sizeof(SfqArena), cudaMemcpyHostToDevice, s));
         h_small[0] = 0; h_small[1] = sizeof(SfqFileHeader); h_small[2] = 0;
         CK(cudaMemcpyAsync(d_scal, h_small, 24, cudaMemcpyHostToDevice, s));
-        SfqWorkspace ws;
+        SfqWorkspace ws{};
         ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
         ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.cbits = level <= 1 ? 4096u : 1u << cbits; ws.pw = ctx->pw.as<uint32_t>();
         for (uint32_t w = 0; w < nwaves; w++) {
@@ -456,7 +458,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         SfqChunkMeta &m = metas[c];
         memset(&m, 0, sizeof m);
         m.text_len = b.text_len; m.out_len = b.out_len; m.nrec = b.nrec; m.nbases = b.nbases; m.nquals = b.nquals;
-        m.hdr_bytes = b.hdr_bytes; m.llen = b.llen; m.solid = b.solid; m.two_id = b.two_id; m.n_byte = b.n_byte;
+        m.hdr_bytes = b.hdr_bytes; m.llen = b.llen; m.solid = b.solid; m.two_id = b.two_id; m.n_byte = b.n_byte; m.pad = b.pad;
         SfqDecChunk &d = dcs[c];
         uint64_t o = off + sizeof(SfqBlobHeader);
         d.rec_first_off = o; d.rec_first_len = b.rec_first_len; o += b.rec_first_len;
@@ -468,7 +470,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         max_bases = std::max<uint64_t>(max_bases, b.nbases);
         max_level = std::max(max_level, (int)b.level);
         // a record prints at least "@h\nb\n+\nq\n": reject headers whose counts cannot match their out_len
-        if (b.out_len < 6ull * b.nrec || (uint64_t)b.nbases + b.nquals + b.hdr_bytes > b.out_len)
+        if (!(b.pad & SFQ_BLOB_IMPORTED) && (b.out_len < 6ull * b.nrec || (uint64_t)b.nbases + b.nquals + b.hdr_bytes > b.out_len))
             return fail(ctx, SFQ_ERR_FORMAT, "chunk %u: inconsistent blob header", c);
     }
     if (no > out_cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)no);
@@ -530,9 +532,10 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         nwaves = (nchunks + R - 1) / R;
         if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
         st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * (gstride + qbytes + pbytes);
-        SfqWorkspace ws;
+        SfqWorkspace ws{};
         ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
         ws.qtab = ctx->qtab.as<uint32_t>(); ws.qtab_words = qbytes / 4; ws.cbits = cbits; ws.pw = ctx->pw.as<uint32_t>();
+        ws.gen_ahead2 = ctx->gen_ahead2 < 0 ? 1u : (uint32_t)ctx->gen_ahead2;
         for (uint32_t w = 0; w < nwaves; w++) {
             const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 0], s));
@@ -659,6 +662,7 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_RC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->rc_lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_SERIAL")) ctx->serial_encoder = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_GEN_AHEAD2")) ctx->gen_ahead2 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QDEC")) ctx->qdec_octets = atoi(e) != 0;
     if (const char *e = getenv("SFQ_SERIAL_ROLES")) ctx->serial_roles = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QGPW")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ctx->qgpw = (uint32_t)v; }
@@ -808,6 +812,101 @@ int sfq_decompress_device(sfq_ctx *ctx, const void *d_sfq, size_t n, void *d_out
     int rc = decompress_on_device(ctx, (const uint8_t *)d_sfq, n, fh, index, blobs, (uint8_t *)d_out, out_cap, out_n);
     if (rc) return rc;
     ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_CODE_END]);
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------ reference file format
+int sfq_is_reference_file(const uint8_t *p, size_t n) {
+    return p && n >= 2 * SFQ_WORM_PAGE && !memcmp(p, SFQ_STAMP, 16) && !sfq_is_chunked_container(p, n);
+}
+
+size_t sfq_export_reference_bound(const uint8_t *sfq, size_t n) {
+    (void)sfq;
+    // every stream rounds up to whole pages and adds one node page per 2047 data pages
+    return n + (size_t)(SFQ_NSTREAMS + 4) * 2 * SFQ_WORM_PAGE + n / SFQ_WORM_NODES + SFQ_WORM_PAGE;
+}
+
+int sfq_export_reference(const uint8_t *sfq, size_t n, const char *orig_filename, uint8_t *out, size_t out_cap, size_t *out_n) {
+    if (!sfq || !out || !out_n) return SFQ_ERR_ARG;
+    if (!sfq_is_chunked_container(sfq, n)) return SFQ_ERR_FORMAT;
+    SfqFileHeader fh;
+    memcpy(&fh, sfq, sizeof fh);
+    if (fh.nchunks != 1) return SFQ_ERR_UNSUPPORTED;               // one reference file = one chunk
+    if (fh.index_off > n || n - fh.index_off < 8) return SFQ_ERR_FORMAT;
+    uint64_t off;
+    memcpy(&off, sfq + fh.index_off, 8);
+    if (off > n || n - off < sizeof(SfqBlobHeader)) return SFQ_ERR_FORMAT;
+    SfqBlobHeader b;
+    memcpy(&b, sfq + off, sizeof b);
+    if (b.magic != SFQ_BLOB_MAGIC || off + sfq_blob_size(&b) > n) return SFQ_ERR_FORMAT;
+    const uint8_t *p = sfq + off + sizeof b;
+    const uint8_t *rec_first = p;
+    p += b.rec_first_len;
+    const uint8_t *stream[SFQ_NSTREAMS];
+    for (int k = 0; k < SFQ_NSTREAMS; k++) { stream[k] = p; p += b.ssize[k]; }
+    std::vector<uint8_t> file;
+    std::string err;
+    if (!sfq_worm_write(b, rec_first, stream, orig_filename, file, err)) return SFQ_ERR_FORMAT;
+    if (file.size() > out_cap) return SFQ_ERR_SPACE;
+    memcpy(out, file.data(), file.size());
+    *out_n = file.size();
+    return 0;
+}
+
+size_t sfq_import_reference_bound(size_t n) { return n + sizeof(SfqFileHeader) + sizeof(SfqBlobHeader) + 0x200 + 64; }
+
+int sfq_import_reference(const uint8_t *ref, size_t n, uint8_t *out, size_t out_cap, size_t *out_n) {
+    if (!ref || !out || !out_n) return SFQ_ERR_ARG;
+    std::map<std::string, std::string> info;
+    std::map<std::string, std::vector<uint8_t>> streams;
+    std::string err;
+    if (!sfq_worm_read(ref, n, info, streams, err)) return SFQ_ERR_FORMAT;
+    auto num = [&](const char *k, long long dflt) { auto it = info.find(k); return it == info.end() || it->second.empty() ? dflt : atoll(it->second.c_str()); };
+    if (num("version", 0) > SFQ_INTERNAL_VERSION) return SFQ_ERR_FORMAT;         // config.cpp:373-377
+    const long long orig = num("orig.size", -1), nrec = num("num_records", 0);
+    if (orig <= 0 || orig >= 0xFFFFFFF0ll || nrec <= 0 || nrec > 0x7fffffffll) return SFQ_ERR_UNSUPPORTED;
+    SfqBlobHeader b;
+    memset(&b, 0, sizeof b);
+    b.magic = SFQ_BLOB_MAGIC;
+    long long level = num("config.level", 2);                                        // config.cpp:363
+    b.level = (uint32_t)(level > 4 ? 4 : level < 1 ? 1 : level);
+    b.text_len = (uint64_t)orig;
+    b.out_len = (uint64_t)orig + 16ull * (uint64_t)nrec + 4096;                      // an upper bound: see SFQ_BLOB_IMPORTED
+    b.nrec = (uint32_t)nrec;
+    b.nbases = b.nquals = b.hdr_bytes = (uint32_t)orig;                              // upper bounds
+    b.llen = (int32_t)num("llen", 0);
+    { auto it = info.find("usr.solid"); b.solid = it != info.end() && !it->second.empty() && it->second[0] != '0'; }   // get_bool, config.cpp:124-127
+    b.two_id = num("usr.2id", 0) != 0;
+    const long long nb = num("gen.N_byte", 'N');
+    b.n_byte = (nb && nb != 'N') ? (uint8_t)nb : 0;
+    b.pad = SFQ_BLOB_IMPORTED;
+    b.extra_hi = (uint32_t)num("qlt.extra.hi", 0);
+    const std::string &first = info["rec.first"];
+    if (first.size() > 399) return SFQ_ERR_UNSUPPORTED;
+    b.rec_first_len = (uint32_t)first.size();
+    uint64_t total = sizeof(SfqFileHeader) + sizeof b + first.size();
+    for (int k = 0; k < SFQ_NSTREAMS; k++) {
+        auto it = streams.find(kSfqStreamNames[k]);
+        const size_t sz = it == streams.end() ? 0 : it->second.size();
+        if (sz > 0xFFFFFF00ull) return SFQ_ERR_UNSUPPORTED;
+        b.ssize[k] = (uint32_t)sz;
+        total += sz;
+    }
+    static const char *const unsupported[] = {"usr.lrec", "usr.lgen", "usr.lqlt"};   // oversized records, usrs.cpp:269-301
+    for (const char *u : unsupported) { auto it = streams.find(u); if (it != streams.end() && !it->second.empty()) return SFQ_ERR_UNSUPPORTED; }
+    if (total + 8 > out_cap) return SFQ_ERR_SPACE;
+    SfqFileHeader fh;
+    sfq_file_header_init(&fh, (int)b.level, (uint64_t)orig, 1, (uint64_t)orig, total, b.out_len);
+    uint8_t *p = out;
+    memcpy(p, &fh, sizeof fh); p += sizeof fh;
+    const uint64_t blob_off = sizeof fh;
+    memcpy(p, &b, sizeof b); p += sizeof b;
+    memcpy(p, first.data(), first.size()); p += first.size();
+    for (int k = 0; k < SFQ_NSTREAMS; k++)
+        if (b.ssize[k]) { memcpy(p, streams[kSfqStreamNames[k]].data(), b.ssize[k]); p += b.ssize[k]; }
+    memcpy(p, &blob_off, 8); p += 8;
+    *out_n = (size_t)(p - out);
     return 0;
 }
 

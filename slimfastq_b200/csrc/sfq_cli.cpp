@@ -50,6 +50,7 @@ Usage: \n\
 -q               : suppress extra stats info that could have been seen by -s \n\
 -c bytes         : chunk size (default 1048576); every chunk is coded as a standalone file \n\
 -g device        : CUDA device index (default 0) \n\
+-R               : write the reference's own file format (one chunk; readable by the original slimfastq) \n\
 \n\
 DWIM (Do what I mean) - Intuitive use of 'slimfastq-b200 A B' : \n\
 If A appears to be a fastq file, and:\n\
@@ -134,11 +135,11 @@ static void statistics_dump(const uint8_t *p, size_t n) {      // config.cpp:76-
 
 int main(int argc, char **argv) {
     std::string usr, fil;
-    bool overwrite = false, statistics = false;
+    bool overwrite = false, statistics = false, ref_format = false;
     int level = 3, device = 0;
     unsigned long long chunk = 1ull << 20;
     if (argc == 1) usage();
-    const char *short_opt = "qPsvhdO1234u:f:l:c:g:";
+    const char *short_opt = "qPsvhdOR1234u:f:l:c:g:";
     for (int opt = getopt(argc, argv, short_opt); opt != -1; opt = getopt(argc, argv, short_opt))
         switch (opt) {
         case 'u': usr = optarg; break;
@@ -149,6 +150,7 @@ int main(int argc, char **argv) {
         case 'g': device = atoi(optarg); break;
         case 'd': g_encode = false; break;
         case 'O': overwrite = true; break;
+        case 'R': ref_format = true; break;
         case 'P': break;                           // profiling cap: accepted, ignored
         case 'q': break;                           // no log.* extras exist in this container
         case 'v': printf("Version 2.04\nInternal format version=%u\n", SFQ_INTERNAL_VERSION); exit(0);
@@ -202,7 +204,15 @@ int main(int argc, char **argv) {
         uint8_t *buf = slurp(in, hint, &n);
         const uint8_t *res = nullptr;
         size_t rn = 0;
+        if (ref_format) chunk = ~0ull >> 1;        // the reference's file holds one set of streams: one chunk
         if (sfq_compress(ctx, buf, n, level, chunk, &res, &rn)) { unlink(fil.c_str()); croak("%s", sfq_last_error(ctx)); }
+        std::vector<uint8_t> paged;
+        if (ref_format) {
+            paged.resize(sfq_export_reference_bound(res, rn));
+            size_t pn = 0;
+            if (sfq_export_reference(res, rn, usr.c_str(), paged.data(), paged.size(), &pn)) { unlink(fil.c_str()); croak("cannot write the reference file format for this input"); }
+            res = paged.data(); rn = pn;
+        }
         if (fwrite(res, 1, rn, out) != rn || fclose(out)) croak("Error writing output: %s", strerror(errno));
         sfq_host_free(buf);
     } else {
@@ -215,17 +225,22 @@ int main(int argc, char **argv) {
             buf = (uint8_t *)malloc(hint + 1);
             n = buf ? fread(buf, 1, hint, in) : 0;
         } else buf = slurp(in, hint, &n);
-        if (!buf || !sfq_is_chunked_container(buf, n)) {
-            if (buf && n >= 16 && !memcmp(buf, SFQ_STAMP, 16))
-                croak("%s is a paged (reference-format) .sfq; this build reads b200.c1 chunked containers", fil.c_str());
-            croak("%s is not a slimfastq file", fil.c_str());
-        }
-        if (statistics) statistics_dump(buf, n);
+        std::vector<uint8_t> imported;
+        const uint8_t *src = buf;
+        if (buf && sfq_is_reference_file(buf, n)) {          // a file written by the original slimfastq: one chunk
+            imported.resize(sfq_import_reference_bound(n));
+            size_t in_n = 0;
+            const int rc = sfq_import_reference(buf, n, imported.data(), imported.size(), &in_n);
+            if (rc == SFQ_ERR_UNSUPPORTED) croak("%s: reference-format file without orig.size or with oversized-record streams is not supported", fil.c_str());
+            if (rc) croak("%s is not a slimfastq file", fil.c_str());
+            src = imported.data(); n = in_n;
+        } else if (!buf || !sfq_is_chunked_container(buf, n)) croak("%s is not a slimfastq file", fil.c_str());
+        if (statistics) statistics_dump(src, n);
         FILE *out = usr.length() ? fopen(usr.c_str(), wr_flags) : stdout;
         if (!out) { fprintf(stderr, "Can't write file '%s': %s\n", usr.c_str(), strerror(errno)); exit(1); }
         const uint8_t *res = nullptr;
         size_t rn = 0;
-        if (sfq_decompress(ctx, buf, n, &res, &rn)) { if (usr.length()) unlink(usr.c_str()); croak("%s", sfq_last_error(ctx)); }
+        if (sfq_decompress(ctx, src, n, &res, &rn)) { if (usr.length()) unlink(usr.c_str()); croak("%s", sfq_last_error(ctx)); }
         if (fwrite(res, 1, rn, out) != rn || (out != stdout ? fclose(out) : fflush(out))) croak("USR: Error writing output");
         sfq_host_free(buf);
     }

@@ -109,5 +109,6 @@ struct SfqWorkspace {
     uint8_t  *gtab;  uint64_t gtab_stride;  uint32_t hbits;     // base-context tables
     uint32_t *qtab;  uint64_t qtab_words;   uint32_t cbits;     // quality-context tables (hashed); cbits = ENTRIES of one table
     uint32_t *pw;                                                // 256-symbol model pools
+    uint32_t gen_ahead2;                                         // base decoder: prefetch the table line two bases ahead
 };
 

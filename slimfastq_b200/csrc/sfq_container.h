@@ -19,6 +19,11 @@
 #define SFQ_BLOB_MAGIC 0x43514653u                  /* "SFQC" */
 #define SFQ_INTERNAL_VERSION 6                      /* config.cpp:44 */
 
+// Blob flag: the chunk was imported from a reference-written file, whose info stream does not record the
+// plane sizes - nbases / nquals / hdr_bytes / out_len are upper bounds (from orig.size), the decoder
+// establishes the real ones from the usr.* streams.
+#define SFQ_BLOB_IMPORTED 1u
+
 #pragma pack(push, 1)
 struct SfqFileHeader {
     char     stamp[16];
@@ -39,7 +44,7 @@ struct SfqBlobHeader {
     uint32_t nrec;           // num_records
     uint32_t nbases, nquals, hdr_bytes;
     int32_t  llen;           // llen
-    uint8_t  solid, two_id, n_byte, pad;
+    uint8_t  solid, two_id, n_byte, pad;      // pad: flags, SFQ_BLOB_IMPORTED
     uint32_t extra_hi;       // qlt.extra.hi
     uint32_t rec_first_len;  // rec.first follows the header
     uint32_t q_used, g_used; // distinct quality / base contexts touched (decoder table sizing hint; 0 = unknown)

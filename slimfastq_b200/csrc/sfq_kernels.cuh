@@ -298,7 +298,7 @@ k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, Sfq
         SfqStage stage;
         stage.cell0 = &cells[threadIdx.x]; stage.cell1 = &cells[32 + threadIdx.x];
         sfq_gen_decode_chunk(in, d.ssize, d.soff, m, d.level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw,
-                             t.llen + d.rec_base, t.boff + d.rec_base, bases, lut, stage);
+                             t.llen + d.rec_base, t.boff + d.rec_base, bases, lut, stage, ws.gen_ahead2);
     }
     else {
         sfq_rec_decode_chunk(in, d.ssize, d.soff, m, pw, in + d.rec_first_off, d.rec_first_len,

@@ -199,14 +199,15 @@ SFQ_HD void sfq_b2_lut_fill(uint32_t *lut, uint32_t first, uint32_t step) {
 // (Level 1 keeps the direct 2^18 x u32 table, stored ^0x03030303.)
 struct SfqGenBuckets {
     uint64_t *slots;
-    uint32_t nb, nl, used, dense;
-    SFQ_HD void init(void *mem, uint32_t nbuckets, bool is_dense) { slots = (uint64_t *)mem; nb = nbuckets & ~3u; nl = nb >> 2; used = 0; dense = is_dense; }
+    uint32_t nb, nl, used, dense, ahead2;
+    SFQ_HD void init(void *mem, uint32_t nbuckets, bool is_dense) { slots = (uint64_t *)mem; nb = nbuckets & ~3u; nl = nb >> 2; used = 0; dense = is_dense; ahead2 = 1; }
     SFQ_HD uint32_t home(uint32_t ctx) const { return 4u * sfq_umulhi((ctx >> 4) * 2654435761u, nl) + ((ctx >> 2) & 3u); }
     // home bucket of whichever context follows `ctx` (mask = context mask of the level)
     SFQ_HD uint32_t next_home(uint32_t ctx, uint32_t mask) const { return 4u * sfq_umulhi(((ctx >> 2) & (mask >> 4)) * 2654435761u, nl) + (ctx & 3u); }
     // line of whichever context comes two bases after `ctx`
     SFQ_HD uint32_t line_after2(uint32_t ctx, uint32_t mask) const { return sfq_umulhi((ctx & (mask >> 4)) * 2654435761u, nl); }
     SFQ_HD void prefetch_line(uint32_t line) const {
+        if (!ahead2) return;
         const uint64_t *p = slots + 16ull * line;
         sfq_prefetch(p); sfq_prefetch(p + 4); sfq_prefetch(p + 8); sfq_prefetch(p + 12);
     }
@@ -418,12 +419,13 @@ SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_
 SFQ_HDN void sfq_gen_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
                                   SfqChunkMeta *meta, int level, void *table_mem, uint32_t nbuckets,
                                   uint32_t *pwpool, const uint32_t *llen_tab, const uint64_t *boff_tab,
-                                  uint8_t *bases, const uint32_t *lut, SfqStage stage) {
+                                  uint8_t *bases, const uint32_t *lut, SfqStage stage, uint32_t ahead2 = 1) {
     SfqByteSrc src;
     src.start(in + soff[SFQ_S_GEN], ssize[SFQ_S_GEN]);
     (void)pwpool;
     SfqGenBuckets tab;
     tab.init(table_mem, nbuckets, level <= 1);
+    tab.ahead2 = ahead2;
     const uint32_t mask = sfq_gen_mask(level);
     const uint32_t alpha = meta->solid ? 0x33323130u : 0x54474341u;             // "0123" / "ACGT", gens.cpp:173-178
     const uint32_t status = level <= 1
@@ -719,7 +721,10 @@ SFQ_HDN void sfq_usr_decode_chunk(const uint8_t *in, const uint32_t *ssize, cons
         pfq_tab[r] = pf_qlt;
         nb += m_llen; nq += m_qlen;
     }
-    if (nb != meta->nbases || nq != meta->nquals) status = SFQ_E_CORRUPT;
+    if (meta->pad & 1u) {                     // imported from a reference file: the header holds upper bounds
+        if (nb > meta->nbases || nq > meta->nquals) status = SFQ_E_CORRUPT;
+        else { meta->nbases = (uint32_t)nb; meta->nquals = (uint32_t)nq; }
+    } else if (nb != meta->nbases || nq != meta->nquals) status = SFQ_E_CORRUPT;
     if (status != SFQ_OK && meta->status == SFQ_OK) meta->status = status;
 }
 

@@ -47,3 +47,23 @@ def test_cli_roundtrip_pipes_dwim_and_overwrite_guard(tmp_path):
     r = run("-u", str(bad), "-f", str(tmp_path / "bad.sfq"))
     assert r.returncode == 1 and b"slimfastq: encoding" in r.stderr and b"unexpected genome char: X" in r.stderr
     assert not (tmp_path / "bad.sfq").exists()
+
+
+@pytest.mark.gpu
+def test_cli_mixes_with_the_original_slimfastq(tmp_path):
+    """-R writes the reference's own page format; a reference-written file is decoded without a flag."""
+    from oracle import oracle as O
+
+    if not O.have_ref():
+        pytest.skip("oracle/_ref/slimfastq is not built")
+    data = synth.illumina(2500)
+    fq, ours, theirs, back = tmp_path / "a.fq", tmp_path / "ours.sfq", tmp_path / "theirs.sfq", tmp_path / "b.fq"
+    fq.write_bytes(data)
+    assert run("-R", "-u", str(fq), "-f", str(ours)).returncode == 0
+    assert subprocess.run([O.REF_BIN, "-d", "-f", str(ours), "-u", str(back), "-O"]).returncode == 0   # theirs reads ours
+    assert back.read_bytes() == data
+    assert subprocess.run([O.REF_BIN, "-u", str(fq), "-f", str(theirs), "-O", "-q"]).returncode == 0
+    r = run(str(theirs))                                                                              # ours reads theirs
+    assert r.returncode == 0 and r.stdout == data
+    r = run("-s", str(theirs))
+    assert r.returncode == 0 and b"num_records      = 2500" in r.stderr
