@@ -50,7 +50,8 @@ def parse_args():
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "utilization.gpu,utilization.memory")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
@@ -74,16 +75,22 @@ class ClockSampler:
                 self.proc.wait(timeout=3)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons, ug, um, pw = [], 0, set(), [], [], []
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                try:
+                    pw.append(float(r[3])); ug.append(float(r[9])); um.append(float(r[10]))
+                except (ValueError, IndexError):
+                    pass
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except (ValueError, IndexError):
                 pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(pw) if pw else None,
+                "nvidia_smi_utilization_pct": {"gpu": statistics.median(ug) if ug else None, "memory": statistics.median(um) if um else None}}
 
 
 # ------------------------------------------------------------------------------ CPU reference legs
@@ -253,18 +260,26 @@ def main():
     e2e_err = None
     if not args.no_e2e:
         try:
+            # pinned host memory of the leg: input + the library's container and output buffers, on every rank of the node
+            need = world * (2 * n + 2 * csz + (1 << 30))
+            try:
+                import psutil  # noqa: PLC0415
+
+                avail = psutil.virtual_memory().available
+            except ImportError:
+                avail = None
+            if avail is not None and need > 0.8 * avail:
+                raise MemoryError("e2e leg needs %.0f GB of pinned host memory on this node, %.0f GB available" % (need / 1e9, avail / 1e9))
             h_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
             h_text.copy_(d_text)
             torch.cuda.synchronize()
             del d_text, d_sfq, d_back                  # the host-buffer entry points stage through the library's own buffers
             torch.cuda.empty_cache()
-            h_sfq = torch.empty(csz, dtype=torch.uint8, pin_memory=True)
 
             def step_e2e():
-                a, cn = codec.compress_view(h_text, args.level, args.chunk)
+                a, cn = codec.compress_view(h_text, args.level, args.chunk)     # container in the context's pinned buffer
                 s1 = codec.stats()
-                ctypes.memmove(h_sfq.data_ptr(), a, cn)          # keep the container (the result view is reused)
-                b, on = codec.decompress_view(h_sfq[:cn])
+                b, on = codec.decompress_addr(a, cn)                            # (decompress returns into a buffer of its own)
                 s2 = codec.stats()
                 return cn, on, s1, s2, b
 
@@ -292,7 +307,7 @@ def main():
             barrier()
             e_wall = time.perf_counter() - t0
             e2e = {"ms": e_ms, "wall_s": e_wall, "h2d": n + cn, "d2h": cn + n}
-            del h_text, h_sfq
+            del h_text
         elif not e2e_err:
             e2e_err = "another rank could not set up its host buffers"
 

@@ -85,7 +85,8 @@ void  sfq_host_free(void *p);
 
 /* Compress a whole FASTQ buffer held in HOST memory.  level 1..4 (clamped like config.cpp:231-236),
  * chunk_bytes = target chunk size (0 = 1 MiB).  *out points to a context-owned pinned buffer that
- * stays valid until the next call on this context. */
+ * stays valid until the next sfq_compress on this context (sfq_decompress returns into a buffer of
+ * its own, so a container can be handed straight back to it). */
 int sfq_compress(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes,
                  const uint8_t **out, size_t *out_n);
 /* Same with input and output resident in DEVICE memory (16-byte aligned). */

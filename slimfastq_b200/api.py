@@ -142,6 +142,13 @@ class Codec:
         del keep
         return C.cast(out, C.c_void_p).value, on.value
 
+    def decompress_addr(self, addr: int, n: int):
+        """decompress_view for a container already in host memory at `addr` (e.g. compress_view's result)."""
+        out = C.POINTER(C.c_uint8)()
+        on = C.c_size_t()
+        self._check(self._L.sfq_decompress(self._h, addr, n, C.byref(out), C.byref(on)))
+        return C.cast(out, C.c_void_p).value, on.value
+
     def decompress(self, sfq) -> bytes:
         addr, n = self.decompress_view(sfq)
         return C.string_at(addr, n)

@@ -86,7 +86,8 @@ struct sfq_ctx {
     bool serial_roles = false;              // SFQ_SERIAL_ROLES=1: gen, qlt, rec kernels of a wave one after another (diagnosis)
     uint32_t qgpw = 2;                      // quality-decoder groups (chunks) per warp (SFQ_QGPW: 1, 2 or 4)
     bool serial_encoder = false;            // SFQ_ENC_SERIAL=1: single-pass coders (one chain per chunk-stream) for A/B runs
-    HostBuf h_out, h_small;
+    HostBuf h_out, h_out_d, h_small;        // results of compress / decompress (separate: a container returned by
+                                            // sfq_compress may be handed straight to sfq_decompress)
     void release_all() {
         DevBuf *all[] = {&text, &out, &tiles, &tile_prefix, &lines, &scalars, &rec_begin, &r0, &r1, &metas,
                          &arenas, &arena_buf, &blob_off, &gtab, &qtab, &pw, &dchunks, &bhdrs, &bases, &quals,
@@ -95,7 +96,7 @@ struct sfq_ctx {
                          &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks, &rec_qoff};
         for (DevBuf *b : all) b->release();
         scratch.release();
-        h_out.release(); h_small.release();
+        h_out.release(); h_out_d.release(); h_small.release();
     }
 };
 
@@ -769,14 +770,14 @@ int sfq_decompress(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **o
     size_t on = 0;
     rc = decompress_on_device(ctx, ctx->text.as<uint8_t>(), n, fh, index, blobs, ctx->out.as<uint8_t>(), total, &on);
     if (rc) return rc;
-    CK(ctx->h_out.ensure(on + 1));
-    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->out.p, on, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx->h_out_d.ensure(on + 1));
+    CK(cudaMemcpyAsync(ctx->h_out_d.p, ctx->out.p, on, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->st.ms_h2d = ev_ms(ctx->ev[EV_START], ctx->ev[EV_H2D]);
     ctx->st.ms_d2h = ev_ms(ctx->ev[EV_CODE_END], ctx->ev[EV_D2H]);
     ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_D2H]);
-    *out = ctx->h_out.as<uint8_t>();
+    *out = ctx->h_out_d.as<uint8_t>();
     *out_n = on;
     return 0;
 }

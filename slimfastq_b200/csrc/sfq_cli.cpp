@@ -51,6 +51,8 @@ Usage: \n\
 -c bytes         : chunk size (default 1048576); every chunk is coded as a standalone file \n\
 -g device        : CUDA device index (default 0) \n\
 -R               : write the reference's own file format (one chunk; readable by the original slimfastq) \n\
+-m MiB           : stream: code the input in segments of about this many MiB of FASTQ (default 2048; 0 = all at once), \n\
+                   so pipes of any length run in bounded host memory \n\
 \n\
 DWIM (Do what I mean) - Intuitive use of 'slimfastq-b200 A B' : \n\
 If A appears to be a fastq file, and:\n\
@@ -133,13 +135,67 @@ static void statistics_dump(const uint8_t *p, size_t n) {      // config.cpp:76-
     exit(0);
 }
 
+
+// ---- bounded-memory streaming (usrs.cpp:96-122 pages its input through a 1 MiB buffer; here the unit is
+// a segment of many chunks: each one is a container of its own, their blobs are appended to the output as
+// they are produced and one index is written at the end).
+// Smallest record start >= pos.  A line starting with '@' is a header iff the line two below starts with
+// '+': a quality line that begins with '@' is followed by a header and then bases, never by a '+' line there.
+static size_t record_start_at_or_after(const uint8_t *t, size_t n, size_t pos) {
+    if (pos == 0) return 0;
+    const uint8_t *p = (const uint8_t *)memchr(t + pos - 1, '\n', n - (pos - 1));
+    while (p && (size_t)(p - t) + 1 < n) {
+        const size_t s = (size_t)(p - t) + 1;
+        if (t[s] == '@') {
+            const uint8_t *l2 = (const uint8_t *)memchr(t + s, '\n', n - s);
+            const uint8_t *l3 = l2 && (size_t)(l2 - t) + 1 < n ? (const uint8_t *)memchr(l2 + 1, '\n', n - (size_t)(l2 + 1 - t)) : nullptr;
+            if (l3 && (size_t)(l3 - t) + 1 < n && l3[1] == '+') return s;
+        }
+        p = (const uint8_t *)memchr(t + s, '\n', n - s);
+    }
+    return n;
+}
+// Last record start in the buffer (everything before it is whole records); 0 if there is none.
+static size_t last_record_start(const uint8_t *t, size_t n) {
+    for (size_t w = 1u << 20;; w *= 4) {
+        const size_t from = n > w ? n - w : 0;
+        size_t cut = 0, s = from ? record_start_at_or_after(t, n, from) : 0;
+        if (from == 0) s = record_start_at_or_after(t, n, 1);
+        while (s < n) { cut = s; s = record_start_at_or_after(t, n, s + 1); }
+        if (cut || from == 0) return cut;
+    }
+}
+
+struct StreamOut {                       // the container being assembled on disk
+    FILE *f = nullptr;
+    std::vector<uint64_t> index;
+    uint64_t pos = sizeof(SfqFileHeader), orig = 0, out_size = 0, chunk_bytes = 0;
+    uint32_t level = 0;
+    void begin(FILE *file) { f = file; SfqFileHeader z; memset(&z, 0, sizeof z); if (fwrite(&z, 1, sizeof z, f) != sizeof z) croak("Error writing output: %s", strerror(errno)); }
+    void add(const uint8_t *part, size_t n) {      // a whole container: append its blobs
+        SfqFileHeader h;
+        memcpy(&h, part, sizeof h);
+        if (h.index_off > n || n - h.index_off < h.nchunks * 8) croak("internal error: bad part container");
+        for (uint64_t c = 0; c < h.nchunks; c++) { uint64_t o; memcpy(&o, part + h.index_off + 8 * c, 8); index.push_back(o - sizeof h + pos); }
+        const size_t body = (size_t)(h.index_off - sizeof h);
+        if (fwrite(part + sizeof h, 1, body, f) != body) croak("Error writing output: %s", strerror(errno));
+        pos += body; orig += h.orig_size; out_size += h.out_size; level = h.level; chunk_bytes = h.chunk_bytes;
+    }
+    void end() {
+        if (index.size() && fwrite(index.data(), 8, index.size(), f) != index.size()) croak("Error writing output: %s", strerror(errno));
+        SfqFileHeader h;
+        sfq_file_header_init(&h, (int)level, orig, index.size(), chunk_bytes, pos, out_size);
+        if (fseek(f, 0L, SEEK_SET) || fwrite(&h, 1, sizeof h, f) != sizeof h || fclose(f)) croak("Error writing output: %s", strerror(errno));
+    }
+};
+
 int main(int argc, char **argv) {
     std::string usr, fil;
     bool overwrite = false, statistics = false, ref_format = false;
     int level = 3, device = 0;
-    unsigned long long chunk = 1ull << 20;
+    unsigned long long chunk = 1ull << 20, seg_mib = 2048;
     if (argc == 1) usage();
-    const char *short_opt = "qPsvhdOR1234u:f:l:c:g:";
+    const char *short_opt = "qPsvhdOR1234u:f:l:c:g:m:";
     for (int opt = getopt(argc, argv, short_opt); opt != -1; opt = getopt(argc, argv, short_opt))
         switch (opt) {
         case 'u': usr = optarg; break;
@@ -148,6 +204,7 @@ int main(int argc, char **argv) {
         case '1': case '2': case '3': case '4': level = opt - '0'; break;
         case 'c': chunk = strtoull(optarg, 0, 0); break;
         case 'g': device = atoi(optarg); break;
+        case 'm': seg_mib = strtoull(optarg, 0, 0); break;
         case 'd': g_encode = false; break;
         case 'O': overwrite = true; break;
         case 'R': ref_format = true; break;
@@ -200,21 +257,67 @@ int main(int argc, char **argv) {
             if (!in) { fprintf(stderr, "Can't read file '%s': %s\n", usr.c_str(), strerror(errno)); exit(1); }
             fseek(in, 0L, SEEK_END); hint = (size_t)ftell(in); fseek(in, 0L, SEEK_SET);
         }
-        size_t n = 0;
-        uint8_t *buf = slurp(in, hint, &n);
-        const uint8_t *res = nullptr;
-        size_t rn = 0;
-        if (ref_format) chunk = ~0ull >> 1;        // the reference's file holds one set of streams: one chunk
-        if (sfq_compress(ctx, buf, n, level, chunk, &res, &rn)) { unlink(fil.c_str()); croak("%s", sfq_last_error(ctx)); }
-        std::vector<uint8_t> paged;
-        if (ref_format) {
-            paged.resize(sfq_export_reference_bound(res, rn));
-            size_t pn = 0;
-            if (sfq_export_reference(res, rn, usr.c_str(), paged.data(), paged.size(), &pn)) { unlink(fil.c_str()); croak("cannot write the reference file format for this input"); }
-            res = paged.data(); rn = pn;
+        const size_t seg = (size_t)seg_mib << 20;
+        if (ref_format || seg == 0 || (hint && hint <= seg)) {             // all at once
+            size_t n = 0;
+            uint8_t *buf = slurp(in, hint, &n);
+            const uint8_t *res = nullptr;
+            size_t rn = 0;
+            if (ref_format) chunk = ~0ull >> 1;        // the reference's file holds one set of streams: one chunk
+            if (sfq_compress(ctx, buf, n, level, chunk, &res, &rn)) { unlink(fil.c_str()); croak("%s", sfq_last_error(ctx)); }
+            std::vector<uint8_t> paged;
+            if (ref_format) {
+                paged.resize(sfq_export_reference_bound(res, rn));
+                size_t pn = 0;
+                if (sfq_export_reference(res, rn, usr.c_str(), paged.data(), paged.size(), &pn)) { unlink(fil.c_str()); croak("cannot write the reference file format for this input"); }
+                res = paged.data(); rn = pn;
+            }
+            if (fwrite(res, 1, rn, out) != rn || fclose(out)) croak("Error writing output: %s", strerror(errno));
+            sfq_host_free(buf);
+        } else {                                                           // stream: bounded host memory
+            size_t cap = seg + (64u << 20), have = 0;
+            uint8_t *buf = (uint8_t *)sfq_host_alloc(cap);
+            if (!buf) croak("cannot allocate %zu bytes of pinned memory", cap);
+            StreamOut so;
+            so.begin(out);
+            bool eof = false;
+            unsigned long long records_done = 0;
+            while (!eof || have) {
+                while (!eof && have < seg) {
+                    const size_t got = fread(buf + have, 1, seg - have, in);
+                    if (got == 0) { if (ferror(in)) croak("read error: %s", strerror(errno)); eof = true; }
+                    have += got;
+                }
+                size_t cut = have;
+                if (!eof) {
+                    cut = last_record_start(buf, have);
+                    if (cut == 0) {                                        // a record longer than the segment: grow and read on
+                        if (have == cap) {
+                            uint8_t *nb = (uint8_t *)sfq_host_alloc(cap * 2);
+                            if (!nb) croak("cannot allocate %zu bytes of pinned memory", cap * 2);
+                            memcpy(nb, buf, have); sfq_host_free(buf); buf = nb; cap *= 2;
+                        }
+                        const size_t got = fread(buf + have, 1, cap - have, in);
+                        if (got == 0) eof = true;
+                        have += got;
+                        continue;
+                    }
+                }
+                if (cut == 0) break;
+                const uint8_t *res = nullptr;
+                size_t rn = 0;
+                if (sfq_compress(ctx, buf, cut, level, chunk, &res, &rn)) { unlink(fil.c_str()); croak("%s (in the segment after record %llu)", sfq_last_error(ctx), records_done); }
+                sfq_stats st;
+                sfq_get_stats(ctx, &st);
+                records_done += st.nrecords;
+                so.add(res, rn);
+                memmove(buf, buf + cut, have - cut);
+                have -= cut;
+            }
+            if (so.index.empty()) { unlink(fil.c_str()); croak("no records were found"); }
+            so.end();
+            sfq_host_free(buf);
         }
-        if (fwrite(res, 1, rn, out) != rn || fclose(out)) croak("Error writing output: %s", strerror(errno));
-        sfq_host_free(buf);
     } else {
         FILE *in = fopen(fil.c_str(), "rb");
         if (!in) { fprintf(stderr, "Can't read file '%s': %s\n", fil.c_str(), strerror(errno)); exit(1); }
@@ -238,10 +341,44 @@ int main(int argc, char **argv) {
         if (statistics) statistics_dump(src, n);
         FILE *out = usr.length() ? fopen(usr.c_str(), wr_flags) : stdout;
         if (!out) { fprintf(stderr, "Can't write file '%s': %s\n", usr.c_str(), strerror(errno)); exit(1); }
-        const uint8_t *res = nullptr;
-        size_t rn = 0;
-        if (sfq_decompress(ctx, src, n, &res, &rn)) { if (usr.length()) unlink(usr.c_str()); croak("%s", sfq_last_error(ctx)); }
-        if (fwrite(res, 1, rn, out) != rn || (out != stdout ? fclose(out) : fflush(out))) croak("USR: Error writing output");
+        SfqFileHeader fh;
+        memcpy(&fh, src, sizeof fh);
+        const size_t seg = (size_t)seg_mib << 20;
+        const bool index_ok = fh.nchunks && fh.index_off <= n && n - fh.index_off >= fh.nchunks * 8;
+        if (seg == 0 || fh.out_size <= seg || !index_ok) {                  // all at once
+            const uint8_t *res = nullptr;
+            size_t rn = 0;
+            if (sfq_decompress(ctx, src, n, &res, &rn)) { if (usr.length()) unlink(usr.c_str()); croak("%s", sfq_last_error(ctx)); }
+            if (fwrite(res, 1, rn, out) != rn) croak("USR: Error writing output");
+        } else {                                                            // groups of chunks: bounded output memory
+            std::vector<uint64_t> idx(fh.nchunks + 1);
+            memcpy(idx.data(), src + fh.index_off, fh.nchunks * 8);
+            idx[fh.nchunks] = fh.index_off;
+            std::vector<uint8_t> part;
+            for (uint64_t c0 = 0; c0 < fh.nchunks;) {
+                uint64_t c1 = c0, bytes = 0;
+                while (c1 < fh.nchunks) {
+                    if (idx[c1] > n || n - idx[c1] < sizeof(SfqBlobHeader) || idx[c1 + 1] < idx[c1] || idx[c1 + 1] > fh.index_off) croak("corrupt container index");
+                    SfqBlobHeader b;
+                    memcpy(&b, src + idx[c1], sizeof b);
+                    if (c1 > c0 && bytes + b.out_len > seg) break;
+                    bytes += b.out_len; c1++;
+                }
+                const uint64_t body = idx[c1] - idx[c0];
+                part.resize(sizeof fh + body + (c1 - c0) * 8);
+                SfqFileHeader ph;
+                sfq_file_header_init(&ph, (int)fh.level, bytes, c1 - c0, fh.chunk_bytes, sizeof fh + body, bytes);
+                memcpy(part.data(), &ph, sizeof ph);
+                memcpy(part.data() + sizeof ph, src + idx[c0], body);
+                for (uint64_t c = c0; c < c1; c++) { const uint64_t o = idx[c] - idx[c0] + sizeof ph; memcpy(part.data() + sizeof ph + body + 8 * (c - c0), &o, 8); }
+                const uint8_t *res = nullptr;
+                size_t rn = 0;
+                if (sfq_decompress(ctx, part.data(), part.size(), &res, &rn)) { if (usr.length()) unlink(usr.c_str()); croak("%s", sfq_last_error(ctx)); }
+                if (fwrite(res, 1, rn, out) != rn) croak("USR: Error writing output");
+                c0 = c1;
+            }
+        }
+        if (out != stdout ? fclose(out) : fflush(out)) croak("USR: Error writing output");
         sfq_host_free(buf);
     }
     if (ctx) sfq_destroy(ctx);

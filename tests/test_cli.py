@@ -67,3 +67,23 @@ def test_cli_mixes_with_the_original_slimfastq(tmp_path):
     assert r.returncode == 0 and r.stdout == data
     r = run("-s", str(theirs))
     assert r.returncode == 0 and b"num_records      = 2500" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_streams_in_bounded_segments(tmp_path):
+    """-m: the input is coded in segments (each cut on a record boundary, carry kept), blobs appended as they
+    come, one index at the end; decoding walks groups of chunks.  Same records, same order, same bytes back."""
+    from slimfastq_b200 import container as K
+
+    data = synth.illumina(9000) + synth.ont(30) + synth.illumina(2000, seed=77)       # ~5 MB, mixed record sizes
+    fq, sfq, back = tmp_path / "a.fq", tmp_path / "a.sfq", tmp_path / "b.fq"
+    fq.write_bytes(data)
+    r = run("-m", "1", "-c", "262144", "-f", str(sfq), input=data)                  # stdin, 1 MiB segments
+    assert r.returncode == 0, r.stderr
+    ct = K.parse(sfq.read_bytes())
+    assert ct.orig_size == len(data) and sum(c.text_len for c in ct.chunks) == len(data) and len(ct.chunks) > 8
+    r = run("-m", "1", "-d", "-f", str(sfq))                                         # grouped decode to stdout
+    assert r.returncode == 0 and r.stdout == data
+    assert run("-m", "0", str(sfq), str(back)).returncode == 0 and back.read_bytes() == data   # ... equals one-shot decode
+    r = run("-m", "1", "-f", str(tmp_path / "t.sfq"), input=data[:-7])              # truncated last record: croak, no file
+    assert r.returncode == 1 and b"truncated" in r.stderr and not (tmp_path / "t.sfq").exists()
