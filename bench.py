@@ -261,14 +261,14 @@ def main():
     if not args.no_e2e:
         try:
             # pinned host memory of the leg: input + the library's container and output buffers, on every rank of the node
-            need = world * (2 * n + 2 * csz + (1 << 30))
+            need = world * (2 * n + csz + (1 << 29))
             try:
                 import psutil  # noqa: PLC0415
 
                 avail = psutil.virtual_memory().available
             except ImportError:
                 avail = None
-            if avail is not None and need > 0.8 * avail:
+            if avail is not None and need > 0.85 * avail:
                 raise MemoryError("e2e leg needs %.0f GB of pinned host memory on this node, %.0f GB available" % (need / 1e9, avail / 1e9))
             h_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
             h_text.copy_(d_text)
@@ -298,15 +298,16 @@ def main():
             ok = float(tok.item())
         if ok:
             barrier()
-            e_ms = 0.0
+            e_ms = e_copy = 0.0
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 cn, on, s1, s2, b = step_e2e()
                 e_ms += s1["ms_total"] + s2["ms_total"]
+                e_copy += s1["ms_h2d"] + s1["ms_d2h"] + s2["ms_h2d"] + s2["ms_d2h"]
                 launches += s1["kernel_launches"] + s2["kernel_launches"]
             barrier()
             e_wall = time.perf_counter() - t0
-            e2e = {"ms": e_ms, "wall_s": e_wall, "h2d": n + cn, "d2h": cn + n}
+            e2e = {"ms": e_ms, "wall_s": e_wall, "h2d": n + cn, "d2h": cn + n, "copy_ms": e_copy}
             del h_text
         elif not e2e_err:
             e2e_err = "another rank could not set up its host buffers"
@@ -403,7 +404,9 @@ def main():
             ev = 2 * tot_bytes * K_ / e2e_wall_max / 1e9
             line["e2e"] = {"value": round(ev, 4), "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                            "timing": "wall clock around K steps of sfq_compress+sfq_decompress on pinned host buffers, barrier+sync both sides",
-                           "device_event_ms_per_step": round(e2e["ms"] / K_, 3)}
+                           "device_event_ms_per_step": round(e2e["ms"] / K_, 3),
+                           "copy_ms_per_step": round(e2e["copy_ms"] / K_, 3),
+                           "note": "copies and coding run back to back (no overlap yet): e2e = value's kernels + PCIe time"}
         elif e2e_err:
             line["e2e"] = {"value": None, "unit": UNIT, "error": e2e_err}
         if world == 1 and not args.no_cpu:

@@ -81,6 +81,7 @@ struct sfq_ctx {
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
            e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff;
+    int gm_variant = 0;                     // SFQ_GM_VARIANT: register budget / batch of k_gen_model (A/B runs)
     int gen_ahead2 = -1;                    // SFQ_GEN_AHEAD2=0/1: base decoder's two-ahead line prefetch (default on)
     bool qdec_octets = true;                // SFQ_QDEC=0: the first (sub-warp mask) quality decoder, for A/B runs
     bool serial_roles = false;              // SFQ_SERIAL_ROLES=1: gen, qlt, rec kernels of a wave one after another (diagnosis)
@@ -353,7 +354,13 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 CK(cudaStreamWaitEvent(side1, ctx->fork_ev, 0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
                 if (two_phase) {
-                    k_gen_model<<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); LAUNCHED();
+                    switch (ctx->gm_variant) {
+                    case 1: k_gen_model<4, 8><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
+                    case 2: k_gen_model<8, 8><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
+                    case 3: k_gen_model<8, 1><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
+                    default: k_gen_model<8, 6><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
+                    }
+                    LAUNCHED();
                     k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes); LAUNCHED();
                 } else {
                     k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
@@ -663,6 +670,7 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_RC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->rc_lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_SERIAL")) ctx->serial_encoder = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_GM_VARIANT")) ctx->gm_variant = atoi(e);
     if (const char *e = getenv("SFQ_GEN_AHEAD2")) ctx->gen_ahead2 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QDEC")) ctx->qdec_octets = atoi(e) != 0;
     if (const char *e = getenv("SFQ_SERIAL_ROLES")) ctx->serial_roles = atoi(e) != 0;

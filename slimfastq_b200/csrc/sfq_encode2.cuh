@@ -185,8 +185,10 @@ SFQ_HDN void sfq_rc_qlt_chunk(const uint64_t *steps, const uint64_t *esteps, uin
 __device__ __forceinline__ uint32_t sfq_ldcg32(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ uint64_t sfq_ldcg64(const uint64_t *p) { return __ldcg(reinterpret_cast<const unsigned long long *>(p)); }
 
-#define SFQ_GM_BATCH 8                 // windows whose text and table slots are requested together
-__global__ void __launch_bounds__(128)
+// SFQ_GM_BATCH = windows whose text and table slots are requested together; MINB = CTAs per SM the register
+// allocation must allow (8 -> 64 registers: every chunk of a 4 741-chunk wave resident at once)
+template <int SFQ_GM_BATCH, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_gen_model(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas,
             SfqArena *arenas, uint8_t *arena_buf, SfqWorkspace ws, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c,
             int level, uint32_t nchunks) {

@@ -78,3 +78,34 @@ def test_errors_are_croaks_not_crashes(codec):
         codec.decompress(b"whoami=slimfastq\nversion=6\n" + b"\0" * 200)
     good = codec.compress(b"@r1\nACGT\n+\nIIII\n", 3)
     assert codec.decompress(good) == b"@r1\nACGT\n+\nIIII\n"
+
+
+def test_decoder_survives_wrong_table_hints(codec):
+    """The blob header's context counts only size the decoder's hash tables: with hints that are far too
+    small the tables fill up, the library reruns the wave with larger ones (SFQ_E_TABLE), same output."""
+    import struct
+
+    from slimfastq_b200 import container as K
+
+    data = synth.illumina(7000)
+    blob = bytearray(codec.compress(data, 3, 1 << 20))
+    _, _, _, _, _, nchunks, _, index_off, _ = K.FILE_HDR.unpack_from(blob, 0)
+    hint_off = K.BLOB_HDR.size - 4 * 10 - 8                     # q_used, g_used sit right before ssize[10]
+    for off in struct.unpack_from(f"<{nchunks}Q", blob, index_off):
+        q_used, g_used = struct.unpack_from("<II", blob, off + hint_off)
+        assert q_used > 1000 and g_used > 100000
+        struct.pack_into("<II", blob, off + hint_off, 40, 3000)
+    assert codec.decompress(bytes(blob)) == data
+    assert codec.stats()["retries"] >= 1
+    for off in struct.unpack_from(f"<{nchunks}Q", blob, index_off):
+        struct.pack_into("<II", blob, off + hint_off, 0, 0)     # hints absent (e.g. an older writer)
+    assert codec.decompress(bytes(blob)) == data
+
+
+def test_alternating_sizes_reuse_the_scratch_arena(codec, oracle):
+    """compress / decompress carve one arena differently; sizes going up and down must not leak state."""
+    big, small = synth.illumina(9000), synth.illumina(700, seed=5)
+    for data in (big, small, big, small):
+        blob = codec.compress(data, 3, 1 << 19)
+        check_container_against_oracle(oracle, data, blob, 3)
+        assert codec.decompress(blob) == data
