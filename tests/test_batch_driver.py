@@ -1,0 +1,52 @@
+"""tools/slimfastq-b200.multi keeps the command line of the reference's tools/slimfastq.multi."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from slimfastq_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MULTI = os.path.join(ROOT, "tools", "slimfastq-b200.multi")
+
+
+def run(*args):
+    return subprocess.run([sys.executable, MULTI, *args], capture_output=True, text=True)
+
+
+def test_dry_run_names_targets_like_the_reference(tmp_path):
+    src = tmp_path / "FQ"
+    (src / "sub").mkdir(parents=True)
+    for name in ("a.fastq", "b.fq", "c.txt", "sub/d.fq"):
+        (src / name).write_text("@r\nA\n+\nI\n")
+    tgt = tmp_path / "SFQ"
+    r = run("-n", "-e", "slimfastq-b200", "-g", "0,1", "-t", str(tgt), str(src))
+    assert r.returncode == 0 and tgt.is_dir()
+    cmds = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("slimfastq-b200")]
+    assert sorted(c[c.index("-f") + 1] for c in cmds) == [str(tgt / "a.sfq"), str(tgt / "b.sfq")]     # suffix list, no recursion
+    assert all("-O" in c and "-u" in c for c in cmds)
+    assert {c[c.index("-g") + 1] for c in cmds} <= {"0", "1"}
+    r = run("-n", "-e", "x", "-r", "-g", "0", str(src))
+    assert sum("d.sfq" in ln for ln in r.stdout.splitlines()) == 1                                      # -r descends
+    good = tmp_path / "z.sfq"
+    good.write_bytes(b"whoami=slimfastq\n" + b"\0" * 64)
+    (tmp_path / "bad.sfq").write_bytes(b"not one")
+    r = run("-n", "-d", "-e", "x", "-g", "3", "-f", ".fq2,.fq", str(tmp_path))
+    lines = r.stdout.splitlines()
+    assert any(ln.startswith("x -g 3 -d -u " + str(tmp_path / "z.fq2")) for ln in lines)                # first suffix of the list
+    assert any("bad.sfq doesn't seem to be a valid slimfastq file" in ln for ln in lines)
+    assert run("-n", str(tmp_path / "nothing-here")).returncode != 0
+
+
+@pytest.mark.gpu
+def test_batch_round_trip(tmp_path):
+    src, mid, back = tmp_path / "FQ", tmp_path / "SFQ", tmp_path / "BACK"
+    src.mkdir()
+    data = {f"s{i}.fq": synth.illumina(1500, seed=100 + i) for i in range(3)}
+    for k, v in data.items():
+        (src / k).write_bytes(v)
+    assert run("-g", "0", "-c", "2", "-t", str(mid), str(src)).returncode == 0
+    assert run("-d", "-g", "0", "-t", str(back), "-f", ".fq", str(mid)).returncode == 0
+    for k, v in data.items():
+        assert (back / k).read_bytes() == v
