@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sfq_b200.h"
@@ -81,6 +82,10 @@ struct sfq_ctx {
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
            e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff;
+    bool trace = false;                     // SFQ_TRACE=1: per-kernel event timings of the coder waves on stderr
+    std::vector<std::pair<const char *, std::pair<cudaEvent_t, cudaEvent_t>>> tr;
+    int gdec32 = 0;                         // SFQ_GDEC=1: warp-converged base decoder (A/B; slower)
+    uint32_t qlpc = 0;                      // SFQ_QLPC=4|8: lanes per chunk of the quality decoder (0 = by wave size)
     int gm_variant = 0;                     // SFQ_GM_VARIANT: register budget / batch of k_gen_model (A/B runs)
     int gen_ahead2 = -1;                    // SFQ_GEN_AHEAD2=0/1: base decoder's two-ahead line prefetch (default on)
     bool qdec_octets = true;                // SFQ_QDEC=0: the first (sub-warp mask) quality decoder, for A/B runs
@@ -177,12 +182,35 @@ uint32_t pick_resident(sfq_ctx *ctx, uint64_t nchunks, uint64_t per_chunk, uint6
 // Chunk-streams per warp of the thread-per-chunk coders: few when the wave is small (the chains are then
 // latency-bound and a lane's slow path stalls fewer neighbours), more when it is large (issue slots are
 // then the scarce resource and a fuller warp spends fewer of them per symbol).
-uint32_t pick_lanes(const sfq_ctx *ctx, uint32_t nc) { return ctx->lanes ? ctx->lanes : nc >= 2048u ? 8u : 4u; }
+uint32_t pick_lanes(const sfq_ctx *ctx, uint32_t nc) { return ctx->lanes ? ctx->lanes : nc >= 4096u ? 16u : nc >= 2048u ? 8u : 4u; }
 
 // kernels index the per-chunk pools by the chunk's position in the wave
 SfqWorkspace ws_at(const SfqWorkspace &ws, uint32_t) { return ws; }
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// SFQ_TRACE: bracket a launch with events on its stream; trace_dump() prints and frees them after the sync.
+struct TraceScope {
+    sfq_ctx *ctx; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; const char *name;
+    TraceScope(sfq_ctx *c, const char *n, cudaStream_t s) : ctx(c), st(s), name(n) {
+        if (ctx->trace) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~TraceScope() { if (ctx->trace) { cudaEventRecord(b, st); ctx->tr.push_back({name, {a, b}}); } }
+};
+void trace_dump(sfq_ctx *ctx, const char *what) {
+    if (!ctx->trace) return;
+    cudaEvent_t t0 = ctx->tr.empty() ? nullptr : ctx->tr[0].second.first;
+    for (auto &e : ctx->tr) {
+        float off = 0, ms = 0;
+        cudaEventElapsedTime(&off, t0, e.second.first); cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+        fprintf(stderr, "[sfq trace] %s %-22s start %9.3f ms  dur %9.3f ms\n", what, e.first, off, ms);
+        if (e.second.first != t0) cudaEventDestroy(e.second.first);
+        cudaEventDestroy(e.second.second);
+    }
+    if (t0) cudaEventDestroy(t0);
+    ctx->tr.clear();
+}
+#define TRACED(name, stream, launch) { TraceScope ts_(ctx, name, stream); launch; }
 
 int ensure_wave_events(sfq_ctx *ctx, size_t waves) {
     while (ctx->wave_ev.size() < waves * WEV) {
@@ -354,14 +382,15 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 CK(cudaStreamWaitEvent(side1, ctx->fork_ev, 0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
                 if (two_phase) {
+                    { TraceScope ts_(ctx, "k_gen_model", s);
                     switch (ctx->gm_variant) {
                     case 1: k_gen_model<4, 8><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
                     case 2: k_gen_model<8, 8><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
                     case 3: k_gen_model<8, 1><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
                     default: k_gen_model<8, 6><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
-                    }
+                    } }
                     LAUNCHED();
-                    k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes); LAUNCHED();
+                    TRACED("k_rc_encode<0>", s, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else {
                     k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
@@ -371,18 +400,18 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     cudaStream_t q = side0;
                     uint32_t wave_max_nrec = 1;
                     for (uint32_t c = c0; c < c0 + nc; c++) wave_max_nrec = std::max(wave_max_nrec, metas[c].nrec);
-                    k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc); LAUNCHED();
-                    k_qlt_scan<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
-                    k_qlt_scatter<<<nwarp_blocks, 128, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
-                    k_qlt_model<<<ctx->sm_count * 4, SFQ_QM_THREADS, 0, q>>>(d_metas + c0, ws_at(ws, c0), e2, d_e2c, c0); LAUNCHED();
+                    TRACED("k_qlt_keys", q, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
+                    TRACED("k_qlt_scan", q, (k_qlt_scan<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    TRACED("k_qlt_scatter", q, (k_qlt_scatter<<<nwarp_blocks, 128, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    TRACED("k_qlt_model", q, (k_qlt_model<<<ctx->sm_count * 4, SFQ_QM_THREADS, 0, q>>>(d_metas + c0, ws_at(ws, c0), e2, d_e2c, c0))); LAUNCHED();
                     k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
-                    k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes); LAUNCHED();
+                    TRACED("k_rc_encode<1>", q, (k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else {
                     k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, side0>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
-                k_encode<2><<<nb, 32, 0, side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
+                TRACED("k_encode<2>", side1, (k_encode<2><<<nb, 32, 0, side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes))); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
                 CK(cudaEventRecord(ctx->join_ev[1], side1));
@@ -401,6 +430,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         CK(cudaMemcpyAsync(h_small, d_scal, 24, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
+        trace_dump(ctx, "compress");
         bool again = false;
         for (uint32_t c = 0; c < nchunks; c++) {
             if (metas[c].status == SFQ_E_CAP || metas[c].status == SFQ_E_TABLE) again = true;
@@ -562,11 +592,22 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 // the quality decoder is the longest chain of the three: it goes first (and on the high-priority
                 // stream) so that its warps are all resident from the start; gen and rec fill in around it
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
-                if (ctx->qdec_octets) { k_qlt_decode4<<<(nc + 4 * SFQ_QD_WARPS - 1) / (4 * SFQ_QD_WARPS), 32 * SFQ_QD_WARPS, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc); LAUNCHED(); }
+                if (ctx->qdec_octets) {
+                    // lanes per chunk: 8 while the chains are latency-bound, 4 (twice the chunks per warp, a longer
+                    // link) once a wave is large enough for issue slots to be what its warps compete for
+                    const uint32_t lpc = ctx->qlpc ? ctx->qlpc : nc >= 4096u ? 4u : 8u;
+                    if (lpc == 4) k_qlt_decode<4><<<(nc + 8 * SFQ_QD_WARPS - 1) / (8 * SFQ_QD_WARPS), 32 * SFQ_QD_WARPS, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    else k_qlt_decode<8><<<(nc + 4 * SFQ_QD_WARPS - 1) / (4 * SFQ_QD_WARPS), 32 * SFQ_QD_WARPS, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    LAUNCHED();
+                }
                 else { k_decode<1><<<(nc + 2 * ctx->qgpw - 1) / (2 * ctx->qgpw), 64, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->qgpw); LAUNCHED(); }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
-                k_decode<0><<<nb, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
+                // base decoder: thread per chunk, `lanes` chunks per warp.  (SFQ_GDEC=1 runs the warp-converged form,
+                // 32 chunks per warp: correct, but its link waits for the slowest of 32 table reads - 45 % slower, kept for A/B.)
+                if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
+                else k_decode<0><<<nb, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
+                LAUNCHED();
                 k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
@@ -670,6 +711,9 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_RC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->rc_lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_SERIAL")) ctx->serial_encoder = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_TRACE")) ctx->trace = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_GDEC")) ctx->gdec32 = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_QLPC")) { int v = atoi(e); if (v == 4 || v == 8) ctx->qlpc = (uint32_t)v; }
     if (const char *e = getenv("SFQ_GM_VARIANT")) ctx->gm_variant = atoi(e);
     if (const char *e = getenv("SFQ_GEN_AHEAD2")) ctx->gen_ahead2 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QDEC")) ctx->qdec_octets = atoi(e) != 0;

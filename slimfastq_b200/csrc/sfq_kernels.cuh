@@ -239,6 +239,7 @@ struct SfqRecTables {
 };
 
 #include "sfq_qlt_dec.cuh"
+#include "sfq_gen_dec.cuh"
 
 __global__ void __launch_bounds__(32)
 k_decode_usr(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,

@@ -1,4 +1,4 @@
-// Quality stream decoder, warp-converged form: four chunks per warp, eight lanes ("an octet") per chunk.
+// Quality stream decoder, warp-converged form: LPC lanes per chunk (eight - four chunks per warp - or four).
 //
 // QltLoad::load_1/2/3 (qlts.cpp:163-234) is a strict serial chain: the context of symbol n+1 depends on
 // symbol n, so one chunk-stream cannot be split.  What can be cut is the time of one link of the chain.
@@ -77,30 +77,96 @@ struct SfqQdSink {
     __device__ __forceinline__ void start(uint8_t *first) { p = first; acc = 0; }
 };
 
-struct SfqQdModel { uint32_t f0, f1, f2, f3, f4, f5, f6, f7, sx, sy, hdr, excl; };
-__device__ __forceinline__ void sfq_qd_load(SfqQdModel &m, const uint32_t *e) {
-    const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(e)), b = __ldcg(reinterpret_cast<const uint4 *>(e + 4));
-    m.f0 = a.x & 0xffffu; m.f1 = a.x >> 16; m.f2 = a.y & 0xffffu; m.f3 = a.y >> 16;
-    m.f4 = a.z & 0xffffu; m.f5 = a.z >> 16; m.f6 = a.w & 0xffffu; m.f7 = a.w >> 16;
-    m.sx = b.x; m.sy = b.y; m.hdr = b.z; m.excl = b.w;
-}
-__device__ __forceinline__ void sfq_qd_store_freqs(const SfqQdModel &m, uint32_t *e) {
-    *reinterpret_cast<uint4 *>(e) = make_uint4(m.f0 | (m.f1 << 16), m.f2 | (m.f3 << 16), m.f4 | (m.f5 << 16), m.f6 | (m.f7 << 16));
-}
-__device__ __forceinline__ void sfq_qd_store_tail(const SfqQdModel &m, uint32_t *e) {
-    *reinterpret_cast<uint4 *>(e + 4) = make_uint4(m.sx, m.sy, m.hdr, m.excl);
-}
-__device__ __forceinline__ void sfq_qd_store_hdr(const SfqQdModel &m, uint32_t *e) {
-    *reinterpret_cast<uint2 *>(e + 6) = make_uint2(m.hdr, m.excl);
+// One context's model as a lane holds it.  LPC = lanes per chunk (8 or 4), SPL = 64 / LPC slots per lane.
+// In memory a lane owns WPL = 8 (LPC 8) or 16 (LPC 4) consecutive words of the 64-word entry:
+//   SPL/2 words of freq pairs | SPL/4 words of symbol bytes | hdr | excl | (padding)
+template <int LPC> struct SfqQdGeo {
+    static constexpr int SPL = 64 / LPC;                    // slots per lane
+    static constexpr int WPL = 64 / LPC;                    // words per lane (8 or 16)
+    static constexpr int FW = SPL / 2, SW = SPL / 4;        // words of frequencies / of symbol bytes
+    static constexpr int HW = FW + SW;                      // word index of hdr (excl follows)
+    static constexpr int NV = WPL / 4;                      // 16-byte vectors per lane
+    static constexpr int CPW = 32 / LPC;                    // chunks per warp
+};
+template <int LPC> struct SfqQdModelT {
+    typedef SfqQdGeo<LPC> G;
+    uint32_t f[G::SPL];
+    uint32_t sy[G::SW];
+    uint32_t hdr, excl;
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int k = 0; k < G::SPL; k++) f[k] = 0;
+#pragma unroll
+        for (int k = 0; k < G::SW; k++) sy[k] = 0;
+        hdr = 0; excl = 0;
+    }
+    // word j (a compile-time index after unrolling) of the lane's vectors: stays in registers
+    static __device__ __forceinline__ uint32_t word(const uint4 (&v)[G::NV], int j) {
+        const uint4 &q = v[j >> 2];
+        return (j & 3) == 0 ? q.x : (j & 3) == 1 ? q.y : (j & 3) == 2 ? q.z : q.w;
+    }
+    __device__ __forceinline__ void unpack(const uint4 (&v)[G::NV]) {
+#pragma unroll
+        for (int k = 0; k < G::FW; k++) { const uint32_t w = word(v, k); f[2 * k] = w & 0xffffu; f[2 * k + 1] = w >> 16; }
+#pragma unroll
+        for (int k = 0; k < G::SW; k++) sy[k] = word(v, G::FW + k);
+        hdr = word(v, G::HW); excl = word(v, G::HW + 1);
+    }
+    __device__ __forceinline__ void store_freqs(uint32_t *e) const {
+#pragma unroll
+        for (int q = 0; q < G::FW / 4; q++)
+            *reinterpret_cast<uint4 *>(e + 4 * q) = make_uint4(f[8 * q] | (f[8 * q + 1] << 16), f[8 * q + 2] | (f[8 * q + 3] << 16),
+                                                               f[8 * q + 4] | (f[8 * q + 5] << 16), f[8 * q + 6] | (f[8 * q + 7] << 16));
+    }
+    __device__ __forceinline__ void store_syms(uint32_t *e) const {
+        if (G::SW == 2) *reinterpret_cast<uint2 *>(e + G::FW) = make_uint2(sy[0], sy[1]);
+        else *reinterpret_cast<uint4 *>(e + G::FW) = make_uint4(sy[0], sy[G::SW > 1 ? 1 : 0], sy[G::SW > 2 ? 2 : 0], sy[G::SW > 3 ? 3 : 0]);
+    }
+    __device__ __forceinline__ void store_hdr(uint32_t *e) const { *reinterpret_cast<uint2 *>(e + G::HW) = make_uint2(hdr, excl); }
+    // Runtime-indexed access to the register arrays, written as mask arithmetic over every element: a chain of
+    // selects or conditional stores gets turned into an indexed access by the compiler, which would move the
+    // whole model to local memory.
+    __device__ __forceinline__ uint32_t sym_byte(uint32_t k) const {          // stored byte of slot k of this lane
+        uint32_t w = 0;
+#pragma unroll
+        for (int q = 0; q < G::SW; q++) w |= sy[q] & (0u - (uint32_t)((k >> 2) == (uint32_t)q));
+        return (w >> (8u * (k & 3u))) & 0xffu;
+    }
+    __device__ __forceinline__ void set_sym_byte(uint32_t k, uint32_t v) {
+        const uint32_t sh = 8u * (k & 3u);
+#pragma unroll
+        for (int q = 0; q < G::SW; q++) {
+            const uint32_t hit = 0u - (uint32_t)((k >> 2) == (uint32_t)q);
+            sy[q] = (sy[q] & ~((0xffu << sh) & hit)) | ((v << sh) & hit);
+        }
+    }
+    __device__ __forceinline__ uint32_t freq_at(uint32_t k) const {
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < G::SPL; j++) v |= f[j] & (0u - (uint32_t)(k == (uint32_t)j));
+        return v;
+    }
+    __device__ __forceinline__ void set_freq(uint32_t k, uint32_t v) {
+#pragma unroll
+        for (int j = 0; j < G::SPL; j++) { const uint32_t hit = 0u - (uint32_t)(k == (uint32_t)j); f[j] = (f[j] & ~hit) | (v & hit); }
+    }
+};
+template <int LPC>
+__device__ __forceinline__ void sfq_qd_fetch(uint4 (&v)[SfqQdGeo<LPC>::NV], const uint32_t *e) {
+#pragma unroll
+    for (int q = 0; q < SfqQdGeo<LPC>::NV; q++) v[q] = __ldcg(reinterpret_cast<const uint4 *>(e + 4 * q));
 }
 
 #define SFQ_QD_WARPS 2                  // warps per CTA
+template <int LPC>
 __global__ void __launch_bounds__(32 * SFQ_QD_WARPS)
-k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas, SfqWorkspace ws,
-              SfqRecTables t, uint8_t *quals, uint32_t nchunks) {
+k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas, SfqWorkspace ws,
+             SfqRecTables t, uint8_t *quals, uint32_t nchunks) {
+    typedef SfqQdGeo<LPC> G;
+    constexpr uint32_t SPL = G::SPL;
     const unsigned FULL = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u, l8 = lane & 7u, osh = lane & 24u;
-    const uint32_t c = (blockIdx.x * SFQ_QD_WARPS + (threadIdx.x >> 5)) * 4u + (lane >> 3);
+    const uint32_t lane = threadIdx.x & 31u, l8 = lane % LPC, osh = lane - l8;       // l8 = lane inside the chunk's group
+    const uint32_t c = (blockIdx.x * SFQ_QD_WARPS + (threadIdx.x >> 5)) * G::CPW + lane / LPC;
     bool live = c < nchunks;
     if (live) live = metas[c].status == SFQ_OK;
     const bool valid = live;
@@ -124,7 +190,7 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
         rc.start(in + d.soff[SFQ_S_QLT], d.ssize[SFQ_S_QLT]);
         oplane = quals + d.qual_plane;
     }
-    tab += l8 * 8u;                                             // this lane's 32 bytes of every entry
+    tab += l8 * G::WPL;                                          // this lane's words of every entry
     // decoded qualities of a chunk are contiguous in the plane: eight bytes are gathered in two registers and
     // stored as one aligned word; `opos` counts from the aligned address at or below the chunk's first byte
     uint8_t *const obase = (uint8_t *)((uintptr_t)oplane & ~(uintptr_t)7);
@@ -151,19 +217,17 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
     uint32_t last = 0, p1 = 0, p2 = 0, dl = 5;
     uint32_t ctx = 0, h = 0, used = 0;
     bool full = false;
-    SfqQdModel m;
-    m.f0 = m.f1 = m.f2 = m.f3 = m.f4 = m.f5 = m.f6 = m.f7 = 0; m.sx = m.sy = m.hdr = m.excl = 0;
-    uint4 na = make_uint4(0, 0, 0, 0), nb = make_uint4(0, 0, 0, 0);      // the next model, as loaded
-    if (live) { na = __ldcg(reinterpret_cast<const uint4 *>(tab)); nb = __ldcg(reinterpret_cast<const uint4 *>(tab + 4)); }
-    bool fresh = live;                                                    // na/nb hold a model not yet unpacked
+    SfqQdModelT<LPC> m;
+    m.zero();
+    uint4 nv[G::NV];                                                      // the next model, as loaded
+#pragma unroll
+    for (int q = 0; q < G::NV; q++) nv[q] = make_uint4(0, 0, 0, 0);
+    if (live) sfq_qd_fetch<LPC>(nv, tab);
+    bool fresh = live;                                                    // nv holds a model not yet unpacked
     bool chk = live && !dense;
 
     while (__any_sync(FULL, live)) {
-        if (fresh) {
-            m.f0 = na.x & 0xffffu; m.f1 = na.x >> 16; m.f2 = na.y & 0xffffu; m.f3 = na.y >> 16;
-            m.f4 = na.z & 0xffffu; m.f5 = na.z >> 16; m.f6 = na.w & 0xffffu; m.f7 = na.w >> 16;
-            m.sx = nb.x; m.sy = nb.y; m.hdr = nb.z; m.excl = nb.w;
-        }
+        if (fresh) m.unpack(nv);
         // ---------------------------------------------------------------- the entry of `ctx` (hash probe)
         // An entry is in use once its total is non-zero (every update adds to it, and every lane holds the
         // total); lane 0 keeps the 16-bit key in its otherwise unused prefix word.
@@ -180,7 +244,7 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
                 } else if (chk && bad) {                                  // somebody else's entry: walk on
                     h = h + 1u == nent ? 0u : h + 1u;
                     if (++probes > nent) { full = true; live = false; chk = false; }
-                    else sfq_qd_load(m, tab + (size_t)h * 64u);
+                    else { sfq_qd_fetch<LPC>(nv, tab + (size_t)h * 64u); m.unpack(nv); }
                 } else chk = false;
                 if (!vb) break;
             }
@@ -190,30 +254,38 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
         // ---------------------------------------------------------------- Log64Ranger::get (log64_ranger.hpp:114-138)
         const uint32_t tot = m.hdr & 0x3fffffu, count = m.hdr >> 24;
         const uint32_t rr = rc.range / (tot + 64u);
-        const uint32_t e0 = (l8 ? m.excl : 0u) + 8u * l8;
-        const uint32_t c0 = e0 + m.f0 + 1u, c1 = c0 + m.f1 + 1u, c2 = c1 + m.f2 + 1u, c3 = c2 + m.f3 + 1u,
-                       c4 = c3 + m.f4 + 1u, c5 = c4 + m.f5 + 1u, c6 = c5 + m.f6 + 1u, c7 = c6 + m.f7 + 1u;
+        const uint32_t e0 = (l8 ? m.excl : 0u) + SPL * l8;
+        uint32_t cs[SPL];                                                  // cumulative (freq + 1) up to and including slot k
+        cs[0] = e0 + m.f[0] + 1u;
+#pragma unroll
+        for (int k = 1; k < (int)SPL; k++) cs[k] = cs[k - 1] + m.f[k] + 1u;
         // (a corrupt stream can leave code >= 2^32: every comparison below is then true, as with the reference's 64-bit quotient)
         const uint32_t code32 = (uint32_t)(rc.code >> 32) ? 0xffffffffu : (uint32_t)rc.code;
-        const unsigned sel = (__ballot_sync(FULL, code32 < c7 * rr) >> osh) & 0xffu;
-        const uint32_t hl = sel ? (uint32_t)(__ffs(sel) - 1) : 7u;          // no lane: corrupt stream, last slot
+        const unsigned sel = (__ballot_sync(FULL, code32 < cs[SPL - 1] * rr) >> osh) & ((1u << LPC) - 1u);
+        const uint32_t hl = sel ? (uint32_t)(__ffs(sel) - 1) : (uint32_t)(LPC - 1);      // no lane: corrupt stream, last slot
         uint32_t cb, hk, pack;
-        {   // binary search of code among this lane's thresholds c0..c6 (meaningful in lane hl)
-            const bool g3 = code32 >= c3 * rr;
-            const uint32_t cm = g3 ? c5 : c1;
-            uint32_t lo = g3 ? c3 : e0, hi = g3 ? c7 : c3;
-            const bool g2 = code32 >= cm * rr;
-            const uint32_t cq = g3 ? (g2 ? c6 : c4) : (g2 ? c2 : c0);
-            lo = g2 ? cm : lo; hi = g2 ? hi : cm;
-            const bool g1 = code32 >= cq * rr;
-            lo = g1 ? cq : lo; hi = g1 ? hi : cq;
-            hk = (g3 ? 4u : 0u) + (g2 ? 2u : 0u) + (g1 ? 1u : 0u);
-            const uint32_t sb = __byte_perm(m.sx, m.sy, hk) & 0xffu;
+        {   // binary search of code among this lane's thresholds cs[0..SPL-2] (meaningful in lane hl)
+            uint32_t idx = 0, lo = e0, hi = cs[SPL - 1];
+            // one level of the search: the candidate is cs[idx + STEP - 1] (all indices compile-time constants)
+#define SFQ_QD_LEVEL(STEP)                                                                                   \
+            {                                                                                                \
+                uint32_t cand = cs[(STEP) - 1];                                                              \
+                _Pragma("unroll")                                                                            \
+                for (int b_ = 2 * (STEP); b_ < (int)SPL; b_ += 2 * (STEP)) cand = idx == (uint32_t)b_ ? cs[b_ + (STEP) - 1] : cand; \
+                const bool g_ = code32 >= cand * rr;                                                         \
+                lo = g_ ? cand : lo; hi = g_ ? hi : cand; idx += g_ ? (uint32_t)(STEP) : 0u;                  \
+            }
+            if (SPL == 16) SFQ_QD_LEVEL(8)
+            SFQ_QD_LEVEL(4)
+            SFQ_QD_LEVEL(2)
+            SFQ_QD_LEVEL(1)
+#undef SFQ_QD_LEVEL
+            hk = idx;
             cb = lo;
-            pack = (hi - lo - 1u) | ((sb ^ (8u * l8 + hk)) << 16) | (hk << 24);
+            pack = (hi - lo - 1u) | ((m.sym_byte(hk) ^ (SPL * l8 + hk)) << 16) | (hk << 24);
         }
-        cb = __shfl_sync(FULL, cb, hl, 8);                                   // the chosen slot, from its lane
-        pack = __shfl_sync(FULL, pack, hl, 8);
+        cb = __shfl_sync(FULL, cb, hl, LPC);                                 // the chosen slot, from its lane
+        pack = __shfl_sync(FULL, pack, hl, LPC);
         const uint32_t f = pack & 0xffffu, ssym = (pack >> 16) & 0xffu;
         hk = pack >> 24;
         {   // Decode (coder.hpp:88-91)
@@ -241,8 +313,8 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
             const bool esc = act && b == 63u;
             if (esc && l8 == 0) { SfqPower ex; ex.m = pwq; b = ex.get(rc); }
             __syncwarp();
-#define SFQ_QD_BC32(x) { const uint32_t v_ = __shfl_sync(FULL, (uint32_t)(x), 0, 8); if (esc) x = v_; }
-#define SFQ_QD_BC64(x) { const uint32_t lo_ = __shfl_sync(FULL, (uint32_t)(x), 0, 8), hi_ = __shfl_sync(FULL, (uint32_t)((uint64_t)(x) >> 32), 0, 8); \
+#define SFQ_QD_BC32(x) { const uint32_t v_ = __shfl_sync(FULL, (uint32_t)(x), 0, LPC); if (esc) x = v_; }
+#define SFQ_QD_BC64(x) { const uint32_t lo_ = __shfl_sync(FULL, (uint32_t)(x), 0, LPC), hi_ = __shfl_sync(FULL, (uint32_t)((uint64_t)(x) >> 32), 0, LPC); \
                          if (esc) x = ((uint64_t)hi_ << 32) | lo_; }
             uint64_t sp = (uint64_t)(uintptr_t)rc.src.p;
             SFQ_QD_BC32(b) SFQ_QD_BC32(rc.range) SFQ_QD_BC32(rc.src.left)
@@ -285,26 +357,24 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
         if (fresh) {
             hn = dense ? nctx : __umulhi(nctx * 2654435761u, nent);
             if (!dense && hn == h) hn = h + 1u == nent ? 0u : h + 1u;       // entry h is ours (key = ctx): skip it unseen, its store is still pending
-            const uint32_t *e = tab + (size_t)hn * 64u;
-            na = __ldcg(reinterpret_cast<const uint4 *>(e));
-            nb = __ldcg(reinterpret_cast<const uint4 *>(e + 4));
+            sfq_qd_fetch<LPC>(nv, tab + (size_t)hn * 64u);
         }
 
         // ---------------------------------------------------------------- update_freq (log64_ranger.hpp:69-87)
-        const uint32_t slot = 8u * hl + hk;
+        const uint32_t slot = SPL * hl + hk;
         bool skip = false, wide = false;
         uint32_t fn = f, tot2 = tot;
         if (__any_sync(FULL, act && f > 65472u - 6u)) {
             const bool hv = act && f > 65472u - 6u;
             if (hv && slot == 0u && f + 20u > tot) skip = true;               // saturated front slot: no update at all
             const bool dohalve = hv && !skip;
-            if (dohalve) { m.f0 >>= 1; m.f1 >>= 1; m.f2 >>= 1; m.f3 >>= 1; m.f4 >>= 1; m.f5 >>= 1; m.f6 >>= 1; m.f7 >>= 1; }
-            const uint32_t ls = m.f0 + m.f1 + m.f2 + m.f3 + m.f4 + m.f5 + m.f6 + m.f7;
+            uint32_t ls = 0;
+#pragma unroll
+            for (int k = 0; k < (int)SPL; k++) { if (dohalve) m.f[k] >>= 1; ls += m.f[k]; }
             uint32_t inc = ls, tmp;
-            tmp = __shfl_up_sync(FULL, inc, 1, 8); if (l8 >= 1u) inc += tmp;
-            tmp = __shfl_up_sync(FULL, inc, 2, 8); if (l8 >= 2u) inc += tmp;
-            tmp = __shfl_up_sync(FULL, inc, 4, 8); if (l8 >= 4u) inc += tmp;
-            const uint32_t total = __shfl_sync(FULL, inc, 7, 8);
+#pragma unroll
+            for (int d = 1; d < LPC; d <<= 1) { tmp = __shfl_up_sync(FULL, inc, d, LPC); if (l8 >= (uint32_t)d) inc += tmp; }
+            const uint32_t total = __shfl_sync(FULL, inc, LPC - 1, LPC);
             if (dohalve) {
                 if (l8) m.excl = inc - ls;
                 tot2 = total;
@@ -319,27 +389,21 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
             tot2 += 6u;
             if (l8 > hl) m.excl += 6u;
         }
-        if (mine) {
-            m.f0 = hk == 0u ? fn : m.f0; m.f1 = hk == 1u ? fn : m.f1; m.f2 = hk == 2u ? fn : m.f2; m.f3 = hk == 3u ? fn : m.f3;
-            m.f4 = hk == 4u ? fn : m.f4; m.f5 = hk == 5u ? fn : m.f5; m.f6 = hk == 6u ? fn : m.f6; m.f7 = hk == 7u ? fn : m.f7;
-        }
+        if (mine) m.set_freq(hk, fn);
         uint32_t cnt2 = count;
         const bool cand = upd && slot != 0u;                                 // `++count` is not evaluated for slot 0
         if (cand) cnt2 = (count + 1u) & 0xffu;
         const bool swapc = cand && (cnt2 & 0xfu) == 0u;
+        bool syms_dirty = false;
         if (__any_sync(FULL, swapc)) {                                       // maybe swap slot with slot-1 (down_level)
-            const uint32_t lf7 = __shfl_up_sync(FULL, m.f7, 1, 8);            // left neighbour's last slot
-            const uint32_t lb7 = __shfl_up_sync(FULL, m.sy >> 24, 1, 8);
-            uint64_t s64 = ((uint64_t)m.sy << 32) | m.sx;
-            // lane hl works out the neighbour slot and the verdict, the octet hears it
-            uint32_t fprev = 0, bprev = 0;
-            if (hk == 0u) { fprev = lf7; bprev = lb7; }
-            else {
-                fprev = hk == 1u ? m.f0 : hk == 2u ? m.f1 : hk == 3u ? m.f2 : hk == 4u ? m.f3 : hk == 5u ? m.f4 : hk == 6u ? m.f5 : m.f6;
-                bprev = (uint32_t)(s64 >> (8u * (hk - 1u))) & 0xffu;
-            }
+            const uint32_t lfl = __shfl_up_sync(FULL, m.f[SPL - 1], 1, LPC);   // left neighbour's last slot
+            const uint32_t lbl = __shfl_up_sync(FULL, m.sy[G::SW - 1] >> 24, 1, LPC);
+            // lane hl works out the neighbour slot and the verdict, the group hears it
+            uint32_t fprev, bprev;
+            if (hk == 0u) { fprev = lfl; bprev = lbl; }
+            else { fprev = m.freq_at(hk - 1u); bprev = m.sym_byte(hk - 1u); }
             uint32_t verdict = (swapc && fn > fprev ? 1u : 0u) | (fprev << 1) | (bprev << 24);
-            verdict = __shfl_sync(FULL, verdict, hl, 8);
+            verdict = __shfl_sync(FULL, verdict, hl, LPC);
             if (verdict & 1u) {
                 fprev = (verdict >> 1) & 0xffffu; bprev = verdict >> 24;
                 const uint32_t symprev = bprev ^ (slot - 1u);
@@ -347,32 +411,28 @@ k_qlt_decode4(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc
                 const uint32_t byte_hi = (symprev ^ slot) & 0xffu;            // ... and slot the neighbour's
                 if (l8 == hl) {
                     if (hk == 0u) {
-                        m.f0 = fprev;
-                        s64 = (s64 & ~0xffull) | byte_hi;
+                        m.f[0] = fprev;
+                        m.set_sym_byte(0u, byte_hi);
                         m.excl += fn - fprev;                                 // (hl >= 1 here: lane 0's word keeps the key)
                     } else {
-                        const uint32_t k1 = hk - 1u;
-                        m.f0 = k1 == 0u ? fn : m.f0;                            m.f1 = k1 == 1u ? fn : hk == 1u ? fprev : m.f1;
-                        m.f2 = k1 == 2u ? fn : hk == 2u ? fprev : m.f2; m.f3 = k1 == 3u ? fn : hk == 3u ? fprev : m.f3;
-                        m.f4 = k1 == 4u ? fn : hk == 4u ? fprev : m.f4; m.f5 = k1 == 5u ? fn : hk == 5u ? fprev : m.f5;
-                        m.f6 = k1 == 6u ? fn : hk == 6u ? fprev : m.f6; m.f7 = hk == 7u ? fprev : m.f7;
-                        s64 = (s64 & ~(0xffffull << (8u * k1))) | ((uint64_t)(byte_lo | (byte_hi << 8)) << (8u * k1));
+                        m.set_freq(hk - 1u, fn); m.set_freq(hk, fprev);
+                        m.set_sym_byte(hk - 1u, byte_lo); m.set_sym_byte(hk, byte_hi);
                     }
-                    wide = true;
+                    syms_dirty = true;
                 }
                 if (hk == 0u && l8 + 1u == hl) {
-                    m.f7 = fn;
-                    s64 = (s64 & ~(0xffull << 56)) | ((uint64_t)byte_lo << 56);
-                    wide = true;
+                    m.f[SPL - 1] = fn;
+                    m.set_sym_byte(SPL - 1u, byte_lo);
+                    syms_dirty = true; wide = true;
                 }
-                m.sx = (uint32_t)s64; m.sy = (uint32_t)(s64 >> 32);
             }
         }
         if (act) {
             m.hdr = tot2 | (cnt2 << 24);
             uint32_t *e = tab + (size_t)h * 64u;
-            if (wide || mine) sfq_qd_store_freqs(m, e);
-            if (wide) sfq_qd_store_tail(m, e); else sfq_qd_store_hdr(m, e);
+            if (wide || mine) m.store_freqs(e);
+            if (syms_dirty) m.store_syms(e);
+            m.store_hdr(e);
         }
         if (fresh) { h = hn; ctx = nctx; chk = !dense; }
     }
