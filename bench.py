@@ -243,6 +243,7 @@ def main():
     launches = 0
     code_ms_c = code_ms_d = scan_ms = qd_ms = 0.0
     waves_c = waves_d = 0
+    per_step = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         csz, sc, sd = step_device()
@@ -250,6 +251,7 @@ def main():
         launches += sc["kernel_launches"] + sd["kernel_launches"]
         code_ms_c += sc["ms_code"]; code_ms_d += sd["ms_code"]; scan_ms += sc["ms_scan"]; qd_ms += sd["ms_qlt"]
         waves_c += sc["waves"]; waves_d += sd["waves"]
+        per_step.append([round(sc["ms_code"], 1), round(sd["ms_gen"], 1), round(sd["ms_qlt"], 1), round(sd["ms_rec"], 1)])
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -299,15 +301,20 @@ def main():
         if ok:
             barrier()
             e_ms = e_copy = 0.0
+            e_steps = []
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 cn, on, s1, s2, b = step_e2e()
                 e_ms += s1["ms_total"] + s2["ms_total"]
                 e_copy += s1["ms_h2d"] + s1["ms_d2h"] + s2["ms_h2d"] + s2["ms_d2h"]
+                e_steps.append([round(s1["ms_total"], 1), round(s1["ms_code"], 1), round(s2["ms_total"], 1), round(s2["ms_gen"], 1), round(s2["ms_qlt"], 1), round(s2["ms_rec"], 1)])
+                e_parts = {"c_total": s1["ms_total"], "c_h2d": s1["ms_h2d"], "c_code": s1["ms_code"], "c_d2h": s1["ms_d2h"], "c_waves": s1["waves"],
+                           "d_total": s2["ms_total"], "d_h2d": s2["ms_h2d"], "d_code": s2["ms_code"], "d_d2h": s2["ms_d2h"], "d_waves": s2["waves"],
+                           "d_resident": s2["resident_chunks"]}
                 launches += s1["kernel_launches"] + s2["kernel_launches"]
             barrier()
             e_wall = time.perf_counter() - t0
-            e2e = {"ms": e_ms, "wall_s": e_wall, "h2d": n + cn, "d2h": cn + n, "copy_ms": e_copy}
+            e2e = {"ms": e_ms, "wall_s": e_wall, "h2d": n + cn, "d2h": cn + n, "copy_ms": e_copy, "steps": e_steps, "parts": {k: round(float(v), 2) for k, v in e_parts.items()}}
             del h_text
         elif not e2e_err:
             e2e_err = "another rank could not set up its host buffers"
@@ -344,7 +351,7 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         K_ = args.steps
         value = 2 * tot_bytes * K_ / (dev_ms_max / 1e3) / 1e9
-        # Dominant kernel = the quality decoder (k_qlt_decode4, the longest launch of a step).  Algorithmic bytes
+        # Dominant kernel = the quality decoder (k_qlt_decode<LPC>, the longest launch of a step).  Algorithmic bytes
         # per launch: one byte out per quality + the qlt stream bytes in.  Its duration is
         # measured with CUDA events on the stream it is launched on (sfq_stats.ms_qlt of the decompress call).
         plane_bytes = sc["nbases"] + sc["nquals"] + (n - sc["nbases"] - sc["nquals"] - 6 * sc["nrecords"])
@@ -362,7 +369,7 @@ def main():
             "compress_qlt (k_qlt_keys/scan/scatter/model + k_rc_encode<1>)": gbps(sc["nquals"] + sc["qlt_stream_bytes"], sc["ms_qlt"]),
             "compress_rec (k_encode<2>)": gbps(hdr_bytes, sc["ms_rec"]),
             "decompress_gen (k_decode<0>)": gbps(sd["nbases"] + sd["gen_stream_bytes"], sd["ms_gen"]),
-            "decompress_qlt (k_qlt_decode4)": gbps(sd["nquals"] + sd["qlt_stream_bytes"], sd["ms_qlt"]),
+            "decompress_qlt (k_qlt_decode<LPC>)": gbps(sd["nquals"] + sd["qlt_stream_bytes"], sd["ms_qlt"]),
             "decompress_rec (k_decode<2>)": gbps(hdr_bytes, sd["ms_rec"]),
         }
         line = {
@@ -378,7 +385,7 @@ def main():
             "wall_s_per_step": round(wall_max / K_, 4),
             "clocks": clocks,
             "gpu_launches": int(launches_sum),
-            "roofline": {"bound": "hbm", "kernel": "k_qlt_decode4 (quality decoder: 4 chunks per warp, 8 lanes per chunk)",
+            "roofline": {"bound": "hbm", "kernel": "k_qlt_decode<%d> (quality decoder: %d lanes per chunk, %d chunks per warp, warp-converged)" % ((4, 4, 8) if sd["resident_chunks"] >= 4096 else (8, 8, 4)),
                          "achieved": round(achieved, 3), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 6),
                          "traffic": None, "traffic_note": "profiles/: dram bytes per decoded quality from the ncu --set full capture (smaller input; a 10 GB launch cannot be replayed)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
@@ -386,6 +393,7 @@ def main():
                          "launch_ms_avg": round(qd_ms / K_ / max(1, sd["waves"]), 3),
                          "note": "a serial adaptive-coder chain per chunk: bound by issue slots and dependent latency, not by HBM (see chain and DESIGN.md section 3)"},
             "coder_kernels_GBps": coder_kernels,
+            "per_step_ms[c_code,d_gen,d_qlt,d_rec]": per_step,
             "chain": {"symbols_per_chunk_stream": round(symbols / 2 / max(1, sc["nchunks"])),
                       "compress": {"resident_chunks": sc["resident_chunks"], "waves": sc["waves"],
                                    "ns_per_symbol_per_wave": round(code_ms_c / K_ * 1e6 / (symbols / 2 / sc["nchunks"]) / max(1, sc["waves"]), 2)},
@@ -405,7 +413,7 @@ def main():
             line["e2e"] = {"value": round(ev, 4), "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                            "timing": "wall clock around K steps of sfq_compress+sfq_decompress on pinned host buffers, barrier+sync both sides",
                            "device_event_ms_per_step": round(e2e["ms"] / K_, 3),
-                           "copy_ms_per_step": round(e2e["copy_ms"] / K_, 3),
+                           "copy_ms_per_step": round(e2e["copy_ms"] / K_, 3), "last_step_ms": e2e["parts"], "per_step_ms[c_total,c_code,d_total,d_gen,d_qlt,d_rec]": e2e["steps"],
                            "note": "copies and coding run back to back (no overlap yet): e2e = value's kernels + PCIe time"}
         elif e2e_err:
             line["e2e"] = {"value": None, "unit": UNIT, "error": e2e_err}

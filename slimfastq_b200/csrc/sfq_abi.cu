@@ -82,6 +82,10 @@ struct sfq_ctx {
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
            e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff;
+    uint32_t dec_warps = 1;                 // SFQ_DEC_WARPS=1..4
+    int enc_order = 0;                      // SFQ_ENC_ORDER=1: quality path's keys+scan before k_gen_model
+    uint32_t enc_rec_lanes = 0;             // SFQ_ENC_REC_LANES: chunk-streams per warp of the header encoder (0 = pick_lanes)
+    cudaEvent_t head_ev = nullptr;
     bool trace = false;                     // SFQ_TRACE=1: per-kernel event timings of the coder waves on stderr
     std::vector<std::pair<const char *, std::pair<cudaEvent_t, cudaEvent_t>>> tr;
     int gdec32 = 0;                         // SFQ_GDEC=1: warp-converged base decoder (A/B; slower)
@@ -380,6 +384,17 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 CK(cudaEventRecord(ctx->fork_ev, s));
                 CK(cudaStreamWaitEvent(side0, ctx->fork_ev, 0));
                 CK(cudaStreamWaitEvent(side1, ctx->fork_ev, 0));
+                uint32_t wave_max_nrec = 1;
+                for (uint32_t c = c0; c < c0 + nc; c++) wave_max_nrec = std::max(wave_max_nrec, metas[c].nrec);
+                if (two_phase && ctx->enc_order == 1) {
+                    // the two short head kernels of the quality path get the machine before k_gen_model's long-running
+                    // CTAs take its registers (they would otherwise trickle through what is left: 118 + 77 ms against 14 + 10)
+                    CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
+                    TRACED("k_qlt_keys", side0, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, side0>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
+                    TRACED("k_qlt_scan", side0, (k_qlt_scan<<<nc, 256, 0, side0>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    CK(cudaEventRecord(ctx->head_ev, side0));
+                    CK(cudaStreamWaitEvent(s, ctx->head_ev, 0));
+                }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
                 if (two_phase) {
                     { TraceScope ts_(ctx, "k_gen_model", s);
@@ -395,13 +410,13 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
+                if (!(two_phase && ctx->enc_order == 1)) CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
                 if (two_phase) {
                     cudaStream_t q = side0;
-                    uint32_t wave_max_nrec = 1;
-                    for (uint32_t c = c0; c < c0 + nc; c++) wave_max_nrec = std::max(wave_max_nrec, metas[c].nrec);
-                    TRACED("k_qlt_keys", q, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
-                    TRACED("k_qlt_scan", q, (k_qlt_scan<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    if (ctx->enc_order != 1) {
+                        TRACED("k_qlt_keys", q, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
+                        TRACED("k_qlt_scan", q, (k_qlt_scan<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    }
                     TRACED("k_qlt_scatter", q, (k_qlt_scatter<<<nwarp_blocks, 128, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
                     TRACED("k_qlt_model", q, (k_qlt_model<<<ctx->sm_count * 4, SFQ_QM_THREADS, 0, q>>>(d_metas + c0, ws_at(ws, c0), e2, d_e2c, c0))); LAUNCHED();
                     k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
@@ -411,7 +426,10 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
-                TRACED("k_encode<2>", side1, (k_encode<2><<<nb, 32, 0, side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes))); LAUNCHED();
+                {
+                    const uint32_t rl = ctx->lanes ? ctx->lanes : ctx->enc_rec_lanes ? ctx->enc_rec_lanes : lanes;
+                    TRACED("k_encode<2>", side1, (k_encode<2><<<(nc + rl - 1) / rl, 32, 0, side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, rl))); LAUNCHED();
+                }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
                 CK(cudaEventRecord(ctx->join_ev[1], side1));
@@ -585,6 +603,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
             {
                 const uint32_t lanes = pick_lanes(ctx, nc);
                 const unsigned nb = (nc + lanes - 1) / lanes;
+                const unsigned dw = ctx->dec_warps;            // warps per CTA of the thread-per-chunk decoders
                 uint8_t *pb = ctx->bases.as<uint8_t>(), *pq = ctx->quals.as<uint8_t>(), *ph = ctx->hdrs.as<uint8_t>();
                 CK(cudaEventRecord(ctx->fork_ev, s));
                 CK(cudaStreamWaitEvent(side0, ctx->fork_ev, 0));
@@ -606,12 +625,12 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 // base decoder: thread per chunk, `lanes` chunks per warp.  (SFQ_GDEC=1 runs the warp-converged form,
                 // 32 chunks per warp: correct, but its link waits for the slowest of 32 table reads - 45 % slower, kept for A/B.)
                 if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
-                else k_decode<0><<<nb, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
+                else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
                 LAUNCHED();
                 k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
-                k_decode<2><<<nb, 32, 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
+                k_decode<2><<<(nb + dw - 1) / dw, 32 * dw, 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
                 CK(cudaEventRecord(ctx->join_ev[1], side1));
@@ -711,6 +730,9 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_RC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->rc_lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_SERIAL")) ctx->serial_encoder = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_DEC_WARPS")) { int v = atoi(e); if (v >= 1 && v <= SFQ_DEC_MAXW) ctx->dec_warps = (uint32_t)v; }
+    if (const char *e = getenv("SFQ_ENC_ORDER")) ctx->enc_order = atoi(e);
+    if (const char *e = getenv("SFQ_ENC_REC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->enc_rec_lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_TRACE")) ctx->trace = atoi(e) != 0;
     if (const char *e = getenv("SFQ_GDEC")) ctx->gdec32 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QLPC")) { int v = atoi(e); if (v == 4 || v == 8) ctx->qlpc = (uint32_t)v; }
@@ -727,6 +749,7 @@ int sfq_create(sfq_ctx **out, int device) {
         if (cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, k == 0 ? prio_hi : prio_lo) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->head_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     *out = ctx;
     return 0;
 }
@@ -740,6 +763,7 @@ void sfq_destroy(sfq_ctx *ctx) {
     for (auto &e : ctx->wave_ev) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) { if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]); if (ctx->join_ev[k]) cudaEventDestroy(ctx->join_ev[k]); }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->head_ev) cudaEventDestroy(ctx->head_ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

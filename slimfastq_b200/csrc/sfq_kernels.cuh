@@ -269,13 +269,14 @@ k_gen_exceptions(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__
     sfq_gen_apply_exceptions(in, d.ssize, d.soff, &metas[c], ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS, bases + d.base_plane);
 }
 
+#define SFQ_DEC_MAXW 4                 // warps per CTA of the thread-per-chunk decoders (1..4; more per CTA = fewer, fatter CTAs)
 template <int ROLE>
-__global__ void __launch_bounds__(ROLE == 1 ? 64 : 32)
+__global__ void __launch_bounds__(ROLE == 1 ? 64 : 32 * SFQ_DEC_MAXW)
 k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
          SfqWorkspace ws, SfqRecTables t, uint8_t *bases, uint8_t *quals, uint8_t *hdrs, uint32_t nchunks, uint32_t lanes) {
     __shared__ uint32_t lut[ROLE == 0 ? SFQ_B2_LUT : 1];       // reciprocals of the 4-symbol model's totals
-    __shared__ uint4 cells[ROLE == 0 ? 64 : 1];                // bucket look-ahead, two 16-byte cells per thread
-    if (ROLE == 0) { sfq_b2_lut_fill(lut, threadIdx.x, 32); __syncthreads(); }
+    __shared__ uint4 cells[ROLE == 0 ? 64 * SFQ_DEC_MAXW : 1]; // bucket look-ahead, two 16-byte cells per thread
+    if (ROLE == 0) { sfq_b2_lut_fill(lut, threadIdx.x, blockDim.x); __syncthreads(); }
     if (ROLE == 1) {
         // `lanes` = groups (chunks) per warp: fewer groups per warp means fewer groups waiting on each
         // other's divergent branches and memory round trips (the chain is latency-bound, lanes are cheap)
@@ -289,15 +290,16 @@ k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, Sfq
                              ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS, t.qlen + d.rec_base, t.qoff + d.rec_base, quals, g);
         return;
     }
-    const uint32_t c = blockIdx.x * lanes + threadIdx.x;
-    if (threadIdx.x >= lanes || c >= nchunks) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes + lane;
+    if (lane >= lanes || c >= nchunks) return;
     const SfqDecChunk &d = dc[c];
     SfqChunkMeta *m = &metas[c];
     if (m->status != SFQ_OK) return;
     uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
     if (ROLE == 0) {
         SfqStage stage;
-        stage.cell0 = &cells[threadIdx.x]; stage.cell1 = &cells[32 + threadIdx.x];
+        stage.cell0 = &cells[threadIdx.x]; stage.cell1 = &cells[blockDim.x + threadIdx.x];
         sfq_gen_decode_chunk(in, d.ssize, d.soff, m, d.level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw,
                              t.llen + d.rec_base, t.boff + d.rec_base, bases, lut, stage, ws.gen_ahead2);
     }

@@ -18,5 +18,5 @@ for r in rows:
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(r[-1]) / 1e6
 for k, (n, ms) in agg.items(): print(f"{k:28s} x{n:3d} {ms:10.3f} ms")
 PY
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_gen_model|k_qlt_scatter|k_rc_encode|k_qlt_model|k_qlt_decode4|k_decode' -c 8 -o gpurun_out/${TAG}_ncu_full -f python bench.py --gb 0.25 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_gen_model|k_qlt_scatter|k_rc_encode|k_qlt_model|k_qlt_decode|k_decode' -c 8 -o gpurun_out/${TAG}_ncu_full -f python bench.py --gb 0.25 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log; ls -la gpurun_out/*.ncu-rep
