@@ -82,6 +82,8 @@ struct sfq_ctx {
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
            e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff;
+    int spread = 0;                         // SFQ_SPREAD=1: fat CTAs + shared-memory reservation for the decoders (A/B; see below)
+    unsigned spread_smem[3] = {0, 0, 0};    // dynamic shared memory reserved per CTA: base, quality, header decoder
     uint32_t dec_warps = 1;                 // SFQ_DEC_WARPS=1..4
     int enc_order = 0;                      // SFQ_ENC_ORDER=1: quality path's keys+scan before k_gen_model
     uint32_t enc_rec_lanes = 0;             // SFQ_ENC_REC_LANES: chunk-streams per warp of the header encoder (0 = pick_lanes)
@@ -603,7 +605,14 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
             {
                 const uint32_t lanes = pick_lanes(ctx, nc);
                 const unsigned nb = (nc + lanes - 1) / lanes;
-                const unsigned dw = ctx->dec_warps;            // warps per CTA of the thread-per-chunk decoders
+                // SFQ_SPREAD=1: a few fat CTAs per kernel (about one per SM), each reserving enough shared memory that no
+                // more than two of a kind fit on an SM.  Background: with hundreds of one-warp CTAs launched next to the
+                // other two kernels, roughly one decode call in twenty sees the base decoder run 3.7x slower while the
+                // other two run faster - its CTAs were packed onto few SMs.  The reservation removes the outliers but
+                // takes the L1 carve-out with it and costs more than they do (quality decoder 860 -> 1 264 ms, header
+                // decoder 486 -> 911 ms at 10 GB), so it is off by default (profiles/README.md, r1e).
+                const bool spread = ctx->spread != 0;
+                const unsigned dw = spread ? SFQ_DEC_MAXW : ctx->dec_warps;            // warps per CTA of the thread-per-chunk decoders
                 uint8_t *pb = ctx->bases.as<uint8_t>(), *pq = ctx->quals.as<uint8_t>(), *ph = ctx->hdrs.as<uint8_t>();
                 CK(cudaEventRecord(ctx->fork_ev, s));
                 CK(cudaStreamWaitEvent(side0, ctx->fork_ev, 0));
@@ -615,8 +624,9 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                     // lanes per chunk: 8 while the chains are latency-bound, 4 (twice the chunks per warp, a longer
                     // link) once a wave is large enough for issue slots to be what its warps compete for
                     const uint32_t lpc = ctx->qlpc ? ctx->qlpc : nc >= 4096u ? 4u : 8u;
-                    if (lpc == 4) k_qlt_decode<4><<<(nc + 8 * SFQ_QD_WARPS - 1) / (8 * SFQ_QD_WARPS), 32 * SFQ_QD_WARPS, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
-                    else k_qlt_decode<8><<<(nc + 4 * SFQ_QD_WARPS - 1) / (4 * SFQ_QD_WARPS), 32 * SFQ_QD_WARPS, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    const unsigned qw = spread ? SFQ_QD_MAXW : 2u;               // warps per CTA
+                    if (lpc == 4) k_qlt_decode<4><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, spread ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    else k_qlt_decode<8><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, spread ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
                     LAUNCHED();
                 }
                 else { k_decode<1><<<(nc + 2 * ctx->qgpw - 1) / (2 * ctx->qgpw), 64, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->qgpw); LAUNCHED(); }
@@ -625,12 +635,12 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 // base decoder: thread per chunk, `lanes` chunks per warp.  (SFQ_GDEC=1 runs the warp-converged form,
                 // 32 chunks per warp: correct, but its link waits for the slowest of 32 table reads - 45 % slower, kept for A/B.)
                 if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
-                else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
+                else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, spread ? ctx->spread_smem[0] : 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
                 LAUNCHED();
                 k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
-                k_decode<2><<<(nb + dw - 1) / dw, 32 * dw, 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
+                k_decode<2><<<(nb + dw - 1) / dw, 32 * dw, spread ? ctx->spread_smem[2] : 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
                 CK(cudaEventRecord(ctx->join_ev[1], side1));
@@ -730,6 +740,7 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_RC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->rc_lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_SERIAL")) ctx->serial_encoder = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_SPREAD")) ctx->spread = atoi(e) != 0;
     if (const char *e = getenv("SFQ_DEC_WARPS")) { int v = atoi(e); if (v >= 1 && v <= SFQ_DEC_MAXW) ctx->dec_warps = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_ORDER")) ctx->enc_order = atoi(e);
     if (const char *e = getenv("SFQ_ENC_REC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->enc_rec_lanes = (uint32_t)v; }
@@ -750,6 +761,17 @@ int sfq_create(sfq_ctx **out, int device) {
             cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->head_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    {   // shared memory the decoders' CTAs reserve when they are spread (one of each kind per SM fits, two of a kind barely)
+        int smem_sm = 0;
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+        const unsigned unit = smem_sm > 0 ? (unsigned)smem_sm / 11u : 20u << 10;      // ~20.7 KB on B200 (228 KB per SM): 4 + 3 + 3 units < one SM
+        ctx->spread_smem[0] = 4 * unit - 8192; ctx->spread_smem[1] = 3 * unit; ctx->spread_smem[2] = 3 * unit - 1024;
+        bool ok = cudaFuncSetAttribute(k_decode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[0]) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[2]) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_qlt_decode<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_qlt_decode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); ctx->spread_smem[0] = ctx->spread_smem[1] = ctx->spread_smem[2] = 0; }
+    }
     *out = ctx;
     return 0;
 }

@@ -157,16 +157,16 @@ __device__ __forceinline__ void sfq_qd_fetch(uint4 (&v)[SfqQdGeo<LPC>::NV], cons
     for (int q = 0; q < SfqQdGeo<LPC>::NV; q++) v[q] = __ldcg(reinterpret_cast<const uint4 *>(e + 4 * q));
 }
 
-#define SFQ_QD_WARPS 2                  // warps per CTA
+#define SFQ_QD_MAXW 8                   // most warps per CTA (the launch picks 2 or 8)
 template <int LPC>
-__global__ void __launch_bounds__(32 * SFQ_QD_WARPS)
+__global__ void __launch_bounds__(32 * SFQ_QD_MAXW)
 k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas, SfqWorkspace ws,
              SfqRecTables t, uint8_t *quals, uint32_t nchunks) {
     typedef SfqQdGeo<LPC> G;
     constexpr uint32_t SPL = G::SPL;
     const unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u, l8 = lane % LPC, osh = lane - l8;       // l8 = lane inside the chunk's group
-    const uint32_t c = (blockIdx.x * SFQ_QD_WARPS + (threadIdx.x >> 5)) * G::CPW + lane / LPC;
+    const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G::CPW + lane / LPC;
     bool live = c < nchunks;
     if (live) live = metas[c].status == SFQ_OK;
     const bool valid = live;
