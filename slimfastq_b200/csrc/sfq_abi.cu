@@ -611,7 +611,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 // other two run faster - its CTAs were packed onto few SMs.  The reservation removes the outliers but
                 // takes the L1 carve-out with it and costs more than they do (quality decoder 860 -> 1 264 ms, header
                 // decoder 486 -> 911 ms at 10 GB), so it is off by default (profiles/README.md, r1e).
-                const bool spread = ctx->spread != 0;
+                const int spread = ctx->spread;
                 const unsigned dw = spread ? SFQ_DEC_MAXW : ctx->dec_warps;            // warps per CTA of the thread-per-chunk decoders
                 uint8_t *pb = ctx->bases.as<uint8_t>(), *pq = ctx->quals.as<uint8_t>(), *ph = ctx->hdrs.as<uint8_t>();
                 CK(cudaEventRecord(ctx->fork_ev, s));
@@ -625,8 +625,8 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                     // link) once a wave is large enough for issue slots to be what its warps compete for
                     const uint32_t lpc = ctx->qlpc ? ctx->qlpc : nc >= 4096u ? 4u : 8u;
                     const unsigned qw = spread ? SFQ_QD_MAXW : 2u;               // warps per CTA
-                    if (lpc == 4) k_qlt_decode<4><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, spread ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
-                    else k_qlt_decode<8><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, spread ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    if (lpc == 4) k_qlt_decode<4><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, spread == 1 ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    else k_qlt_decode<8><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, spread == 1 ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
                     LAUNCHED();
                 }
                 else { k_decode<1><<<(nc + 2 * ctx->qgpw - 1) / (2 * ctx->qgpw), 64, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->qgpw); LAUNCHED(); }
@@ -635,12 +635,12 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 // base decoder: thread per chunk, `lanes` chunks per warp.  (SFQ_GDEC=1 runs the warp-converged form,
                 // 32 chunks per warp: correct, but its link waits for the slowest of 32 table reads - 45 % slower, kept for A/B.)
                 if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
-                else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, spread ? ctx->spread_smem[0] : 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
+                else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, spread == 1 ? ctx->spread_smem[0] : 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
                 LAUNCHED();
                 k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
-                k_decode<2><<<(nb + dw - 1) / dw, 32 * dw, spread ? ctx->spread_smem[2] : 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
+                k_decode<2><<<(nb + dw - 1) / dw, 32 * dw, spread == 1 ? ctx->spread_smem[2] : 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
                 CK(cudaEventRecord(ctx->join_ev[1], side1));
@@ -740,7 +740,7 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_RC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->rc_lanes = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_SERIAL")) ctx->serial_encoder = atoi(e) != 0;
-    if (const char *e = getenv("SFQ_SPREAD")) ctx->spread = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_SPREAD")) ctx->spread = atoi(e);          // 1: fat CTAs + reservation, 2: fat CTAs only
     if (const char *e = getenv("SFQ_DEC_WARPS")) { int v = atoi(e); if (v >= 1 && v <= SFQ_DEC_MAXW) ctx->dec_warps = (uint32_t)v; }
     if (const char *e = getenv("SFQ_ENC_ORDER")) ctx->enc_order = atoi(e);
     if (const char *e = getenv("SFQ_ENC_REC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->enc_rec_lanes = (uint32_t)v; }
