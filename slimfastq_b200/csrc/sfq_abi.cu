@@ -82,9 +82,10 @@ struct sfq_ctx {
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
            e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff;
-    int spread = 0;                         // SFQ_SPREAD=1: fat CTAs + shared-memory reservation for the decoders (A/B; see below)
+    int spread = -1;                        // SFQ_SPREAD=0..3 (default: 3 for large waves, else 0; see decompress_on_device)
     unsigned spread_smem[3] = {0, 0, 0};    // dynamic shared memory reserved per CTA: base, quality, header decoder
-    uint32_t dec_warps = 1;                 // SFQ_DEC_WARPS=1..4
+    uint32_t dec_warps = 4;                 // SFQ_DEC_WARPS=1..4: warps per CTA of the thread-per-chunk decoders (one-warp CTAs each
+                                            // carry the whole static shared memory: 4x the footprint, less L1 for everyone - 35 % slower decode)
     int enc_order = 0;                      // SFQ_ENC_ORDER=1: quality path's keys+scan before k_gen_model
     uint32_t enc_rec_lanes = 0;             // SFQ_ENC_REC_LANES: chunk-streams per warp of the header encoder (0 = pick_lanes)
     cudaEvent_t head_ev = nullptr;
@@ -605,14 +606,17 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
             {
                 const uint32_t lanes = pick_lanes(ctx, nc);
                 const unsigned nb = (nc + lanes - 1) / lanes;
-                // SFQ_SPREAD=1: a few fat CTAs per kernel (about one per SM), each reserving enough shared memory that no
-                // more than two of a kind fit on an SM.  Background: with hundreds of one-warp CTAs launched next to the
-                // other two kernels, roughly one decode call in twenty sees the base decoder run 3.7x slower while the
-                // other two run faster - its CTAs were packed onto few SMs.  The reservation removes the outliers but
-                // takes the L1 carve-out with it and costs more than they do (quality decoder 860 -> 1 264 ms, header
-                // decoder 486 -> 911 ms at 10 GB), so it is off by default (profiles/README.md, r1e).
-                const int spread = ctx->spread;
-                const unsigned dw = spread ? SFQ_DEC_MAXW : ctx->dec_warps;            // warps per CTA of the thread-per-chunk decoders
+                // Launched next to the other two kernels, the base decoder's CTAs are now and then packed onto few SMs by
+                // the block scheduler: that call's base decoder runs 3.7x slower while the other two run faster (about one
+                // decode call in eight at 10 GB; profiles/README.md, r1e/r1f).  A shared-memory reservation bounds how many
+                // CTAs of a kind fit on an SM:
+                //   3 (default for large waves)  only the base decoder reserves (at most two of its CTAs per SM): no outlier
+                //                                in 7 steps, 1.5 % slower than an outlier-free default step;
+                //   1  all three decoders as ~one fat CTA per SM with reservations: no outliers either, but the reservations
+                //      take the L1 carve-out with them (quality decoder 860 -> 1 264 ms, header decoder 486 -> 911 ms);
+                //   2  the fat CTAs of 1 without reservations: slower and still packs;   0  nothing.
+                const int spread = ctx->spread >= 0 ? ctx->spread : nc >= 4096u ? 3 : 0;
+                const unsigned dw = spread ? SFQ_DEC_MAXW : ctx->dec_warps;      // (spread 3: only the base decoder reserves)            // warps per CTA of the thread-per-chunk decoders
                 uint8_t *pb = ctx->bases.as<uint8_t>(), *pq = ctx->quals.as<uint8_t>(), *ph = ctx->hdrs.as<uint8_t>();
                 CK(cudaEventRecord(ctx->fork_ev, s));
                 CK(cudaStreamWaitEvent(side0, ctx->fork_ev, 0));
@@ -624,7 +628,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                     // lanes per chunk: 8 while the chains are latency-bound, 4 (twice the chunks per warp, a longer
                     // link) once a wave is large enough for issue slots to be what its warps compete for
                     const uint32_t lpc = ctx->qlpc ? ctx->qlpc : nc >= 4096u ? 4u : 8u;
-                    const unsigned qw = spread ? SFQ_QD_MAXW : 2u;               // warps per CTA
+                    const unsigned qw = (spread == 1 || spread == 2) ? SFQ_QD_MAXW : 2u;               // warps per CTA
                     if (lpc == 4) k_qlt_decode<4><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, spread == 1 ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
                     else k_qlt_decode<8><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, spread == 1 ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
                     LAUNCHED();
@@ -635,7 +639,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 // base decoder: thread per chunk, `lanes` chunks per warp.  (SFQ_GDEC=1 runs the warp-converged form,
                 // 32 chunks per warp: correct, but its link waits for the slowest of 32 table reads - 45 % slower, kept for A/B.)
                 if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
-                else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, spread == 1 ? ctx->spread_smem[0] : 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
+                else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, (spread == 1 || spread == 3) ? ctx->spread_smem[0] : 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
                 LAUNCHED();
                 k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED();
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
