@@ -120,6 +120,17 @@ int    sfq_export_reference(const uint8_t *sfq, size_t n, const char *orig_filen
 size_t sfq_import_reference_bound(size_t n);
 int    sfq_import_reference(const uint8_t *ref, size_t n, uint8_t *out, size_t out_cap, size_t *out_n);
 
+/* ---- record boundaries in FASTQ text (host-only helpers of the streaming CLI and of N-GPU sharding) -----------
+ * The reference finds records while it pages its input (usrs.cpp:96-122, 303-390); a caller that cuts the
+ * input itself - segments of a pipe, shards for several GPUs - needs the same notion without coding anything.
+ * A line that starts with '@' is a header iff the line two below starts with '+' (a quality line may begin
+ * with '@', but it is then followed by a header and a base line, never by a '+' line two below).
+ *   sfq_record_start_at_or_after   smallest record start >= pos (n if there is none)
+ *   sfq_last_record_start          largest record start in [1, n) whose '+' line is inside the buffer; 0 if none:
+ *                                  everything before it is whole records, the tail is carried to the next segment */
+size_t sfq_record_start_at_or_after(const uint8_t *fastq, size_t n, size_t pos);
+size_t sfq_last_record_start(const uint8_t *fastq, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,7 @@ EXPORTS = [
     "sfq_decompress_device", "sfq_decompressed_size", "sfq_get_stats",
     "sfq_is_reference_file", "sfq_export_reference_bound", "sfq_export_reference",
     "sfq_import_reference_bound", "sfq_import_reference",
+    "sfq_record_start_at_or_after", "sfq_last_record_start",
 ]
 
 _lib = None
@@ -77,6 +78,8 @@ def load_library():
     L.sfq_export_reference.argtypes = [vp, sz, C.c_char_p, vp, sz, C.POINTER(sz)]; L.sfq_export_reference.restype = C.c_int
     L.sfq_import_reference_bound.argtypes = [sz]; L.sfq_import_reference_bound.restype = sz
     L.sfq_import_reference.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]; L.sfq_import_reference.restype = C.c_int
+    L.sfq_record_start_at_or_after.argtypes = [vp, sz, sz]; L.sfq_record_start_at_or_after.restype = sz
+    L.sfq_last_record_start.argtypes = [vp, sz]; L.sfq_last_record_start.restype = sz
     _lib = L
     return L
 

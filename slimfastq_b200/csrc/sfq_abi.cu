@@ -1013,4 +1013,32 @@ int sfq_import_reference(const uint8_t *ref, size_t n, uint8_t *out, size_t out_
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------ record boundaries (host)
+size_t sfq_record_start_at_or_after(const uint8_t *t, size_t n, size_t pos) {
+    if (pos == 0) return 0;
+    if (!t || pos > n) return n;
+    const uint8_t *p = (const uint8_t *)memchr(t + pos - 1, '\n', n - (pos - 1));
+    while (p && (size_t)(p - t) + 1 < n) {
+        const size_t s = (size_t)(p - t) + 1;
+        if (t[s] == '@') {
+            const uint8_t *l2 = (const uint8_t *)memchr(t + s, '\n', n - s);
+            const uint8_t *l3 = l2 && (size_t)(l2 - t) + 1 < n ? (const uint8_t *)memchr(l2 + 1, '\n', n - (size_t)(l2 + 1 - t)) : nullptr;
+            if (l3 && (size_t)(l3 - t) + 1 < n && l3[1] == '+') return s;
+        }
+        p = (const uint8_t *)memchr(t + s, '\n', n - s);
+    }
+    return n;
+}
+
+size_t sfq_last_record_start(const uint8_t *t, size_t n) {
+    if (!t || n == 0) return 0;
+    for (size_t w = 1u << 20;; w *= 4) {            // look in a growing window at the end: records are short
+        const size_t from = n > w ? n - w : 0;
+        size_t cut = 0, s = sfq_record_start_at_or_after(t, n, from ? from : 1);
+        while (s < n) { cut = s; s = sfq_record_start_at_or_after(t, n, s + 1); }
+        if (cut || from == 0) return cut;
+    }
+}
+
 }  // extern "C"

@@ -139,32 +139,7 @@ static void statistics_dump(const uint8_t *p, size_t n) {      // config.cpp:76-
 // ---- bounded-memory streaming (usrs.cpp:96-122 pages its input through a 1 MiB buffer; here the unit is
 // a segment of many chunks: each one is a container of its own, their blobs are appended to the output as
 // they are produced and one index is written at the end).
-// Smallest record start >= pos.  A line starting with '@' is a header iff the line two below starts with
-// '+': a quality line that begins with '@' is followed by a header and then bases, never by a '+' line there.
-static size_t record_start_at_or_after(const uint8_t *t, size_t n, size_t pos) {
-    if (pos == 0) return 0;
-    const uint8_t *p = (const uint8_t *)memchr(t + pos - 1, '\n', n - (pos - 1));
-    while (p && (size_t)(p - t) + 1 < n) {
-        const size_t s = (size_t)(p - t) + 1;
-        if (t[s] == '@') {
-            const uint8_t *l2 = (const uint8_t *)memchr(t + s, '\n', n - s);
-            const uint8_t *l3 = l2 && (size_t)(l2 - t) + 1 < n ? (const uint8_t *)memchr(l2 + 1, '\n', n - (size_t)(l2 + 1 - t)) : nullptr;
-            if (l3 && (size_t)(l3 - t) + 1 < n && l3[1] == '+') return s;
-        }
-        p = (const uint8_t *)memchr(t + s, '\n', n - s);
-    }
-    return n;
-}
-// Last record start in the buffer (everything before it is whole records); 0 if there is none.
-static size_t last_record_start(const uint8_t *t, size_t n) {
-    for (size_t w = 1u << 20;; w *= 4) {
-        const size_t from = n > w ? n - w : 0;
-        size_t cut = 0, s = from ? record_start_at_or_after(t, n, from) : 0;
-        if (from == 0) s = record_start_at_or_after(t, n, 1);
-        while (s < n) { cut = s; s = record_start_at_or_after(t, n, s + 1); }
-        if (cut || from == 0) return cut;
-    }
-}
+static size_t last_record_start(const uint8_t *t, size_t n) { return sfq_last_record_start(t, n); }
 
 struct StreamOut {                       // the container being assembled on disk
     FILE *f = nullptr;
