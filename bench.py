@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--gb", type=float, default=10.0, help="workload size per GPU in decimal GB")
     ap.add_argument("--level", type=int, default=3)
     ap.add_argument("--chunk", type=int, default=1 << 20)
+    ap.add_argument("--bins8", action="store_true", help="Illumina 8-bin quantised qualities (BASELINE configs[2] variant)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-mb", type=int, default=0, help="CPU baseline sample (0 = 32 MiB x cores, <= 1 GiB)")
@@ -172,12 +173,12 @@ def reference_whole_file_ratio(sample: bytes, level: int) -> dict:
 
 
 # ------------------------------------------------------------------------------ workload
-def make_workload(nbytes: int, rank: int):
+def make_workload(nbytes: int, rank: int, bins8: bool = False):
     """(unique block bytes, tiles): Markov-quality Illumina block, tiled to `nbytes`.  Chunks are coded
     independently, so tiling changes neither the ratio nor the per-chunk work."""
     from slimfastq_b200 import synth
 
-    block = synth.illumina(UNIQUE_READS, seed=synth.SEED0 + 1 + 1000 * rank)
+    block = synth.illumina(UNIQUE_READS, seed=synth.SEED0 + 1 + 1000 * rank, bins8=bins8)
     tiles = max(1, round(nbytes / len(block)))
     return block, tiles
 
@@ -214,7 +215,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    block, tiles = make_workload(nbytes, rank)
+    block, tiles = make_workload(nbytes, rank, args.bins8)
     n = len(block) * tiles
     d_block = torch.frombuffer(bytearray(block), dtype=torch.uint8).cuda()
     d_text = d_block.repeat(tiles)
@@ -376,7 +377,7 @@ def main():
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": args.warmup,
             "ms_per_step": round(dev_ms_max / K_, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic (Markov-quality Illumina block of %d MB, tiled x%d; chunks are coded independently)" % (len(block) // 10**6, tiles),
-            "config": {"workload": "illumina_2x150_phred40_%.1fGB_per_gpu" % (n / 1e9), "level": args.level, "chunk_bytes": args.chunk,
+            "config": {"workload": "illumina_2x150_%s_%.1fGB_per_gpu" % ("8bin" if args.bins8 else "phred40", n / 1e9), "level": args.level, "chunk_bytes": args.chunk,
                        "bytes_per_gpu": n, "l2": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" % (n / 1e9),
                        "step": "compress + decompress", "sharding": "chunks by rank, no data-path collective"},
             "compress_GBps": round(tot_bytes * K_ / (t_c_max / 1e3) / 1e9, 4),
