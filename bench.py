@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--level", type=int, default=3)
     ap.add_argument("--chunk", type=int, default=1 << 20)
     ap.add_argument("--bins8", action="store_true", help="Illumina 8-bin quantised qualities (BASELINE configs[2] variant)")
+    ap.add_argument("--workload", default="illumina", choices=["illumina", "ont"],
+                    help="illumina = BASELINE configs[1] (the metric's config); ont = configs[3], long reads 1-50 kb with N runs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-mb", type=int, default=0, help="CPU baseline sample (0 = 32 MiB x cores, <= 1 GiB)")
@@ -173,12 +175,21 @@ def reference_whole_file_ratio(sample: bytes, level: int) -> dict:
 
 
 # ------------------------------------------------------------------------------ workload
-def make_workload(nbytes: int, rank: int, bins8: bool = False):
-    """(unique block bytes, tiles): Markov-quality Illumina block, tiled to `nbytes`.  Chunks are coded
-    independently, so tiling changes neither the ratio nor the per-chunk work."""
+ONT_READS = 6400                # ~129 MB of ONT-style reads (log-normal 1-50 kb), tiled like the Illumina block
+
+
+def workload_block(kind: str, rank: int, bins8: bool = False) -> bytes:
     from slimfastq_b200 import synth
 
-    block = synth.illumina(UNIQUE_READS, seed=synth.SEED0 + 1 + 1000 * rank, bins8=bins8)
+    if kind == "ont":
+        return synth.ont(ONT_READS, seed=synth.SEED0 + 4 + 1000 * rank)
+    return synth.illumina(UNIQUE_READS, seed=synth.SEED0 + 1 + 1000 * rank, bins8=bins8)
+
+
+def make_workload(nbytes: int, rank: int, bins8: bool = False, kind: str = "illumina"):
+    """(unique block bytes, tiles): one synthetic block, tiled to `nbytes`.  Chunks are coded independently,
+    so tiling changes neither the ratio nor the per-chunk work."""
+    block = workload_block(kind, rank, bins8)
     tiles = max(1, round(nbytes / len(block)))
     return block, tiles
 
@@ -215,7 +226,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    block, tiles = make_workload(nbytes, rank, args.bins8)
+    block, tiles = make_workload(nbytes, rank, args.bins8, args.workload)
     n = len(block) * tiles
     d_block = torch.frombuffer(bytearray(block), dtype=torch.uint8).cuda()
     d_text = d_block.repeat(tiles)
@@ -376,9 +387,9 @@ def main():
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": args.warmup,
             "ms_per_step": round(dev_ms_max / K_, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic (Markov-quality Illumina block of %d MB, tiled x%d; chunks are coded independently)" % (len(block) // 10**6, tiles),
-            "config": {"workload": "illumina_2x150_%s_%.1fGB_per_gpu" % ("8bin" if args.bins8 else "phred40", n / 1e9), "level": args.level, "chunk_bytes": args.chunk,
-                       "bytes_per_gpu": n, "l2": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" % (n / 1e9),
+            "dtype": "u32", "data": "synthetic (%s block of %d MB, tiled x%d; chunks are coded independently)" % ("ONT-style long-read" if args.workload == "ont" else "Markov-quality Illumina", len(block) // 10**6, tiles),
+            "config": {"workload": ("ont_1-50kb_%.1fGB_per_gpu" % (n / 1e9)) if args.workload == "ont" else "illumina_2x150_%s_%.1fGB_per_gpu" % ("8bin" if args.bins8 else "phred40", n / 1e9),
+                       "level": args.level, "chunk_bytes": args.chunk, "bytes_per_gpu": n, "l2": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" % (n / 1e9),
                        "step": "compress + decompress", "sharding": "chunks by rank, no data-path collective"},
             "compress_GBps": round(tot_bytes * K_ / (t_c_max / 1e3) / 1e9, 4),
             "decompress_GBps": round(tot_bytes * K_ / (t_d_max / 1e3) / 1e9, 4),
@@ -463,9 +474,7 @@ def cpu_baseline(args, block, codec, cores, K) -> dict:
 
 def run_reference_arm(args, nbytes, cores):
     """--impl reference: the reference's own CPU implementation on all host cores, same metric/config."""
-    from slimfastq_b200 import synth
-
-    block = synth.illumina(UNIQUE_READS, seed=synth.SEED0 + 1)
+    block = workload_block(args.workload, 0, args.bins8)
     sample = cpu_sample(args, block, cores)
     from slimfastq_b200.api import chunk_lengths
 
@@ -481,7 +490,8 @@ def run_reference_arm(args, nbytes, cores):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(tot / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic (same generator and seed as the GPU arm)",
-            "config": {"workload": "illumina_2x150_phred40_%.1fGB_per_gpu" % (nbytes / 1e9), "level": args.level, "chunk_bytes": args.chunk,
+            "config": {"workload": ("ont_1-50kb_%.1fGB_per_gpu" % (nbytes / 1e9)) if args.workload == "ont" else "illumina_2x150_%s_%.1fGB_per_gpu" % ("8bin" if args.bins8 else "phred40", nbytes / 1e9),
+                       "level": args.level, "chunk_bytes": args.chunk,
                        "step": "compress + decompress", "note": "each step codes a bounded sample of the workload"},
             "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": cores, "kind": "reference",
                              "sample": "%d MiB as %d chunk files on tmpfs, level %d, via %s" % (len(sample) >> 20, len(lens), args.level, last["how"])},
