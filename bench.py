@@ -399,7 +399,10 @@ def main():
             "gpu_launches": int(launches_sum),
             "roofline": {"bound": "hbm", "kernel": "k_qlt_decode<%d> (quality decoder: %d lanes per chunk, %d chunks per warp, warp-converged)" % ((4, 4, 8) if sd["resident_chunks"] >= 4096 else (8, 8, 4)),
                          "achieved": round(achieved, 3), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 6),
-                         "traffic": None, "traffic_note": "profiles/: dram bytes per decoded quality from the ncu --set full capture (smaller input; a 10 GB launch cannot be replayed)",
+                         "traffic": None,
+                         "traffic_profiled": {"source": "profiles/r1e_ncu_full_summary.txt (ncu --set full, k_qlt_decode<8>, 247 chunks = 108.3 M qualities per launch)",
+                                              "dram_bytes_per_launch": 8436278000, "algorithmic_bytes_per_launch": 135400000,
+                                              "note": "a 10 GB launch cannot be replayed by ncu; at full residency every model visit misses L2 (256 B read + up to 256 B written back per quality)"},
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": int(qd_bytes / max(1, sd["waves"])),
                          "launch_ms_avg": round(qd_ms / K_ / max(1, sd["waves"]), 3),
