@@ -79,6 +79,14 @@ const char *sfq_version(void);          /* "2.04/6 b200" - user version / intern
 /* Upper bound on resident chunks per coder wave (0 = as many as device memory allows). */
 int sfq_set_max_resident(sfq_ctx *ctx, uint32_t chunks);
 
+/* The chunk grid of a PART of a file (a segment of a pipe, the shard of one GPU).  Chunk c of a whole file
+ * holds the records that start in [c*chunk_bytes, (c+1)*chunk_bytes); "chunks are partitioned by index
+ * across the GPUs" means every part must form those very chunks.  A part must begin with the first record
+ * that starts at or after a grid line k*chunk_bytes; `phase` = (global offset of that record) - k*chunk_bytes.
+ * It applies to the next sfq_compress / sfq_compress_device call on the context only.  The blobs of the parts,
+ * laid out back to back with one index, are then byte-identical to the one-call container. */
+int sfq_set_chunk_phase(sfq_ctx *ctx, uint64_t phase);
+
 /* Pinned host staging buffers (optional, but pageable memory halves the PCIe rate). */
 void *sfq_host_alloc(size_t bytes);
 void  sfq_host_free(void *p);
@@ -130,6 +138,11 @@ int    sfq_import_reference(const uint8_t *ref, size_t n, uint8_t *out, size_t o
  *                                  everything before it is whole records, the tail is carried to the next segment */
 size_t sfq_record_start_at_or_after(const uint8_t *fastq, size_t n, size_t pos);
 size_t sfq_last_record_start(const uint8_t *fastq, size_t n);
+/* Where to cut a buffered part of a stream so that the NEXT part starts on the chunk grid (sfq_set_chunk_phase):
+ * `global_off` = offset in the whole stream of fastq[0] (itself such a start, or 0).  Returns the cut (bytes of
+ * this part; the rest is carried over) and the phase of the part that begins there; 0 if the buffer holds no
+ * grid line followed by a verifiable record start yet (read more, or at end of input code everything). */
+size_t sfq_stream_cut(const uint8_t *fastq, size_t n, uint64_t global_off, uint64_t chunk_bytes, uint64_t *next_phase);
 
 #ifdef __cplusplus
 }

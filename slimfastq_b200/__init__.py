@@ -5,7 +5,7 @@ include/sfq_b200.h; `container` reads the chunked .sfq container; `synth` genera
 inputs.  All coding runs in libsfq_b200.so's sm_100a kernels - there is no CPU path.
 """
 from .api import (Codec, SfqError, decompressed_size, export_reference, import_reference,  # noqa: F401
-                  is_reference_file, merge_containers, split_records)
+                  is_reference_file, merge_containers, split_on_grid, split_records)
 
 __all__ = ["Codec", "SfqError", "decompressed_size", "export_reference", "import_reference", "is_reference_file",
-           "merge_containers", "split_records"]
+           "merge_containers", "split_on_grid", "split_records"]

@@ -44,7 +44,7 @@ EXPORTS = [
     "sfq_decompress_device", "sfq_decompressed_size", "sfq_get_stats",
     "sfq_is_reference_file", "sfq_export_reference_bound", "sfq_export_reference",
     "sfq_import_reference_bound", "sfq_import_reference",
-    "sfq_record_start_at_or_after", "sfq_last_record_start",
+    "sfq_record_start_at_or_after", "sfq_last_record_start", "sfq_set_chunk_phase", "sfq_stream_cut",
 ]
 
 _lib = None
@@ -64,6 +64,7 @@ def load_library():
     L.sfq_last_error.argtypes = [vp]; L.sfq_last_error.restype = C.c_char_p
     L.sfq_version.argtypes = []; L.sfq_version.restype = C.c_char_p
     L.sfq_set_max_resident.argtypes = [vp, C.c_uint32]; L.sfq_set_max_resident.restype = C.c_int
+    L.sfq_set_chunk_phase.argtypes = [vp, C.c_uint64]; L.sfq_set_chunk_phase.restype = C.c_int
     L.sfq_host_alloc.argtypes = [sz]; L.sfq_host_alloc.restype = vp
     L.sfq_host_free.argtypes = [vp]; L.sfq_host_free.restype = None
     L.sfq_compress.argtypes = [vp, vp, sz, C.c_int, C.c_uint64, C.POINTER(u8p), C.POINTER(sz)]; L.sfq_compress.restype = C.c_int
@@ -80,6 +81,7 @@ def load_library():
     L.sfq_import_reference.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]; L.sfq_import_reference.restype = C.c_int
     L.sfq_record_start_at_or_after.argtypes = [vp, sz, sz]; L.sfq_record_start_at_or_after.restype = sz
     L.sfq_last_record_start.argtypes = [vp, sz]; L.sfq_last_record_start.restype = sz
+    L.sfq_stream_cut.argtypes = [vp, sz, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]; L.sfq_stream_cut.restype = sz
     _lib = L
     return L
 
@@ -124,17 +126,20 @@ class Codec:
             raise SfqError(rc, self._L.sfq_last_error(self._h).decode("latin1"))
 
     # ---- host buffers in, host bytes out (the call a user of the reference makes)
-    def compress_view(self, fastq, level: int = 3, chunk_bytes: int = DEFAULT_CHUNK):
-        """Returns (address, nbytes) of the context-owned pinned result, valid until the next call."""
+    def compress_view(self, fastq, level: int = 3, chunk_bytes: int = DEFAULT_CHUNK, phase: int = 0):
+        """Returns (address, nbytes) of the context-owned pinned result, valid until the next call.
+        `phase`: chunk-grid offset when `fastq` is a part of a larger file (see split_on_grid)."""
         addr, n, keep = _host_ptr(fastq)
+        if phase:
+            self._L.sfq_set_chunk_phase(self._h, phase)
         out = C.POINTER(C.c_uint8)()
         on = C.c_size_t()
         self._check(self._L.sfq_compress(self._h, addr, n, level, chunk_bytes, C.byref(out), C.byref(on)))
         del keep
         return C.cast(out, C.c_void_p).value, on.value
 
-    def compress(self, fastq, level: int = 3, chunk_bytes: int = DEFAULT_CHUNK) -> bytes:
-        addr, n = self.compress_view(fastq, level, chunk_bytes)
+    def compress(self, fastq, level: int = 3, chunk_bytes: int = DEFAULT_CHUNK, phase: int = 0) -> bytes:
+        addr, n = self.compress_view(fastq, level, chunk_bytes, phase)
         return C.string_at(addr, n)
 
     def decompress_view(self, sfq):
@@ -238,13 +243,13 @@ def record_start_at_or_after(fastq: bytes, pos: int) -> int:
     return n
 
 
-def chunk_lengths(fastq: bytes, chunk_bytes: int = DEFAULT_CHUNK) -> list[int]:
-    """Byte lengths of the chunks the device planner forms (records starting in [c*B, (c+1)*B),
-    sfq_plan.cuh) - used to hand the CPU reference the very same chunks."""
+def chunk_lengths(fastq: bytes, chunk_bytes: int = DEFAULT_CHUNK, phase: int = 0) -> list[int]:
+    """Byte lengths of the chunks the device planner forms (records starting in [c*B, (c+1)*B) of the
+    grid shifted by `phase`, sfq_plan.cuh) - used to hand the CPU reference the very same chunks."""
     n, cuts = len(fastq), [0]
     c = 1
     while cuts[-1] < n:
-        s = record_start_at_or_after(fastq, c * chunk_bytes) if c * chunk_bytes < n else n
+        s = record_start_at_or_after(fastq, c * chunk_bytes - phase) if c * chunk_bytes - phase < n else n
         c += 1
         if s > cuts[-1]:
             cuts.append(s)
@@ -259,6 +264,26 @@ def split_records(fastq: bytes, parts: int) -> list[tuple[int, int]]:
         cuts.append(max(cuts[-1], record_start_at_or_after(fastq, n * p // parts)))
     cuts.append(n)
     return [(cuts[i], cuts[i + 1]) for i in range(parts)]
+
+
+def split_on_grid(fastq: bytes, parts: int, chunk_bytes: int = DEFAULT_CHUNK) -> list[tuple[int, int, int]]:
+    """Cut FASTQ text into up to `parts` ranges that respect the chunk grid: (start, end, phase) per range,
+    every range beginning with the first record at or after a grid line k*chunk_bytes (phase = start - k*B).
+    Compressing the ranges with their phases and merging gives the one-call container byte for byte -
+    "chunks partitioned by index across the GPUs".  Ranges without records are dropped."""
+    n = len(fastq)
+    nslots = (n + chunk_bytes - 1) // chunk_bytes
+    lines = sorted({min(nslots, round(nslots * p / parts)) for p in range(parts)} | {0})
+    cuts = []
+    for k in lines:
+        g = record_start_at_or_after(fastq, k * chunk_bytes) if k else 0
+        cuts.append((g, g - k * chunk_bytes))
+    out = []
+    for i, (g, ph) in enumerate(cuts):
+        end = cuts[i + 1][0] if i + 1 < len(cuts) else n
+        if end > g:
+            out.append((g, end, ph))
+    return out
 
 
 def merge_containers(parts: list[bytes]) -> bytes:

@@ -67,6 +67,7 @@ struct sfq_ctx {
     std::string err;
     sfq_stats st{};
     uint32_t max_resident = 0;
+    uint64_t chunk_phase = 0;               // sfq_set_chunk_phase: grid offset of the next compress call's input
     uint32_t lanes = 0;                     // chunk-streams per gen/rec coder warp (SFQ_LANES); 0 = by wave size
     int sm_count = 148;
     uint32_t rc_lanes = 8;                  // chunk-streams per warp of the coder-chain kernel (SFQ_RC_LANES)
@@ -235,6 +236,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     cudaStream_t side0 = ctx->serial_roles ? s : ctx->side[0], side1 = ctx->serial_roles ? s : ctx->side[1];
     sfq_stats &st = ctx->st;
     level = level > 4 ? 4 : level < 1 ? 1 : level;                    // range_level, config.cpp:231-236
+    const uint64_t phase_arg = ctx->chunk_phase;                      // consumed by this call whatever its outcome
+    ctx->chunk_phase = 0;
     if (!chunk_bytes) chunk_bytes = 1ull << 20;
     if (chunk_bytes < 4096) chunk_bytes = 4096;
     if (n == 0) return fail(ctx, SFQ_ERR_FASTQ, "no records were found");
@@ -266,9 +269,10 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     CK(cudaEventRecord(ctx->ev[EV_SCAN], s));
 
     // ---- plan: chunk boundaries, then per-chunk framing facts
-    const uint64_t nslots = (n + chunk_bytes - 1) / chunk_bytes;
+    const uint64_t phase = phase_arg;                         // (one call only: sfq_set_chunk_phase)
+    const uint64_t nslots = sfq_slot_count(n, chunk_bytes, phase);
     CK(ctx->rec_begin.ensure((nslots + 1) * 8));
-    k_chunk_bounds<<<(unsigned)((nslots + 1 + 127) / 128), 128, 0, s>>>(d_ls, nrec_total, chunk_bytes, nslots, ctx->rec_begin.as<uint64_t>()); LAUNCHED();
+    k_chunk_bounds<<<(unsigned)((nslots + 1 + 127) / 128), 128, 0, s>>>(d_ls, nrec_total, chunk_bytes, nslots, phase, ctx->rec_begin.as<uint64_t>()); LAUNCHED();
     std::vector<uint64_t> rb(nslots + 1);
     CK(cudaMemcpyAsync(rb.data(), ctx->rec_begin.p, (nslots + 1) * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -796,6 +800,7 @@ void sfq_destroy(sfq_ctx *ctx) {
 
 const char *sfq_last_error(const sfq_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context (is a CUDA device present?)"; }
 int sfq_set_max_resident(sfq_ctx *ctx, uint32_t chunks) { if (!ctx) return SFQ_ERR_ARG; ctx->max_resident = chunks; return 0; }
+int sfq_set_chunk_phase(sfq_ctx *ctx, uint64_t phase) { if (!ctx) return SFQ_ERR_ARG; ctx->chunk_phase = phase; return 0; }
 int sfq_get_stats(const sfq_ctx *ctx, sfq_stats *st) { if (!ctx || !st) return SFQ_ERR_ARG; *st = ctx->st; return 0; }
 
 void *sfq_host_alloc(size_t bytes) { void *p = nullptr; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
@@ -1039,6 +1044,23 @@ size_t sfq_last_record_start(const uint8_t *t, size_t n) {
         while (s < n) { cut = s; s = sfq_record_start_at_or_after(t, n, s + 1); }
         if (cut || from == 0) return cut;
     }
+}
+
+
+size_t sfq_stream_cut(const uint8_t *t, size_t n, uint64_t global_off, uint64_t chunk_bytes, uint64_t *next_phase) {
+    if (!t || !n || !chunk_bytes) return 0;
+    // grid lines m*B with a local position in (0, n), the last one first; tried a few lines back only
+    // (a line without a verifiable record start after it lies in the truncated tail of the buffer)
+    const uint64_t last = (global_off + n - 1) / chunk_bytes;
+    for (uint64_t m = last, tries = 0; m * chunk_bytes > global_off && tries < 64; m--, tries++) {
+        const size_t local = (size_t)(m * chunk_bytes - global_off);
+        const size_t s = sfq_record_start_at_or_after(t, n, local);
+        if (s < n) {
+            if (next_phase) *next_phase = global_off + s - m * chunk_bytes;
+            return s;
+        }
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -137,10 +137,8 @@ static void statistics_dump(const uint8_t *p, size_t n) {      // config.cpp:76-
 
 
 // ---- bounded-memory streaming (usrs.cpp:96-122 pages its input through a 1 MiB buffer; here the unit is
-// a segment of many chunks: each one is a container of its own, their blobs are appended to the output as
-// they are produced and one index is written at the end).
-static size_t last_record_start(const uint8_t *t, size_t n) { return sfq_last_record_start(t, n); }
-
+// a part of many chunks cut on the chunk grid: each part is coded by one sfq_compress call, its blobs are
+// appended to the output as they are produced and one index is written at the end).
 struct StreamOut {                       // the container being assembled on disk
     FILE *f = nullptr;
     std::vector<uint64_t> index;
@@ -250,6 +248,8 @@ int main(int argc, char **argv) {
             if (fwrite(res, 1, rn, out) != rn || fclose(out)) croak("Error writing output: %s", strerror(errno));
             sfq_host_free(buf);
         } else {                                                           // stream: bounded host memory
+            // Every part begins with the first record at or after a line of the chunk grid and is coded with its
+            // phase (sfq_set_chunk_phase), so the appended blobs are those of the one-shot container.
             size_t cap = seg + (64u << 20), have = 0;
             uint8_t *buf = (uint8_t *)sfq_host_alloc(cap);
             if (!buf) croak("cannot allocate %zu bytes of pinned memory", cap);
@@ -257,37 +257,38 @@ int main(int argc, char **argv) {
             so.begin(out);
             bool eof = false;
             unsigned long long records_done = 0;
+            uint64_t global_off = 0, phase = 0;
+            size_t want = seg;                                             // bytes to have buffered before cutting
             while (!eof || have) {
-                while (!eof && have < seg) {
-                    const size_t got = fread(buf + have, 1, seg - have, in);
+                while (!eof && have < want) {
+                    if (want > cap) {
+                        uint8_t *nb = (uint8_t *)sfq_host_alloc(want + (64u << 20));
+                        if (!nb) croak("cannot allocate %zu bytes of pinned memory", want + (64u << 20));
+                        memcpy(nb, buf, have); sfq_host_free(buf); buf = nb; cap = want + (64u << 20);
+                    }
+                    const size_t got = fread(buf + have, 1, want - have, in);
                     if (got == 0) { if (ferror(in)) croak("read error: %s", strerror(errno)); eof = true; }
                     have += got;
                 }
+                if (have == 0) break;
                 size_t cut = have;
+                uint64_t next_phase = 0;
                 if (!eof) {
-                    cut = last_record_start(buf, have);
-                    if (cut == 0) {                                        // a record longer than the segment: grow and read on
-                        if (have == cap) {
-                            uint8_t *nb = (uint8_t *)sfq_host_alloc(cap * 2);
-                            if (!nb) croak("cannot allocate %zu bytes of pinned memory", cap * 2);
-                            memcpy(nb, buf, have); sfq_host_free(buf); buf = nb; cap *= 2;
-                        }
-                        const size_t got = fread(buf + have, 1, cap - have, in);
-                        if (got == 0) eof = true;
-                        have += got;
-                        continue;
-                    }
+                    const uint64_t grid = !chunk ? 1ull << 20 : chunk < 4096 ? 4096 : chunk;      // as sfq_compress reads it
+                    cut = sfq_stream_cut(buf, have, global_off, grid, &next_phase);
+                    if (cut == 0) { want = have + seg; continue; }         // no grid line with a record after it yet: read on
                 }
-                if (cut == 0) break;
                 const uint8_t *res = nullptr;
                 size_t rn = 0;
-                if (sfq_compress(ctx, buf, cut, level, chunk, &res, &rn)) { unlink(fil.c_str()); croak("%s (in the segment after record %llu)", sfq_last_error(ctx), records_done); }
+                sfq_set_chunk_phase(ctx, phase);
+                if (sfq_compress(ctx, buf, cut, level, chunk, &res, &rn)) { unlink(fil.c_str()); croak("%s (in the part after record %llu)", sfq_last_error(ctx), records_done); }
                 sfq_stats st;
                 sfq_get_stats(ctx, &st);
                 records_done += st.nrecords;
                 so.add(res, rn);
                 memmove(buf, buf + cut, have - cut);
                 have -= cut;
+                global_off += cut; phase = next_phase; want = seg;
             }
             if (so.index.empty()) { unlink(fil.c_str()); croak("no records were found"); }
             so.end();

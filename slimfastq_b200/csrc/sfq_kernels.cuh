@@ -117,12 +117,12 @@ k_fill_lines(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__res
     }
 }
 
-// rec_begin[c] = first record starting at or after c * chunk_bytes (c in [0, nslots]).
+// rec_begin[c] = first record starting at or after grid slot c (c in [0, nslots]); see sfq_slot_target.
 __global__ void k_chunk_bounds(const uint64_t *__restrict__ ls, uint64_t nrec_total, uint64_t chunk_bytes,
-                               uint64_t nslots, uint64_t *__restrict__ rec_begin) {
+                               uint64_t nslots, uint64_t phase, uint64_t *__restrict__ rec_begin) {
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c > nslots) return;
-    rec_begin[c] = c == nslots ? nrec_total : sfq_first_record_at(ls, nrec_total, c * chunk_bytes);
+    rec_begin[c] = c == nslots ? nrec_total : sfq_first_record_at(ls, nrec_total, sfq_slot_target(c, chunk_bytes, phase));
 }
 __global__ void k_chunk_plan(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls,
                              const uint64_t *__restrict__ r0, const uint64_t *__restrict__ r1,

@@ -14,6 +14,17 @@ SFQ_HD uint64_t sfq_first_record_at(const uint64_t *ls, uint64_t nrec_total, uin
     return lo;
 }
 
+// The chunk grid.  Chunk c of a whole file holds the records that START in [c*B, (c+1)*B).  When only a
+// part of the file is given to a call (a segment of a pipe, the shard of one GPU), `phase` = how far the
+// part's first byte lies past the grid line it belongs to, so that its chunks are the very chunks the
+// whole-file call would form: slot c of the part starts at local offset max(0, c*B - phase).
+// (The part must begin with the first record at or after a grid line, see sfq_b200.h.)
+SFQ_HD uint64_t sfq_slot_target(uint64_t c, uint64_t chunk_bytes, uint64_t phase) {
+    const uint64_t t = c * chunk_bytes;
+    return t > phase ? t - phase : 0;
+}
+SFQ_HD uint64_t sfq_slot_count(uint64_t n, uint64_t chunk_bytes, uint64_t phase) { return (n + phase + chunk_bytes - 1) / chunk_bytes; }
+
 // Fills `m` for the chunk made of records [r0, r1).  nrec == 0 chunks are left empty (text_len 0).
 // `rec_qoff` (may be null): rec_qoff[r - r0] = index of record r's first coded quality within the chunk.
 SFQ_HDN void sfq_plan_chunk(const uint8_t *text, const uint64_t *ls, uint64_t r0, uint64_t r1, SfqChunkMeta *m, uint32_t *rec_qoff = nullptr) {

@@ -24,6 +24,7 @@ def lib():
                                           C.POINTER(C.c_uint32)]
         L.sfq_emul_free.argtypes = [C.c_void_p]
         L.sfq_emul_set_two_phase.argtypes = [C.c_int]
+        L.sfq_emul_set_chunk_phase.argtypes = [C.c_uint64]
         _lib = L
     return _lib
 
@@ -32,9 +33,10 @@ class EmulError(RuntimeError):
     pass
 
 
-def compress(data: bytes, level: int, chunk_bytes: int = 1 << 20, two_phase: bool = False) -> bytes:
+def compress(data: bytes, level: int, chunk_bytes: int = 1 << 20, two_phase: bool = False, phase: int = 0) -> bytes:
     out, n, st = C.POINTER(C.c_uint8)(), C.c_size_t(), C.c_uint32()
     lib().sfq_emul_set_two_phase(1 if two_phase else 0)
+    lib().sfq_emul_set_chunk_phase(phase)
     if lib().sfq_emul_compress(data, len(data), level, chunk_bytes, C.byref(out), C.byref(n), C.byref(st)):
         raise EmulError(f"status {st.value}")
     r = C.string_at(out, n.value)

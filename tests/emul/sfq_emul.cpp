@@ -88,8 +88,13 @@ static void emul_qlt_two_phase(const uint8_t *text, const uint64_t *ls, SfqChunk
     if (ovf && m->status == SFQ_OK) m->status = SFQ_E_CAP;
 }
 
+static uint64_t g_phase = 0;
+extern "C" void sfq_emul_set_chunk_phase(uint64_t phase) { g_phase = phase; }
+
 extern "C" int sfq_emul_compress(const uint8_t *text_in, size_t n, int level, uint64_t chunk_bytes,
                                  uint8_t **out, size_t *out_n, uint32_t *status_out) {
+    const uint64_t phase = g_phase;
+    g_phase = 0;
     const std::vector<uint8_t> text_copy = padded(text_in, n);
     const uint8_t *text = text_copy.data();
     level = level > 4 ? 4 : level < 1 ? 1 : level;
@@ -99,13 +104,13 @@ extern "C" int sfq_emul_compress(const uint8_t *text_in, size_t n, int level, ui
     for (size_t i = 0; i < n; i++) if (text[i] == '\n') ls.push_back(i + 1);
     if (n == 0 || text[n - 1] != '\n' || (ls.size() - 1) % 4) { *status_out = SFQ_E_TRUNC; return 1; }
     const uint64_t nrec = (ls.size() - 1) / 4;
-    const uint64_t nslots = (n + chunk_bytes - 1) / chunk_bytes;
+    const uint64_t nslots = sfq_slot_count(n, chunk_bytes, phase);
     std::vector<uint8_t> file(sizeof(SfqFileHeader));
     std::vector<uint64_t> index;
     uint64_t out_total = 0;
     for (uint64_t c = 0; c < nslots; c++) {
-        uint64_t r0 = sfq_first_record_at(ls.data(), nrec, c * chunk_bytes);
-        uint64_t r1 = c + 1 == nslots ? nrec : sfq_first_record_at(ls.data(), nrec, (c + 1) * chunk_bytes);
+        uint64_t r0 = sfq_first_record_at(ls.data(), nrec, sfq_slot_target(c, chunk_bytes, phase));
+        uint64_t r1 = c + 1 == nslots ? nrec : sfq_first_record_at(ls.data(), nrec, sfq_slot_target(c + 1, chunk_bytes, phase));
         if (r0 == r1) continue;
         SfqChunkMeta m;
         sfq_plan_chunk(text, ls.data(), r0, r1, &m);

@@ -82,6 +82,8 @@ def test_cli_streams_in_bounded_segments(tmp_path):
     assert r.returncode == 0, r.stderr
     ct = K.parse(sfq.read_bytes())
     assert ct.orig_size == len(data) and sum(c.text_len for c in ct.chunks) == len(data) and len(ct.chunks) > 8
+    assert run("-m", "0", "-c", "262144", "-u", str(fq), "-f", str(tmp_path / "oneshot.sfq")).returncode == 0
+    assert sfq.read_bytes() == (tmp_path / "oneshot.sfq").read_bytes()              # parts on the chunk grid: same container
     r = run("-m", "1", "-d", "-f", str(sfq))                                         # grouped decode to stdout
     assert r.returncode == 0 and r.stdout == data
     assert run("-m", "0", str(sfq), str(back)).returncode == 0 and back.read_bytes() == data   # ... equals one-shot decode

@@ -49,3 +49,56 @@ def test_two_phase_encoder_algorithm(oracle):
     for data, level in cases:
         blob = emul.compress(data, level, 1 << 19, two_phase=True)
         check_container_against_oracle(oracle, data, blob, level)
+
+
+def test_parts_on_the_chunk_grid_give_the_one_call_container():
+    """sfq_slot_target / sfq_set_chunk_phase: parts that begin at the first record after a grid line, coded
+    with their phase and merged, are the whole-file container byte for byte (the rule the N-GPU sharding
+    and the streaming CLI rely on).  Run through the CPU emulation of the planner and coders."""
+    import emul
+    from slimfastq_b200 import api, synth
+
+    data = synth.illumina(5200) + synth.ont(25) + synth.illumina(1500, seed=9)
+    for chunk in (1 << 17, 300_000):
+        whole = emul.compress(data, 3, chunk)
+        for nparts in (2, 3, 7):
+            ranges = api.split_on_grid(data, nparts, chunk)
+            assert ranges[0][0] == 0 and ranges[-1][1] == len(data)
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            parts = [emul.compress(data[s:e], 3, chunk, phase=ph) for s, e, ph in ranges]
+            assert api.merge_containers(parts) == whole, (chunk, nparts)
+        lens = [ln for s, e, ph in api.split_on_grid(data, 3, chunk) for ln in api.chunk_lengths(data[s:e], chunk, ph)]
+        assert lens == api.chunk_lengths(data, chunk)
+
+
+def test_stream_cuts_keep_the_chunk_grid():
+    """The streaming CLI's loop (read a segment, sfq_stream_cut, code the part with its phase, carry the tail)
+    replayed here with the CPU emulation as the coder: whatever the segment size, the appended blobs are the
+    one-shot container."""
+    import ctypes as C
+
+    import emul
+    from slimfastq_b200 import api, synth
+
+    L = api.load_library()
+    data = synth.illumina(4000) + synth.ont(20) + synth.illumina(2500, seed=3)
+    chunk = 1 << 17
+    whole = emul.compress(data, 3, chunk)
+    for seg in (400_000, 1_000_003, len(data) + 5):
+        parts, pos, carry, goff, phase = [], 0, b"", 0, 0
+        while pos < len(data) or carry:
+            take = max(0, seg - len(carry))
+            buf = carry + data[pos:pos + take]
+            pos += take
+            eof = pos >= len(data)
+            cut, nph = len(buf), C.c_uint64(0)
+            if not eof:
+                cut = L.sfq_stream_cut(C.cast(C.c_char_p(buf), C.c_void_p), len(buf), goff, chunk, C.byref(nph))
+                if cut == 0:                      # no grid line with a record after it yet: read on
+                    seg_more = data[pos:pos + seg]
+                    carry, pos = buf + seg_more, pos + len(seg_more)
+                    continue
+            parts.append(emul.compress(buf[:cut], 3, chunk, phase=phase))
+            carry, goff, phase = buf[cut:], goff + cut, nph.value
+        assert api.merge_containers(parts) == whole, seg
+        assert len(parts) > 1 or seg > len(data)
