@@ -1,6 +1,7 @@
-"""CPU, world_size 2 over gloo: the N>1 host path - shard by record range, code shards
+"""CPU, world_size 2 over gloo: the N>1 host path - shard on the chunk grid, code shards
 independently (here with the CPU emulation of the kernels, there is no GPU), exchange only the
-compressed sizes, lay the container out from their prefix sum."""
+compressed sizes, lay the container out from their prefix sum.  The merged container must be the
+single-process container byte for byte ("chunks partitioned by index across the GPUs")."""
 import os
 import sys
 
@@ -19,8 +20,8 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     data = synth.illumina(3000)
-    a, b = api.split_records(data, world)[rank]
-    blob = emul.compress(data[a:b], 3, 1 << 18)
+    a, b, phase = api.split_on_grid(data, world, 1 << 18)[rank]
+    blob = emul.compress(data[a:b], 3, 1 << 18, phase=phase)
     sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([len(blob)], dtype=torch.int64))       # the only exchange
     offsets = [0]
@@ -30,7 +31,7 @@ def _worker(rank, world, port, q):
     dist.all_gather_object(gathered, blob)
     if rank == 0:
         merged = api.merge_containers(gathered)
-        q.put((offsets, emul.decompress(merged) == data, len(merged)))
+        q.put((offsets, emul.decompress(merged) == data and merged == emul.compress(data, 3, 1 << 18), len(merged)))
     dist.barrier()
     dist.destroy_process_group()
 
