@@ -55,26 +55,27 @@ def is_container(blob: bytes) -> bool:
     return len(blob) >= FILE_HDR.size and blob[:16] == STAMP and blob[16:32] == KIND
 
 
+def parse_blob(blob: bytes, off: int = 0) -> Chunk:
+    """One chunk blob (header, rec.first, streams) starting at `off`."""
+    f = BLOB_HDR.unpack_from(blob, off)
+    if f[0] != BLOB_MAGIC:
+        raise ValueError("bad chunk magic")
+    (_, lvl, text_len, out_len, nrec, nb, nq, hb, llen, solid, two_id, n_byte, _pad, extra_hi, rfl, _qu, _gu) = f[:17]
+    ssize = f[17:]
+    p = off + BLOB_HDR.size
+    rec_first = blob[p:p + rfl]
+    p += rfl
+    streams = {}
+    for nm, sz in zip(STREAM_NAMES, ssize):
+        if sz:
+            streams[nm] = blob[p:p + sz]
+        p += sz
+    return Chunk(lvl, text_len, out_len, nrec, nb, nq, hb, llen, solid, two_id, n_byte, extra_hi, rec_first, streams, p - off)
+
+
 def parse(blob: bytes) -> Container:
     if not is_container(blob):
         raise ValueError("not a b200 chunked .sfq container")
     _, _, version, level, orig, nchunks, chunk_bytes, index_off, out_size = FILE_HDR.unpack_from(blob, 0)
     offs = struct.unpack_from(f"<{nchunks}Q", blob, index_off)
-    chunks = []
-    for off in offs:
-        f = BLOB_HDR.unpack_from(blob, off)
-        if f[0] != BLOB_MAGIC:
-            raise ValueError("bad chunk magic")
-        (_, lvl, text_len, out_len, nrec, nb, nq, hb, llen, solid, two_id, n_byte, _pad, extra_hi, rfl, _qu, _gu) = f[:17]
-        ssize = f[17:]
-        p = off + BLOB_HDR.size
-        rec_first = blob[p:p + rfl]
-        p += rfl
-        streams = {}
-        for nm, sz in zip(STREAM_NAMES, ssize):
-            if sz:
-                streams[nm] = blob[p:p + sz]
-            p += sz
-        chunks.append(Chunk(lvl, text_len, out_len, nrec, nb, nq, hb, llen, solid, two_id, n_byte,
-                            extra_hi, rec_first, streams, p - off))
-    return Container(level, orig, chunk_bytes, chunks, out_size)
+    return Container(level, orig, chunk_bytes, [parse_blob(blob, off) for off in offs], out_size)
