@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, "libsfq_oracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "slimfastq")
 REF_SAMPLES = os.path.join(HERE, "_ref", "samples")
 
-STREAM_NAMES = ["rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq"]
+STREAM_NAMES = ["rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq",
+                "usr.lrec", "usr.lgen", "usr.lqlt"]
 NSTREAMS = len(STREAM_NAMES)
 
 

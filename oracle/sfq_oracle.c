@@ -518,8 +518,10 @@ static size_t h_load(hmodel *h, rc_dec *rc, xload *x_rec, uint64_t recno, uint8_
 
 /* ------------------------------------------------------------------ record framing + drivers */
 static const char *const k_names[SFQ_OR_NSTREAMS] = {
-    "rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq"
+    "rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq",
+    "usr.lrec", "usr.lgen", "usr.lqlt"
 };
+#define NXS 10      /* exception-list streams: gen.Ns gen.Nn rec.x usr.x usr.x.q usr.pfg usr.pfq usr.lrec usr.lgen usr.lqlt */
 const char *sfq_oracle_stream_name(int id) { return id >= 0 && id < SFQ_OR_NSTREAMS ? k_names[id] : ""; }
 
 #define MAX_ID_LLEN 0x2000
@@ -547,28 +549,53 @@ int sfq_oracle_encode(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out
 
     qmodel Q; gmodel G; hmodel H;
     rc_enc rc_rec, rc_gen, rc_qlt;
-    xsave *xs = (xsave *)calloc(7, sizeof(xsave));    /* gen.Ns gen.Nn rec.x usr.x usr.x.q usr.pfg usr.pfq */
+    xsave *xs = (xsave *)calloc(NXS, sizeof(xsave));
     memset(&rc_rec, 0, sizeof rc_rec); memset(&rc_gen, 0, sizeof rc_gen); memset(&rc_qlt, 0, sizeof rc_qlt);
     int okq = q_init(&Q, level), okg = g_init(&G, level), okh = h_init(&H);
     if (!xs || !okq || !okg || !okh) { fail(&e, "out of memory"); goto done; }
     enc_init(&rc_rec); enc_init(&rc_gen); enc_init(&rc_qlt);
     xsave *x_ns = &xs[0], *x_nn = &xs[1], *x_rec = &xs[2], *x_llen = &xs[3], *x_qlen = &xs[4],
-          *x_sgen = &xs[5], *x_sqlt = &xs[6];
+          *x_sgen = &xs[5], *x_sqlt = &xs[6], *x_lrec = &xs[7], *x_lgen = &xs[8], *x_lqlt = &xs[9];
+    uint64_t recno = 0, i_long = 0;
+    size_t cur = 0;
 
-    /* ---- determine_record, usrs.cpp:186-267 */
+    /* get_oversized_record, usrs.cpp:269-301: the record starting at `at` goes, line by line and newline included,
+     * to usr.lrec (id line without its '@', and the '+' line), usr.lgen and usr.lqlt */
+#define OVERSIZED(at)                                                                                   \
+    do {                                                                                                \
+        xs_put(x_lrec, recno - i_long); i_long = recno;                                                 \
+        size_t c_ = (at);                                                                               \
+        if (buf[c_++] != '@') { fail(&e, "record %llu: bad (long) record", (unsigned long long)recno); break; } \
+        xsave *dst_[4] = { x_lrec, x_lgen, x_lrec, x_lqlt };                                            \
+        for (int l_ = 0; l_ < 4 && !e.failed; l_++) {                                                   \
+            for (;;) {                                                                                  \
+                if (c_ >= n) { fail(&e, "record %llu: seems truncated", (unsigned long long)recno); break; } \
+                const uint8_t ch_ = buf[c_++];                                                          \
+                xs_put_chr(dst_[l_], ch_);                                                              \
+                if (ch_ == '\n') break;                                                                 \
+            }                                                                                           \
+        }                                                                                               \
+        cur = c_;                                                                                       \
+    } while (0)
+
+    /* ---- determine_record, usrs.cpp:186-267 (oversized leading records are put away first) */
     int m_llen = 0, m_solid = 0;
     if (n == 0) { fail(&e, "no records were found"); goto done; }
-    {
-        if (buf[0] != '@') { fail(&e, "first record: Missing prefix '@', is it really a fastq format?"); goto done; }
-        long long q = scan_line(buf, n, 1, MAX_ID_LLEN);
-        if (q == -2) { fail(&e, "oversized record (id line): not supported by the oracle"); goto done; }
+    for (;;) {
+        if (cur >= n) break;                           /* "all records were oversized": no llen / usr.* keys */
+        if (buf[cur] != '@') { fail(&e, "first record: Missing prefix '@', is it really a fastq format?"); goto done; }
+        long long q = scan_line(buf, n, cur + 1, MAX_ID_LLEN);
+        if (q == -2) { recno++; OVERSIZED(cur); if (e.failed) goto done; continue; }
         if (q < 0) { fail(&e, "fastq file: record seems truncated  after record 0"); goto done; }
         size_t qg = (size_t)q + 1;
         for (int i = 1; i < MAX_GN_LLEN && !m_llen; i++) {
             if (qg + (size_t)i >= n) break;
             if (buf[qg + (size_t)i] == '\n') m_llen = i;
         }
-        if (!m_llen) { fail(&e, "oversized or truncated first record: not supported by the oracle"); goto done; }
+        if (!m_llen) {
+            if (qg + MAX_GN_LLEN > n) { fail(&e, "oversized or truncated first record"); goto done; }
+            recno++; OVERSIZED(cur); if (e.failed) goto done; continue;
+        }
         size_t p = qg + (size_t)m_llen + 1;
         if (p >= n || buf[p] != '+') { fail(&e, "first record: Missing 2nd prefix '+', is it really a fastq format?"); goto done; }
         int has2 = 0;
@@ -588,20 +615,21 @@ int sfq_oracle_encode(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out
         out->solid = m_solid;
         out->llen = m_llen;
         out->two_id = has2;
+        break;
     }
 
     /* ---- encode loop, usrs.cpp:392-407 with get_record :303-390 */
-    uint64_t recno = 0, i_llen = 0, i_qlen = 0, i_sgen = 0, i_sqlt = 0;
+    uint64_t i_llen = 0, i_qlen = 0, i_sgen = 0, i_sqlt = 0;
     uint8_t pf_gen = 0, pf_qlt = 0;
     const uint8_t *rec = NULL, *prev_rec = NULL;
-    size_t cur = 0;
     for (;;) {
         ++recno;
-        if (cur >= n) break;
+    next_record:
+        if (e.failed || cur >= n) break;
         size_t currec = cur;
         if (buf[cur++] != '@') { fail(&e, "fastq file: expecting '@', got '%c' after record %llu", buf[cur - 1], (unsigned long long)recno); break; }
         long long nl = scan_line(buf, n, cur, MAX_ID_LLEN);
-        if (nl == -2) { fail(&e, "oversized record (id line): not supported by the oracle"); break; }
+        if (nl == -2) { OVERSIZED(currec); recno++; goto next_record; }
         if (nl < 0) { fail(&e, "fastq file: record seems truncated  after record %llu", (unsigned long long)recno); break; }
         const uint8_t *rec_end = buf + nl;
         cur = (size_t)nl + 1;
@@ -613,7 +641,7 @@ int sfq_oracle_encode(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out
         }
         size_t gi = cur;
         nl = scan_line(buf, n, cur, MAX_GN_LLEN);
-        if (nl == -2) { fail(&e, "oversized record (base line): not supported by the oracle"); break; }
+        if (nl == -2) { OVERSIZED(currec); recno++; goto next_record; }
         if (nl < 0) { fail(&e, "fastq file: record seems truncated  after record %llu", (unsigned long long)recno); break; }
         cur = (size_t)nl;
         if (upd_pf) {                                                                  /* update(ET_SOLPF_GEN) :140-145 */
@@ -639,7 +667,7 @@ int sfq_oracle_encode(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out
         }
         size_t qi = cur;
         nl = scan_line(buf, n, cur, MAX_GN_LLEN);
-        if (nl == -2) { fail(&e, "oversized record (quality line): not supported by the oracle"); break; }
+        if (nl == -2) { OVERSIZED(currec); recno++; goto next_record; }      /* (the updates above have happened, as in the reference) */
         if (nl < 0) { fail(&e, "fastq file: record seems truncated  after record %llu", (unsigned long long)recno); break; }
         int m_qlen = (int)((size_t)nl - qi);
         if (m_qlen != m_llen) {                                                        /* update(ET_QLEN) :133-138 */
@@ -660,17 +688,18 @@ int sfq_oracle_encode(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out
     out->n_byte = (G.n_byte && G.n_byte != 'N') ? G.n_byte : 0;
     out->extra_hi_qlt = Q.extra_hi;
     enc_done(&rc_rec); enc_done(&rc_gen); enc_done(&rc_qlt);
-    for (int k = 0; k < 7; k++) xs_close(&xs[k]);
+    for (int k = 0; k < NXS; k++) xs_close(&xs[k]);
     out->data[SFQ_OR_REC] = rc_rec.out.p; out->size[SFQ_OR_REC] = rc_rec.out.n; rc_rec.out.p = NULL;
     out->data[SFQ_OR_GEN] = rc_gen.out.p; out->size[SFQ_OR_GEN] = rc_gen.out.n; rc_gen.out.p = NULL;
     out->data[SFQ_OR_QLT] = rc_qlt.out.p; out->size[SFQ_OR_QLT] = rc_qlt.out.n; rc_qlt.out.p = NULL;
-    for (int k = 0; k < 7; k++) {
-        out->data[SFQ_OR_GEN_NS + k] = xs[k].rc.out.p; out->size[SFQ_OR_GEN_NS + k] = xs[k].rc.out.n;
-        xs[k].rc.out.p = NULL;
+    {
+        static const int sid[NXS] = { SFQ_OR_GEN_NS, SFQ_OR_GEN_NN, SFQ_OR_REC_X, SFQ_OR_USR_X, SFQ_OR_USR_XQ, SFQ_OR_USR_PFG, SFQ_OR_USR_PFQ,
+                                      SFQ_OR_USR_LREC, SFQ_OR_USR_LGEN, SFQ_OR_USR_LQLT };
+        for (int k = 0; k < NXS; k++) { out->data[sid[k]] = xs[k].rc.out.p; out->size[sid[k]] = xs[k].rc.out.n; xs[k].rc.out.p = NULL; }
     }
 done:
     free(rc_rec.out.p); free(rc_gen.out.p); free(rc_qlt.out.p);
-    if (xs) for (int k = 0; k < 7; k++) free(xs[k].rc.out.p);
+    if (xs) for (int k = 0; k < NXS; k++) free(xs[k].rc.out.p);
     free(xs); free(Q.ranger); free(G.ranger); free(H.ranger);
     if (e.failed) sfq_oracle_free_chunk(out);
     return e.failed;
@@ -683,7 +712,7 @@ int sfq_oracle_decode(const sfq_or_chunk *in, uint8_t **outp, size_t *out_n, cha
     int level = in->level > 4 ? 4 : in->level < 1 ? 1 : in->level;
     qmodel Q; gmodel G; hmodel H;
     obuf o = { 0, 0, 0 };
-    xload *xl = (xload *)calloc(7, sizeof(xload));
+    xload *xl = (xload *)calloc(NXS, sizeof(xload));
     uint8_t *m_rec = (uint8_t *)malloc(2 * (MAX_ID_LLEN + 1)), *m_gen = (uint8_t *)malloc(MAX_GN_LLEN + 4),
             *m_qlt = (uint8_t *)malloc(MAX_GN_LLEN + 2);
     int okq = q_init(&Q, level), okg = g_init(&G, level), okh = h_init(&H);
@@ -692,9 +721,9 @@ int sfq_oracle_decode(const sfq_or_chunk *in, uint8_t **outp, size_t *out_n, cha
     dec_init(&rc_rec, in->data[SFQ_OR_REC], in->size[SFQ_OR_REC]);
     dec_init(&rc_gen, in->data[SFQ_OR_GEN], in->size[SFQ_OR_GEN]);
     dec_init(&rc_qlt, in->data[SFQ_OR_QLT], in->size[SFQ_OR_QLT]);
-    for (int k = 0; k < 7; k++) xl_open(&xl[k], in->data[SFQ_OR_GEN_NS + k], in->size[SFQ_OR_GEN_NS + k]);
+    for (int k = 0; k < NXS; k++) xl_open(&xl[k], in->data[SFQ_OR_GEN_NS + k], in->size[SFQ_OR_GEN_NS + k]);
     xload *x_ns = &xl[0], *x_nn = &xl[1], *x_rec = &xl[2], *x_llen = &xl[3], *x_qlen = &xl[4],
-          *x_sgen = &xl[5], *x_sqlt = &xl[6];
+          *x_sgen = &xl[5], *x_sqlt = &xl[6], *x_lrec = &xl[7], *x_lgen = &xl[8], *x_lqlt = &xl[9];
 
     /* UsrLoad ctor, usrs.cpp:411-456; GenLoad ctor gens.cpp:164-190; RecLoad ctor recs.cpp:93-106 */
     size_t m_llen = (size_t)in->llen, m_qlen = m_llen;
@@ -709,10 +738,26 @@ int sfq_oracle_decode(const sfq_or_chunk *in, uint8_t **outp, size_t *out_n, cha
     int flip = 0;
     uint8_t pf_gen = 0, pf_qlt = 0;
     uint64_t recno = 0;
-    if (!in->num_records) { fail(&e, "Zero records, what's going on?"); goto done; }
+    uint64_t i_long = xl_get(x_lrec);                                                    /* usrs.cpp:444-452 */
+    if (!in->num_records && !i_long) { fail(&e, "Zero records, what's going on?"); goto done; }
     for (;;) {
         recno++;
         /* update(), usrs.cpp:471-510 */
+        while (i_long == recno) {                                                        /* an oversized record, verbatim */
+            xload *src[4] = { x_lrec, x_lgen, x_lrec, x_lqlt };
+            ob_put(&o, '@');
+            for (int l = 0; l < 4; l++) {
+                if (!src[l]->valid) { fail(&e, "oversized-record stream missing"); goto done; }
+                for (uint64_t guard = 0;; guard++) {
+                    const uint8_t c = xl_get_chr(src[l]);
+                    ob_put(&o, c);
+                    if (c == '\n') break;
+                    if (guard > ((uint64_t)1 << 32)) { fail(&e, "corrupt oversized-record stream"); goto done; }
+                }
+            }
+            i_long += xl_get(x_lrec);
+            recno++;
+        }
         if (i_llen == recno) { m_llen = (size_t)xl_get(x_llen); m_qlen = m_llen; i_llen += xl_get(x_llen); }
         if (i_qlen == recno) { m_qlen = (size_t)xl_get(x_qlen); i_qlen += xl_get(x_qlen); }
         else if (m_qlen != m_llen) m_qlen = m_llen;

@@ -26,7 +26,9 @@ extern "C" {
  * gens.cpp:68-69; recs.cpp:46). */
 enum {
     SFQ_OR_REC = 0, SFQ_OR_GEN, SFQ_OR_QLT, SFQ_OR_GEN_NS, SFQ_OR_GEN_NN, SFQ_OR_REC_X,
-    SFQ_OR_USR_X, SFQ_OR_USR_XQ, SFQ_OR_USR_PFG, SFQ_OR_USR_PFQ, SFQ_OR_NSTREAMS
+    SFQ_OR_USR_X, SFQ_OR_USR_XQ, SFQ_OR_USR_PFG, SFQ_OR_USR_PFQ,
+    SFQ_OR_USR_LREC, SFQ_OR_USR_LGEN, SFQ_OR_USR_LQLT,      /* oversized records, usrs.cpp:269-301 */
+    SFQ_OR_NSTREAMS
 };
 
 typedef struct sfq_or_chunk {
@@ -50,7 +52,7 @@ const char *sfq_oracle_stream_name(int id);
 
 /* Encode one FASTQ buffer exactly as `slimfastq -u buf -f out -l level -q` would
  * (UsrSave::encode, usrs.cpp:392-407).  Returns 0, or non-zero with a croak-style message in
- * err[256].  Oversized records (usrs.hpp:34-36) are reported as an error, not coded. */
+ * err[256].  Oversized records (usrs.hpp:34-36: id of 8 KiB or line of 64 KiB) go to usr.lrec / usr.lgen / usr.lqlt. */
 int sfq_oracle_encode(const uint8_t *fastq, size_t n, int level, sfq_or_chunk *out, char *err);
 
 /* Decode (UsrLoad::decode, usrs.cpp:539-574).  *out is malloc'ed. */

@@ -9,10 +9,11 @@ import struct
 from dataclasses import dataclass, field
 
 STAMP = b"whoami=slimfastq"
-KIND = b"\nformat=b200.c1\n"
-STREAM_NAMES = ["rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq"]
+KIND = b"\nformat=b200.c2\n"
+STREAM_NAMES = ["rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq",
+                "usr.lrec", "usr.lgen", "usr.lqlt"]
 FILE_HDR = struct.Struct("<16s16sIIQQQQQ")
-BLOB_HDR = struct.Struct("<IIQQIIIIiBBBBIIII10I")
+BLOB_HDR = struct.Struct("<IIQQIIIIiBBBBIIIIIIII13I")
 BLOB_MAGIC = 0x43514653
 
 
@@ -60,8 +61,9 @@ def parse_blob(blob: bytes, off: int = 0) -> Chunk:
     f = BLOB_HDR.unpack_from(blob, off)
     if f[0] != BLOB_MAGIC:
         raise ValueError("bad chunk magic")
-    (_, lvl, text_len, out_len, nrec, nb, nq, hb, llen, solid, two_id, n_byte, _pad, extra_hi, rfl, _qu, _gu) = f[:17]
-    ssize = f[17:]
+    (_, lvl, text_len, out_len, nrec, nb, nq, hb, llen, solid, two_id, n_byte, _pad, extra_hi, rfl, _qu, _gu,
+     _nbig, _bb, _bq, _bh) = f[:21]
+    ssize = f[21:]
     p = off + BLOB_HDR.size
     rec_first = blob[p:p + rfl]
     p += rfl

@@ -82,7 +82,8 @@ struct sfq_ctx {
     DevBuf text, out, tiles, tile_prefix, lines, scalars, rec_begin, r0, r1, metas, arenas, arena_buf,
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
-           e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff;
+           e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff,
+           e2_gbins, e2_gcnt;
     int spread = -1;                        // SFQ_SPREAD=0..3 (default: 3 for large waves, else 0; see decompress_on_device)
     unsigned spread_smem[3] = {0, 0, 0};    // dynamic shared memory reserved per CTA: base, quality, header decoder
     uint32_t dec_warps = 4;                 // SFQ_DEC_WARPS=1..4: warps per CTA of the thread-per-chunk decoders (one-warp CTAs each
@@ -95,6 +96,8 @@ struct sfq_ctx {
     int gdec32 = 0;                         // SFQ_GDEC=1: warp-converged base decoder (A/B; slower)
     uint32_t qlpc = 0;                      // SFQ_QLPC=4|8: lanes per chunk of the quality decoder (0 = by wave size)
     int gm_variant = 0;                     // SFQ_GM_VARIANT: register budget / batch of k_gen_model (A/B runs)
+    bool q_scatter1 = false;                // SFQ_QSCATTER=1: one-pass quality scatter over 65 536 global cursors (the round-1 form)
+    bool gm_table = false;                  // SFQ_GM_TABLE=1: base models in a global hash table (k_gen_model, the round-1 form) instead of partitioned replay
     int gen_ahead2 = -1;                    // SFQ_GEN_AHEAD2=0/1: base decoder's two-ahead line prefetch (default on)
     bool qdec_octets = true;                // SFQ_QDEC=0: the first (sub-warp mask) quality decoder, for A/B runs
     bool serial_roles = false;              // SFQ_SERIAL_ROLES=1: gen, qlt, rec kernels of a wave one after another (diagnosis)
@@ -107,7 +110,7 @@ struct sfq_ctx {
                          &arenas, &arena_buf, &blob_off, &gtab, &qtab, &pw, &dchunks, &bhdrs, &bases, &quals,
                          &hdrs, &rec_chunk, &t_llen, &t_qlen, &t_hlen, &t_pfg, &t_pfq, &t_boff, &t_qoff,
                          &t_hoff, &t_ooff, &e2_gsteps, &e2_qkey, &e2_qb, &e2_sorted, &e2_qsteps, &e2_cnt, &e2_esorted,
-                         &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks, &rec_qoff};
+                         &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks, &rec_qoff, &e2_gbins, &e2_gcnt};
         for (DevBuf *b : all) b->release();
         scratch.release();
         h_out.release(); h_out_d.release(); h_small.release();
@@ -120,7 +123,7 @@ void release_workspace(sfq_ctx *ctx) {
     DevBuf *views[] = {&ctx->arena_buf, &ctx->qtab, &ctx->bases, &ctx->quals, &ctx->hdrs, &ctx->t_llen, &ctx->t_qlen, &ctx->t_hlen,
                        &ctx->t_pfg, &ctx->t_pfq, &ctx->t_boff, &ctx->t_qoff, &ctx->t_hoff, &ctx->t_ooff,
                        &ctx->e2_gsteps, &ctx->e2_qkey, &ctx->e2_qb, &ctx->e2_sorted, &ctx->e2_qsteps, &ctx->e2_cnt,
-                       &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs};
+                       &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs, &ctx->e2_gbins, &ctx->e2_gcnt};
     for (DevBuf *d : views) d->release();
     ctx->scratch.release(); ctx->gtab.release(); ctx->pw.release();
 }
@@ -158,12 +161,13 @@ int status_to_error(sfq_ctx *ctx, const SfqChunkMeta &m, uint64_t chunk, uint64_
     case SFQ_E_AT: return fail(ctx, SFQ_ERR_FASTQ, "fastq file: expecting '@' at record %llu (chunk %llu)", rec, (unsigned long long)chunk);
     case SFQ_E_PLUS: return fail(ctx, SFQ_ERR_FASTQ, "fastq file: expecting '+' at record %llu (chunk %llu)", rec, (unsigned long long)chunk);
     case SFQ_E_TRUNC: return fail(ctx, SFQ_ERR_FASTQ, "fastq file: record seems truncated  after record %llu", rec);
-    case SFQ_E_OVERSIZE: return fail(ctx, SFQ_ERR_UNSUPPORTED, "record %llu: oversized record (id >= 8 KiB or line >= 64 KiB) is not supported", rec);
+    case SFQ_E_OVERSIZE: return fail(ctx, SFQ_ERR_FASTQ, "wierd second id at record %llu", rec);
     case SFQ_E_BASE: return fail(ctx, SFQ_ERR_FASTQ, "unexpected genome char: %c", (int)m.status_arg);
     case SFQ_E_NBYTE: return fail(ctx, SFQ_ERR_FASTQ, "switched N_byte: %c", (int)m.status_arg);
     case SFQ_E_SEPS: return fail(ctx, SFQ_ERR_FASTQ, "ERROR: irregulal record (over 64 non alpha non digit). Is it a valid fastq file?");
     case SFQ_E_FIRSTHDR: return fail(ctx, SFQ_ERR_UNSUPPORTED, "chunk %llu: first header longer than 399 chars", (unsigned long long)chunk);
     case SFQ_E_EMPTYSEQ: return fail(ctx, SFQ_ERR_UNSUPPORTED, "chunk %llu: first record has an empty base line", (unsigned long long)chunk);
+    case SFQ_E_CHUNKSIZE: return fail(ctx, SFQ_ERR_UNSUPPORTED, "chunk %llu holds 4 GiB or more of bases, qualities or headers: use a smaller chunk size (-c; -R codes the file as one chunk)", (unsigned long long)chunk);
     case SFQ_E_CORRUPT: return fail(ctx, SFQ_ERR_FORMAT, "chunk %llu: corrupt stream", (unsigned long long)chunk);
     default: return fail(ctx, SFQ_ERR_CUDA, "chunk %llu: internal status %u", (unsigned long long)chunk, m.status);
     }
@@ -310,27 +314,31 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     uint64_t end_cursor = 0;
     st.retries = 0;
     for (uint32_t grow = 0;; grow++) {
+        uint64_t max_nb = 0, max_nq = 0;
+        for (uint32_t c = 0; c < nchunks; c++) { max_nb = std::max<uint64_t>(max_nb, metas[c].nbases); max_nq = std::max<uint64_t>(max_nq, metas[c].nquals); }
+        // The two-phase encoder packs stream positions into 24 bits: a chunk of 2^24 or more bases or qualities (CLI -R on a
+        // large file, a huge -c) goes through the single-pass coders instead (one chain per chunk-stream: slow, any size).
+        const bool two_phase = !ctx->serial_encoder && max_nq < (1u << 24) && max_nb < (1u << 24);
+        const bool gm_table = !two_phase || ctx->gm_table;            // base models in a global table (single-pass coder, or A/B)
         const uint32_t hbits = sfq_gen_hbits(level, max_bases, grow);
         const uint32_t cbits = sfq_q_cbits(level, grow);
-        const uint64_t gstride = sfq_gtable_bytes(level, hbits), qbytes = sfq_qhash_bytes(level, cbits), pbytes = sfq_pwpool_bytes();
+        const uint32_t gp_bits = sfq_gen_gp_bits(max_nb, grow);
+        const uint64_t gstride = gm_table ? sfq_gtable_bytes(level, hbits) : 0, qbytes = sfq_qhash_bytes(level, cbits), pbytes = sfq_pwpool_bytes();
         uint64_t max_arena = 0;
         for (uint32_t c = 0; c < nchunks; c++) {
             uint64_t end; SfqArena a;
             sfq_arena_layout(&metas[c], grow, 0, &a, &end);
             max_arena = std::max(max_arena, end);
         }
-        const bool two_phase = !ctx->serial_encoder;
-        uint64_t max_nb = 0, max_nq = 0;
-        for (uint32_t c = 0; c < nchunks; c++) { max_nb = std::max<uint64_t>(max_nb, metas[c].nbases); max_nq = std::max<uint64_t>(max_nq, metas[c].nquals); }
-        if (two_phase && max_nq >= (1u << 24)) return fail(ctx, SFQ_ERR_UNSUPPORTED, "chunk of %llu quality values: chunk_bytes is too large (limit 16 Mi values per chunk)", (unsigned long long)max_nq);
         auto esc_cap = [grow](uint64_t nq) { return std::min<uint64_t>(nq, (nq >> 4) << grow) + 64; };
         auto seg_cap = [](uint64_t nq) { return std::min<uint64_t>(SFQ_Q_NCTX, nq) + 1; };
         // two-phase encoder: no quality-model table in global memory, but the coding steps of every symbol
-        const uint64_t e2_per_chunk = 4 * max_nb + 15 * max_nq + SFQ_Q_CNT * 4ull + 16 * seg_cap(max_nq) + 12 * esc_cap(max_nq) + 256;
+        const uint64_t e2_per_chunk = 4 * max_nb + (gm_table ? 0 : 8 * max_nb + (36ull << gp_bits)) + 15 * max_nq + SFQ_Q_CNT * 4ull + 16 * seg_cap(max_nq) + 12 * esc_cap(max_nq) + 256;
         const uint64_t per_chunk = gstride + pbytes + max_arena + 4096 + (two_phase ? e2_per_chunk : qbytes);
         const uint64_t have_now = ctx->gtab.cap + ctx->pw.cap + ctx->scratch.cap;
         const uint32_t R = pick_resident(ctx, nchunks, per_chunk, have_now);
-        CK(ctx->gtab.ensure(R * gstride)); CK(ctx->pw.ensure(R * pbytes));
+        if (gm_table) CK(ctx->gtab.ensure(R * gstride)); else ctx->gtab.release();
+        CK(ctx->pw.ensure(R * pbytes));
         const uint32_t nwaves = (nchunks + R - 1) / R;
         if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
         st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * per_chunk;
@@ -350,15 +358,16 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         SfqEnc2Ws e2{};
         {   // everything wave-sized comes out of the shared scratch arena
             const size_t sz[] = {wave_arena_max + 64, wave_nb * 4 + 256, wave_nq * 2 + 64, wave_nq + 64, wave_nq * 4 + 64, wave_nq * 8 + 256,
-                                 (size_t)R * SFQ_Q_CNT * 4, wave_ne * 4 + 64, wave_ne * 8 + 64, wave_seg * sizeof(SfqSeg), (size_t)R * qbytes};
+                                 (size_t)R * SFQ_Q_CNT * 4, wave_ne * 4 + 64, wave_ne * 8 + 64, wave_seg * sizeof(SfqSeg),
+                                 gm_table ? 0 : (wave_nb + ((size_t)R * 4 << gp_bits)) * 8 + 256, gm_table ? 0 : ((size_t)R * 4 << gp_bits) + 64, (size_t)R * qbytes};
             DevBuf *bufs[] = {&ctx->arena_buf, &ctx->e2_gsteps, &ctx->e2_qkey, &ctx->e2_qb, &ctx->e2_sorted, &ctx->e2_qsteps,
-                              &ctx->e2_cnt, &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs, &ctx->qtab};
-            const int first = 0, last = two_phase ? 10 : 11;
+                              &ctx->e2_cnt, &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs, &ctx->e2_gbins, &ctx->e2_gcnt, &ctx->qtab};
+            const int first = 0, last = two_phase ? 12 : 13;
             size_t total = 0;
-            for (int k = first; k < last; k++) if (two_phase || k == 0 || k == 10) total += (sz[k] + 255) & ~(size_t)255;
+            for (int k = first; k < last; k++) if (two_phase || k == 0 || k == 12) total += (sz[k] + 255) & ~(size_t)255;
             CK(ctx->scratch.ensure(total));
             size_t off = 0;
-            for (int k = first; k < last; k++) if (two_phase || k == 0 || k == 10) bufs[k]->carve(ctx->scratch, sz[k], &off);
+            for (int k = first; k < last; k++) if (two_phase || k == 0 || k == 12) bufs[k]->carve(ctx->scratch, sz[k], &off);
         }
         if (two_phase) {
             CK(ctx->e2_ctr.ensure(64)); CK(ctx->e2_chunks.ensure(nchunks * sizeof(SfqEnc2Chunk)));
@@ -367,6 +376,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             e2.sorted = ctx->e2_sorted.as<uint32_t>(); e2.qsteps = ctx->e2_qsteps.as<uint64_t>(); e2.cnt = ctx->e2_cnt.as<uint32_t>();
             e2.esorted = ctx->e2_esorted.as<uint32_t>(); e2.esteps = ctx->e2_esteps.as<uint64_t>(); e2.segs = ctx->e2_segs.as<SfqSeg>();
             e2.seg_cap = wave_seg; e2.ctr = ctx->e2_ctr.as<uint32_t>();
+            e2.gbins = ctx->e2_gbins.as<SfqU2>(); e2.gcnt = ctx->e2_gcnt.as<uint32_t>(); e2.gp_bits = gp_bits;
         }
         CK(cudaMemcpyAsync(d_arenas, arenas.data(), nchunks * sizeof(SfqArena), cudaMemcpyHostToDevice, s));
         h_small[0] = 0; h_small[1] = sizeof(SfqFileHeader); h_small[2] = 0;
@@ -377,7 +387,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         for (uint32_t w = 0; w < nwaves; w++) {
             const uint32_t c0 = w * R, nc = std::min(nchunks, c0 + R) - c0;
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 0], s));
-            CK(cudaMemsetAsync(ctx->gtab.p, 0, nc * gstride, s));
+            if (gm_table) CK(cudaMemsetAsync(ctx->gtab.p, 0, nc * gstride, s));
+            else CK(cudaMemsetAsync(ctx->e2_gcnt.p, 0, (size_t)nc * 4 << gp_bits, s));
             if (!two_phase) CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
             else { CK(cudaMemsetAsync(ctx->e2_cnt.p, 0, (uint64_t)nc * SFQ_Q_CNT * 4, s)); CK(cudaMemsetAsync(ctx->e2_ctr.p, 0, 64, s)); }
             CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
@@ -403,7 +414,13 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     CK(cudaStreamWaitEvent(s, ctx->head_ev, 0));
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
-                if (two_phase) {
+                if (two_phase && !gm_table) {
+                    const bool gp_smem = (1u << gp_bits) <= SFQ_GP_SMEM_MAX;
+                    TRACED("k_gen_count", s, (k_gen_count<<<dim3((wave_max_nrec + SFQ_GC_RECS - 1) / SFQ_GC_RECS, nc), 128, gp_smem ? (size_t)4 << gp_bits : 0, s>>>(d_text, d_ls, d_metas + c0, e2.gcnt, gp_bits, level, nc))); LAUNCHED();
+                    TRACED("k_gen_scatter", s, (k_gen_scatter<8><<<nc, 32, gp_smem ? (size_t)36 << gp_bits : 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc))); LAUNCHED();
+                    TRACED("k_gen_replay", s, (k_gen_replay<<<ctx->sm_count, 32 * SFQ_GR_WARPS, SFQ_GR_SMEM, s>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    TRACED("k_rc_encode<0>", s, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
+                } else if (two_phase) {
                     { TraceScope ts_(ctx, "k_gen_model", s);
                     switch (ctx->gm_variant) {
                     case 1: k_gen_model<4, 8><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
@@ -424,7 +441,11 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                         TRACED("k_qlt_keys", q, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
                         TRACED("k_qlt_scan", q, (k_qlt_scan<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
                     }
-                    TRACED("k_qlt_scatter", q, (k_qlt_scatter<<<nwarp_blocks, 128, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    if (ctx->q_scatter1) { TRACED("k_qlt_scatter", q, (k_qlt_scatter<<<nwarp_blocks, 128, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED(); }
+                    else {
+                        TRACED("k_qlt_part1", q, (k_qlt_part1<<<nc, 32, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                        TRACED("k_qlt_part2", q, (k_qlt_part2<<<ctx->sm_count * 6, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    }
                     TRACED("k_qlt_model", q, (k_qlt_model<<<ctx->sm_count * 4, SFQ_QM_THREADS, 0, q>>>(d_metas + c0, ws_at(ws, c0), e2, d_e2c, c0))); LAUNCHED();
                     k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
                     TRACED("k_rc_encode<1>", q, (k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
@@ -473,7 +494,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         if (!again) { end_cursor = h_small[1]; if (*reinterpret_cast<uint32_t *>(&h_small[2])) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need more than %llu bytes)", (unsigned long long)out_cap); break; }
         if (grow >= 6) return fail(ctx, SFQ_ERR_CUDA, "stream arena still too small after 6 doublings");
         st.retries++;
-        for (uint32_t c = 0; c < nchunks; c++) metas[c].status = SFQ_OK;
+        for (uint32_t c = 0; c < nchunks; c++) { metas[c].status = SFQ_OK; metas[c].g_used = 0; metas[c].q_used = 0; }
         CK(cudaMemcpyAsync(d_metas, metas.data(), nchunks * sizeof(SfqChunkMeta), cudaMemcpyHostToDevice, s));
     }
 
@@ -516,12 +537,13 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         const SfqBlobHeader &b = blobs[c];
         const uint64_t off = index[c];
         if (b.magic != SFQ_BLOB_MAGIC || off + sfq_blob_size(&b) > n || b.level < 1 || b.level > 4 ||
-            b.nrec == 0 || b.rec_first_len > 399)
+            b.nrec == 0 || b.rec_first_len > 399)       // (rec_first_len 0: every record of the chunk is oversized)
             return fail(ctx, SFQ_ERR_FORMAT, "chunk %u: bad blob header", c);
         SfqChunkMeta &m = metas[c];
         memset(&m, 0, sizeof m);
         m.text_len = b.text_len; m.out_len = b.out_len; m.nrec = b.nrec; m.nbases = b.nbases; m.nquals = b.nquals;
         m.hdr_bytes = b.hdr_bytes; m.llen = b.llen; m.solid = b.solid; m.two_id = b.two_id; m.n_byte = b.n_byte; m.pad = b.pad;
+        m.nbig = b.nbig; m.big_bases = b.big_bases; m.big_quals = b.big_quals; m.big_hdr = b.big_hdr;
         SfqDecChunk &d = dcs[c];
         uint64_t o = off + sizeof(SfqBlobHeader);
         d.rec_first_off = o; d.rec_first_len = b.rec_first_len; o += b.rec_first_len;
@@ -529,11 +551,13 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         st.gen_stream_bytes += b.ssize[SFQ_S_GEN]; st.qlt_stream_bytes += b.ssize[SFQ_S_QLT];
         d.level = (int32_t)b.level;
         d.rec_base = nrec; d.base_plane = nb; d.qual_plane = nq; d.hdr_plane = nh;
-        nrec += b.nrec; nb += b.nbases; nq += b.nquals; nh += SFQ_HDR_PLANE(&m); no += b.out_len;
+        d.base_cap = (uint64_t)b.nbases + b.big_bases; d.qual_cap = (uint64_t)b.nquals + b.big_quals; d.hdr_cap = SFQ_HDR_PLANE(&m);
+        nrec += b.nrec; nb += d.base_cap; nq += d.qual_cap; nh += d.hdr_cap; no += b.out_len;
         max_bases = std::max<uint64_t>(max_bases, b.nbases);
         max_level = std::max(max_level, (int)b.level);
         // a record prints at least "@h\nb\n+\nq\n": reject headers whose counts cannot match their out_len
-        if (!(b.pad & SFQ_BLOB_IMPORTED) && (b.out_len < 6ull * b.nrec || (uint64_t)b.nbases + b.nquals + b.hdr_bytes > b.out_len))
+        if (!(b.pad & SFQ_BLOB_IMPORTED) && (b.out_len < 6ull * b.nrec || b.nbig > b.nrec ||
+                                             (uint64_t)b.nbases + b.nquals + b.hdr_bytes + b.big_bases + b.big_quals + b.big_hdr > b.out_len))
             return fail(ctx, SFQ_ERR_FORMAT, "chunk %u: inconsistent blob header", c);
     }
     if (no > out_cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)no);
@@ -606,7 +630,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
             CK(cudaMemsetAsync(ctx->qtab.p, 0, nc * qbytes, s));
             CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
-            k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, nc); LAUNCHED();
+            k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, ctx->bases.as<uint8_t>(), ctx->quals.as<uint8_t>(), ctx->hdrs.as<uint8_t>(), nc); LAUNCHED();
             {
                 const uint32_t lanes = pick_lanes(ctx, nc);
                 const unsigned nb = (nc + lanes - 1) / lanes;
@@ -756,6 +780,8 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_GDEC")) ctx->gdec32 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QLPC")) { int v = atoi(e); if (v == 4 || v == 8) ctx->qlpc = (uint32_t)v; }
     if (const char *e = getenv("SFQ_GM_VARIANT")) ctx->gm_variant = atoi(e);
+    if (const char *e = getenv("SFQ_GM_TABLE")) ctx->gm_table = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_QSCATTER")) ctx->q_scatter1 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_GEN_AHEAD2")) ctx->gen_ahead2 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QDEC")) ctx->qdec_octets = atoi(e) != 0;
     if (const char *e = getenv("SFQ_SERIAL_ROLES")) ctx->serial_roles = atoi(e) != 0;
@@ -769,6 +795,8 @@ int sfq_create(sfq_ctx **out, int device) {
             cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->head_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    if (cudaFuncSetAttribute(k_gen_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SFQ_GR_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gen_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(36u * SFQ_GP_SMEM_MAX)) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     {   // shared memory the decoders' CTAs reserve when they are spread (one of each kind per SM fits, two of a kind barely)
         int smem_sm = 0;
         cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
@@ -990,6 +1018,8 @@ int sfq_import_reference(const uint8_t *ref, size_t n, uint8_t *out, size_t out_
     b.n_byte = (nb && nb != 'N') ? (uint8_t)nb : 0;
     b.pad = SFQ_BLOB_IMPORTED;
     b.extra_hi = (uint32_t)num("qlt.extra.hi", 0);
+    // oversized records: their count is not recorded either; the planes' upper bounds (orig.size) cover them
+    b.nbig = 0; b.big_bases = b.big_quals = b.big_hdr = 0;
     const std::string &first = info["rec.first"];
     if (first.size() > 399) return SFQ_ERR_UNSUPPORTED;
     b.rec_first_len = (uint32_t)first.size();
@@ -1001,8 +1031,6 @@ int sfq_import_reference(const uint8_t *ref, size_t n, uint8_t *out, size_t out_
         b.ssize[k] = (uint32_t)sz;
         total += sz;
     }
-    static const char *const unsupported[] = {"usr.lrec", "usr.lgen", "usr.lqlt"};   // oversized records, usrs.cpp:269-301
-    for (const char *u : unsupported) { auto it = streams.find(u); if (it != streams.end() && !it->second.empty()) return SFQ_ERR_UNSUPPORTED; }
     if (total + 8 > out_cap) return SFQ_ERR_SPACE;
     SfqFileHeader fh;
     sfq_file_header_init(&fh, (int)b.level, (uint64_t)orig, 1, (uint64_t)orig, total, b.out_len);

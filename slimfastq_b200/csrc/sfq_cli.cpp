@@ -109,7 +109,7 @@ static void statistics_dump(const uint8_t *p, size_t n) {      // config.cpp:76-
     fprintf(stderr, "%-16s = %llu\n", "comp.size", (unsigned long long)n);
     fprintf(stderr, "%-16s = %llu\n", "chunks", (unsigned long long)fh.nchunks);
     fprintf(stderr, "%-16s = %llu\n", "chunk.bytes", (unsigned long long)fh.chunk_bytes);
-    static const char *names[SFQ_NSTREAMS] = {"rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq"};
+    static const char *names[SFQ_NSTREAMS] = {"rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq", "usr.lrec", "usr.lgen", "usr.lqlt"};
     unsigned long long tot[SFQ_NSTREAMS] = {0}, nrec = 0, extra = 0;
     if (fh.index_off <= n && n - fh.index_off >= fh.nchunks * 8)
         for (uint64_t c = 0; c < fh.nchunks; c++) {

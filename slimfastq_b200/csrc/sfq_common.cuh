@@ -24,7 +24,9 @@
 // (usrs.cpp:47-54,396-398; gens.cpp:68-69; recs.cpp:46).
 enum {
     SFQ_S_REC = 0, SFQ_S_GEN, SFQ_S_QLT, SFQ_S_GEN_NS, SFQ_S_GEN_NN, SFQ_S_REC_X,
-    SFQ_S_USR_X, SFQ_S_USR_XQ, SFQ_S_USR_PFG, SFQ_S_USR_PFQ, SFQ_NSTREAMS
+    SFQ_S_USR_X, SFQ_S_USR_XQ, SFQ_S_USR_PFG, SFQ_S_USR_PFQ,
+    SFQ_S_USR_LREC, SFQ_S_USR_LGEN, SFQ_S_USR_LQLT,        // oversized records, stored verbatim (usrs.cpp:269-301)
+    SFQ_NSTREAMS
 };
 
 // Per-chunk status codes written by kernels; the host turns the first non-zero one into the
@@ -34,7 +36,7 @@ enum {
     SFQ_E_AT = 1,          // record does not start with '@'            usrs.cpp:158-163,200
     SFQ_E_PLUS = 2,        // third line does not start with '+'        usrs.cpp:232,346
     SFQ_E_TRUNC = 3,       // truncated record / missing final newline  usrs.cpp:165-168
-    SFQ_E_OVERSIZE = 4,    // id >= 8 KiB or line >= 64 KiB             usrs.hpp:34-36 (unsupported)
+    SFQ_E_OVERSIZE = 4,    // '+' line of 8 191+ chars ("wierd second id", usrs.cpp:349-352); oversized records themselves are coded
     SFQ_E_BASE = 5,        // unexpected genome char                    gens.cpp:125-126
     SFQ_E_NBYTE = 6,       // switched N byte                           gens.cpp:107-108
     SFQ_E_SEPS = 7,        // > 64 separators in a header               recs.cpp:153-154
@@ -43,6 +45,7 @@ enum {
     SFQ_E_FIRSTHDR = 10,   // first header > 399 chars                  recs.cpp:31,69-70
     SFQ_E_CORRUPT = 11,    // decoder: impossible value in a stream
     SFQ_E_EMPTYSEQ = 12,   // first record of a chunk has an empty base line (usrs.cpp:216-231 cannot represent it)
+    SFQ_E_CHUNKSIZE = 13,  // a chunk's bases, qualities or headers do not fit the container's 32-bit counts
 };
 
 // Sizes of the per-chunk model pools.
@@ -50,14 +53,14 @@ enum {
 #define SFQ_PW_WORDS    340u           // one 256-symbol model: 256 slots + inverse map + group sums (SfqPower)
 // 256-symbol model instances per chunk:
 //   header fields: 66 x (type, str, num[14])            recs.hpp:42-48
-//   7 exception streams x (num[14], str)                xfile.hpp:41-42
+//   10 exception streams x (num[14], str)               xfile.hpp:41-42
 //   1 quality escape model                              qlts.hpp:44
 #define SFQ_PW_REC_BASE   0u
 #define SFQ_PW_PER_FIELD  16u
 #define SFQ_PW_X_BASE     (66u * 16u)
 #define SFQ_PW_PER_X      15u
-#define SFQ_PW_QEX        (SFQ_PW_X_BASE + 7u * SFQ_PW_PER_X)
-#define SFQ_PW_PER_CHUNK  (SFQ_PW_QEX + 1u)      // 1162 models = 1.5 MiB per resident chunk
+#define SFQ_PW_QEX        (SFQ_PW_X_BASE + 10u * SFQ_PW_PER_X)
+#define SFQ_PW_PER_CHUNK  (SFQ_PW_QEX + 1u)      // 1207 models = 1.6 MiB per resident chunk
 // exception-stream slot -> stream id
 #define SFQ_X_NS 0
 #define SFQ_X_NN 1
@@ -66,6 +69,9 @@ enum {
 #define SFQ_X_QLEN 4
 #define SFQ_X_SGEN 5
 #define SFQ_X_SQLT 6
+#define SFQ_X_LREC 7
+#define SFQ_X_LGEN 8
+#define SFQ_X_LQLT 9
 
 #define SFQ_MAX_ID_LLEN 0x2000
 #define SFQ_MAX_GN_LLEN 0x10000
@@ -91,11 +97,17 @@ struct SfqChunkMeta {
     uint32_t g_used;        // distinct base contexts the chunk touched
     uint32_t status;        // SFQ_OK or first error
     uint32_t status_arg;    // record number / offending byte for the message
+    // oversized records of the chunk (usrs.cpp:269-301): how many, and the bytes of their lines - base lines and quality
+    // lines without the newline, id line (without '@') + '\n' + '+' line as one block.  nbases / nquals / hdr_bytes count
+    // the CODED records only; the decoder's planes hold both.
+    uint32_t nbig, big_bases, big_quals, big_hdr;
+    uint32_t first_coded;   // index of the first record that goes through the models (its id line is `rec.first`); nrec if none
+    uint32_t pad2;
 };
 
 // Bytes reserved for a chunk's decoded headers (each followed by '\n').  The slack covers the few
 // cases where the reference prints a header field longer than it was (sign of a "%lld" value).
-#define SFQ_HDR_PLANE(m) ((uint64_t)(m)->hdr_bytes + 9ull * (m)->nrec + 64ull)
+#define SFQ_HDR_PLANE(m) ((uint64_t)(m)->hdr_bytes + (m)->big_hdr + 9ull * (m)->nrec + 64ull)
 
 // Output arena of one resident chunk: SFQ_NSTREAMS sub-ranges.
 struct SfqArena {

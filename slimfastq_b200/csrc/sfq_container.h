@@ -6,7 +6,8 @@
 //
 // A blob carries exactly what the reference keeps for a standalone file: the semantic keys of its
 // info stream (config.level, llen, usr.solid, usr.2id, gen.N_byte, num_records, rec.first,
-// qlt.extra.hi) and the named range-coded streams, byte-identical to the reference's.
+// qlt.extra.hi) and the named range-coded streams (rec gen qlt gen.Ns gen.Nn rec.x usr.x usr.x.q usr.pfg usr.pfq usr.lrec
+// usr.lgen usr.lqlt), byte-identical to the reference's.
 // The first 16 bytes are the stamp the reference sniffs (config.cpp:295-304); the next 16 tell the
 // two container kinds apart.  All integers little-endian.
 #pragma once
@@ -15,7 +16,7 @@
 #include "sfq_common.cuh"
 
 #define SFQ_STAMP      "whoami=slimfastq"           /* 16 bytes */
-#define SFQ_KIND       "\nformat=b200.c1\n"         /* 16 bytes */
+#define SFQ_KIND       "\nformat=b200.c2\n"         /* 16 bytes */
 #define SFQ_BLOB_MAGIC 0x43514653u                  /* "SFQC" */
 #define SFQ_INTERNAL_VERSION 6                      /* config.cpp:44 */
 
@@ -48,8 +49,9 @@ struct SfqBlobHeader {
     uint32_t extra_hi;       // qlt.extra.hi
     uint32_t rec_first_len;  // rec.first follows the header
     uint32_t q_used, g_used; // distinct quality / base contexts touched (decoder table sizing hint; 0 = unknown)
+    uint32_t nbig, big_bases, big_quals, big_hdr;   // oversized records (usr.lrec/lgen/lqlt): count and line bytes, see SfqChunkMeta
     uint32_t ssize[SFQ_NSTREAMS];
-};                           // 104 bytes
+};                           // 132 bytes
 #pragma pack(pop)
 
 static inline void sfq_file_header_init(SfqFileHeader *h, int level, uint64_t orig, uint64_t nchunks,

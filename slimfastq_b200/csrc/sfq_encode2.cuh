@@ -54,7 +54,8 @@ struct SfqEnc2Chunk {
 #define SFQ_Q_NCTX   65536u
 #define SFQ_Q_CNT    65544u           // counters per chunk: 65536 contexts + [65536] = escapes, padded
 #define SFQ_SEG_BIG  2048u            // segments at least this long are scheduled first
-struct SfqSeg { uint32_t chunk, start, count, flags; };      // flags bit 0: escape segment
+struct SfqSeg { uint32_t chunk, start, count, flags; };
+struct SfqU2 { uint32_t x, y; };                              // (uint2 outside nvcc)      // flags bit 0: escape segment
 struct SfqEnc2Ws {
     uint32_t *gsteps;
     uint16_t *qkey;
@@ -66,7 +67,10 @@ struct SfqEnc2Ws {
     uint64_t *esteps;
     SfqSeg   *segs;         // small segments grow from the front, big ones from the back
     uint64_t  seg_cap;
-    uint32_t *ctr;          // [0] small segments, [1] big segments, [2] next segment to hand out
+    uint32_t *ctr;          // [0] small segments, [1] big segments, [2] next segment to hand out, [4] next (chunk, partition) of k_gen_replay
+    SfqU2    *gbins;        // gen: (position | symbol << 24, context) grouped by context partition, stream order inside
+    uint32_t *gcnt;         // gen: per chunk, gp partition sizes -> end offsets
+    uint32_t  gp_bits;      // gen: log2 of the partitions per chunk
 };
 
 // ---------------------------------------------------------------------------- Log64Ranger, replay form
@@ -356,6 +360,339 @@ k_gen_model(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, S
     }
 }
 
+// ============================================================================ gen, phase 1, partitioned form
+// k_gen_model above keeps a chunk's 4-symbol models in a hash table in global memory: one random 8-byte slot
+// per base, i.e. two DRAM sectors per base and 8 MiB of table per 1 MiB chunk, walked by ONE warp per chunk.
+// The kernels below bring the models into shared memory instead:
+//   k_gen_count    how many bases of the chunk fall into each of GP partitions of the context space
+//                  (partition = top bits of a multiplicative hash of the context); order-free, all records in parallel
+//   k_gen_scatter  one warp per chunk walks the bases in stream order (exception lists gen.Ns / gen.Nn are
+//                  written on the way, gens.cpp:91-114) and appends (position, symbol, context) to the list of
+//                  the context's partition - a stable partition, 8 bytes per base.  Lists start on 32-byte
+//                  boundaries and are staged four entries at a time in shared memory, so what goes to DRAM
+//                  are whole sectors
+//   k_gen_replay   one warp per (chunk, partition): the partition's few hundred contexts live in a 2048-slot hash
+//                  table in the warp's shared memory; the warp replays the list 32 entries at a time - every lane
+//                  finds or claims its context's slot by itself (compare-and-swap on the key), windows in which two
+//                  lanes meet in one slot take the ordered path (entries of one context in list order,
+//                  base2_ranger.hpp:74-84) - and writes each base's coding step to its stream position.
+// A context belongs to exactly one partition and a partition's list keeps stream order, so every model sees its
+// symbols in the reference's order: the steps, hence the bytes, are those of the single-pass coder.
+#define SFQ_GP_TARGET   768u           // bases per partition the partition count aims for (sfq_gen_gp_bits)
+#define SFQ_GP_SLOTS    2048u          // hash slots per replay warp (8 bytes each) + one owner byte per slot
+#define SFQ_GP_SMEM_MAX 4096u          // the scatter warp keeps cursors and staging rows in shared memory up to this many partitions
+#define SFQ_GR_WARPS    12             // replay warps per CTA (12 x 18 KB)
+#define SFQ_GR_BATCH    8u             // (chunk, partition) items a replay warp takes per trip to the work counter
+#define SFQ_GR_SMEM     (SFQ_GR_WARPS * (SFQ_GP_SLOTS * 8u + SFQ_GP_SLOTS))
+#define SFQ_GC_RECS     128u           // records per CTA of k_gen_count
+__device__ __forceinline__ uint32_t sfq_gp_of(uint32_t ctx, uint32_t gp_bits) { return gp_bits ? (ctx * 2654435761u) >> (32u - gp_bits) : 0u; }
+__device__ __forceinline__ uint32_t sfq_gp_slot(uint32_t ctx, uint32_t gp_bits) { return ((ctx * 2654435761u) >> (21u - gp_bits)) & (SFQ_GP_SLOTS - 1u); }   // the 11 bits below the partition's (gp_bits <= 14)
+__host__ __device__ __forceinline__ uint64_t sfq_gbins_off(uint64_t goff, uint32_t c_in_wave, uint32_t gp_bits) { return goff + ((uint64_t)c_in_wave << (gp_bits + 2u)); }   // lists are padded to 4 entries
+
+// Contexts of a window of 32 bases (2 bits per base, newest lowest; gens.cpp:139-147): n = this lane's code,
+// prev = context carried in from the bases before the window (updated for the next window).
+__device__ __forceinline__ uint32_t sfq_gen_window_ctx(uint32_t n, uint32_t lane, uint32_t &prev, uint32_t mask) {
+    const unsigned FULL = 0xffffffffu;
+    uint32_t h = n, t;
+    t = __shfl_up_sync(FULL, h, 1); if (lane >= 1) h |= t << 2;
+    t = __shfl_up_sync(FULL, h, 2); if (lane >= 2) h |= t << 4;
+    t = __shfl_up_sync(FULL, h, 4); if (lane >= 4) h |= t << 8;
+    t = __shfl_up_sync(FULL, h, 8); if (lane >= 8) h |= t << 16;
+    t = __shfl_up_sync(FULL, h, 1);
+    const uint32_t ctx = ((lane < 16 ? prev << (2 * lane) : 0u) | (lane ? t : 0u)) & mask;
+    prev = __shfl_sync(FULL, h, 31);
+    return ctx;
+}
+// Lanes holding the same `bits`-bit value as this lane (one ballot per bit: the cost does not depend on how many
+// different values the warp holds, unlike __match_any_sync, whose hardware loop takes one turn per distinct value).
+__device__ __forceinline__ unsigned sfq_match_bits(uint32_t v, uint32_t bits, unsigned among) {
+    unsigned peers = among;
+    for (uint32_t b = 0; b < bits; b++) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (v >> b) & 1u);
+        peers &= ((v >> b) & 1u) ? bal : ~bal;
+    }
+    return peers;
+}
+
+// gcnt[c * gp + p] += bases of chunk c whose context lies in partition p.  A CTA takes SFQ_GC_RECS records of one
+// chunk (blockIdx.y), a warp one record at a time.
+__global__ void __launch_bounds__(128)
+k_gen_count(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, const SfqChunkMeta *__restrict__ metas,
+            uint32_t *gcnt, uint32_t gp_bits, int level, uint32_t nchunks) {
+    extern __shared__ uint32_t hist[];                     // gp counters (gp <= SFQ_GP_SMEM_MAX), else straight to global
+    const uint32_t c = blockIdx.y;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (c >= nchunks) return;
+    const SfqChunkMeta *meta = &metas[c];
+    if (meta->status != SFQ_OK) return;
+    const uint32_t nrec = meta->nrec;
+    if (blockIdx.x * SFQ_GC_RECS >= nrec) return;
+    const uint32_t gp = 1u << gp_bits;
+    const bool in_smem = gp <= SFQ_GP_SMEM_MAX;
+    uint32_t *out = gcnt + (size_t)c * gp;
+    if (in_smem) { for (uint32_t k = threadIdx.x; k < gp; k += blockDim.x) hist[k] = 0; __syncthreads(); }
+    uint32_t *h = in_smem ? hist : out;
+    const uint32_t solid = meta->solid, mask = sfq_gen_mask(level);
+    const uint64_t line0 = meta->line0;
+    const uint32_t r_end = min(nrec, (blockIdx.x + 1u) * SFQ_GC_RECS);
+    for (uint32_t r = blockIdx.x * SFQ_GC_RECS + warp; r < r_end; r += 4) {
+        const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+        uint32_t prev = 0x007616c7u;                                           // gens.cpp:139
+        for (uint32_t w0 = 0; w0 < v.llen; w0 += 32) {
+            const bool active = w0 + lane < v.llen;
+            uint32_t n = sfq_gencode(active ? v.seq[w0 + lane] : (uint8_t)'A');
+            if (n > 3u) n = 0;
+            const uint32_t ctx = sfq_gen_window_ctx(n, lane, prev, mask);
+            if (active) atomicAdd(h + sfq_gp_of(ctx, gp_bits), 1u);
+        }
+    }
+    if (in_smem) {
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < gp; k += blockDim.x) { const uint32_t v = hist[k]; if (v) atomicAdd(out + k, v); }
+    }
+}
+
+// One warp per chunk, in stream order: exceptions, then (position | symbol << 24, context) appended to the list of
+// the context's partition.  gcnt holds the partition sizes on entry and each partition's END offset on exit (list p
+// starts at the end of list p-1 rounded up to 4 entries).
+template <int SFQ_GM_BATCH>
+__global__ void __launch_bounds__(32)
+k_gen_scatter(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas,
+              SfqArena *arenas, uint8_t *arena_buf, SfqWorkspace ws, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c,
+              int level, uint32_t nchunks) {
+    extern __shared__ uint4 sc_smem[];                     // gp staging rows of 4 entries (32 bytes), then gp cursors
+    const uint32_t c = blockIdx.x;
+    const uint32_t lane = threadIdx.x;
+    if (c >= nchunks) return;
+    SfqChunkMeta *meta = &metas[c];
+    if (meta->status != SFQ_OK) return;
+    SfqArena *ar = &arenas[c];
+    uint32_t *pwpool = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
+    SfqXSave xns, xnn;
+    xns.init(pwpool, SFQ_X_NS, arena_buf + ar->off[SFQ_S_GEN_NS], ar->cap[SFQ_S_GEN_NS]);
+    xnn.init(pwpool, SFQ_X_NN, arena_buf + ar->off[SFQ_S_GEN_NN], ar->cap[SFQ_S_GEN_NN]);
+    const uint32_t gp_bits = e2.gp_bits, gp = 1u << gp_bits;
+    uint32_t *gc = e2.gcnt + (size_t)c * gp;
+    const bool staged = gp <= SFQ_GP_SMEM_MAX;             // beyond that (chunks of > 3 M bases): cursors in global memory, entries written one by one
+    uint2 *stage = reinterpret_cast<uint2 *>(sc_smem);
+    uint32_t *cur = staged ? reinterpret_cast<uint32_t *>(sc_smem + 2 * (size_t)gp) : gc;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    {   // exclusive prefix of the padded partition sizes -> cursors (lane k owns a block of consecutive partitions)
+        const uint32_t per = (gp + 31u) / 32u, lo = min(gp, lane * per), hi = min(gp, lo + per);
+        uint32_t s = 0;
+        for (uint32_t k = lo; k < hi; k++) s += (gc[k] + 3u) & ~3u;
+        uint32_t inc = s, t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { t = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += t; }
+        uint32_t run = inc - s;
+        for (uint32_t k = lo; k < hi; k++) { const uint32_t v = (gc[k] + 3u) & ~3u; cur[k] = run; run += v; }
+        __syncwarp();
+    }
+    const uint32_t mask = sfq_gen_mask(level);
+    const uint32_t solid = meta->solid, nrec = meta->nrec;
+    const uint64_t line0 = meta->line0;
+    uint2 *bins = reinterpret_cast<uint2 *>(e2.gbins) + sfq_gbins_off(e2c[c].goff, c, gp_bits);
+
+    uint32_t gbase = 0;                  // bases coded so far (g_genofs_count before this window)
+    uint64_t ns_index = 0, nn_index = 0;
+    uint32_t n_byte = 0;
+    uint32_t status = SFQ_OK, status_arg = 0;
+
+    for (uint32_t r = 0; r < nrec && status == SFQ_OK; r++) {
+        const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+        if (r + 2 < nrec && lane < 4) sfq_prefetch(text + ls[line0 + 4ull * (r + 2)] + 128u * lane);   // the record after next
+        uint32_t prev = 0x007616c7u;                                           // gens.cpp:139
+        for (uint32_t w0 = 0; w0 < v.llen && status == SFQ_OK; w0 += 32 * SFQ_GM_BATCH) {
+            uint32_t gg[SFQ_GM_BATCH], qq[SFQ_GM_BATCH];
+#pragma unroll
+            for (int j = 0; j < SFQ_GM_BATCH; j++) {                            // the batch's text: all loads in flight together
+                const uint32_t i = w0 + 32u * j + lane;
+                const bool active = i < v.llen;
+                gg[j] = active ? v.seq[i] : (uint32_t)'A';
+                qq[j] = active ? (i < v.qlen ? v.qual[i] : 40u) : (uint32_t)'I';            // gens.cpp:153
+            }
+#pragma unroll
+            for (int j = 0; j < SFQ_GM_BATCH; j++) {
+                const uint32_t wj = w0 + 32u * j;
+                if (wj < v.llen && status == SFQ_OK) {
+                    const bool active = wj + lane < v.llen;
+                    const uint32_t g = gg[j];
+                    uint32_t n = sfq_gencode((uint8_t)g);
+                    const bool bad_n = n == 4u;
+                    const unsigned errb = __ballot_sync(FULL, n > 4u);
+                    if (n > 3u) n = 0;
+                    const bool bad_q = qq[j] == (uint32_t)'!';
+                    unsigned excb = __ballot_sync(FULL, active && (bad_n || bad_q));
+                    if (errb) { status = SFQ_E_BASE; status_arg = __shfl_sync(FULL, g, __ffs(errb) - 1); }
+                    while (excb && status == SFQ_OK) {                         // exception lists, in base order (gens.cpp:91-114); rare
+                        const int b = __ffs(excb) - 1;
+                        excb &= excb - 1;
+                        const bool bn = __shfl_sync(FULL, (int)bad_n, b) != 0, bq = __shfl_sync(FULL, (int)bad_q, b) != 0;
+                        const uint32_t gb = __shfl_sync(FULL, g, b);
+                        const uint64_t genofs = (uint64_t)gbase + (uint32_t)b + 1u;
+                        if (!bn) { if (lane == 0) xnn.put(genofs - nn_index); nn_index = genofs; }
+                        else {
+                            if (!n_byte) n_byte = gb;
+                            if (gb != n_byte) { status = SFQ_E_NBYTE; status_arg = gb; break; }
+                            if (!bq) { if (lane == 0) xns.put(genofs - ns_index); ns_index = genofs; }
+                        }
+                    }
+                    const uint32_t ctx = sfq_gen_window_ctx(n, lane, prev, mask);
+                    if (status == SFQ_OK) {
+                        const unsigned am = __ballot_sync(FULL, active);
+                        const uint32_t p = sfq_gp_of(ctx, gp_bits);
+                        unsigned peers = sfq_match_bits(p, gp_bits, am);
+                        if (!active) peers = 1u << lane;
+                        const uint32_t rank = __popc(peers & lt), k = __popc(peers);
+                        uint32_t at0 = 0;
+                        if (active && rank == 0) { at0 = cur[p]; cur[p] = at0 + k; }
+                        at0 = __shfl_sync(FULL, at0, __ffs(peers) - 1);
+                        const uint32_t at = at0 + rank;
+                        const uint2 e = make_uint2((gbase + lane) | (n << 24), ctx);
+                        if (!staged) { if (active) bins[at] = e; }
+                        else {
+                            // the rows (4 entries = one sector) this window's group of partition p touches: entries of its first
+                            // row join what earlier windows staged; rows it fills alone go out directly (four lanes, one sector);
+                            // an unfinished last row is staged once the first one has left
+                            const uint32_t row = at >> 2, first = at0 >> 2, last = (at0 + k - 1u) >> 2;
+                            const bool last_done = ((at0 + k - 1u) & 3u) == 3u;
+                            const bool in_first = active && row == first;
+                            const bool direct = active && row != first && (row != last || last_done);
+                            const bool in_last = active && row != first && !direct;
+                            if (in_first) stage[4u * p + (at & 3u)] = e;
+                            if (direct) bins[at] = e;
+                            __syncwarp();
+                            if (in_first && (at & 3u) == 3u) {
+                                const uint4 *rowp = reinterpret_cast<const uint4 *>(stage + 4u * p);
+                                uint4 *dst = reinterpret_cast<uint4 *>(bins + (at - 3u));
+                                dst[0] = rowp[0]; dst[1] = rowp[1];
+                            }
+                            __syncwarp();
+                            if (in_last) stage[4u * p + (at & 3u)] = e;
+                        }
+                        gbase += min(32u, v.llen - wj);
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+    if (staged) {
+        for (uint32_t k = lane; k < gp; k += 32) {                             // unfinished rows, and the end offsets for k_gen_replay
+            const uint32_t endk = cur[k];
+            for (uint32_t q = endk & ~3u; q < endk; q++) bins[q] = stage[4u * k + (q & 3u)];
+            gc[k] = endk;
+        }
+    }
+    if (lane == 0) {
+        bool ovf = false;
+        ar->size[SFQ_S_GEN_NS] = xns.close(ovf);
+        ar->size[SFQ_S_GEN_NN] = xnn.close(ovf);
+        if (status == SFQ_OK && ovf) status = SFQ_E_CAP;
+        meta->n_byte = (n_byte && n_byte != 'N') ? (uint8_t)n_byte : 0;        // gens.cpp:103-104
+        if (status != SFQ_OK && meta->status == SFQ_OK) { meta->status = status; meta->status_arg = status_arg; }
+    }
+}
+
+// One warp per (chunk, partition), handed out through e2.ctr[4] in chunk-major order, SFQ_GR_BATCH at a time (the
+// partitions of a chunk run close together in time, so the chunk's step array fills in L2 before it goes out to DRAM).
+__global__ void __launch_bounds__(32 * SFQ_GR_WARPS)
+k_gen_replay(SfqChunkMeta *metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, uint32_t nchunks) {
+    extern __shared__ uint4 gr_smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint2 *tab = reinterpret_cast<uint2 *>(gr_smem) + (size_t)warp * SFQ_GP_SLOTS;                       // (key, freq) slots
+    uint8_t *owner = reinterpret_cast<uint8_t *>(reinterpret_cast<uint2 *>(gr_smem) + (size_t)SFQ_GR_WARPS * SFQ_GP_SLOTS) + (size_t)warp * SFQ_GP_SLOTS;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t gp_bits = e2.gp_bits, gp = 1u << gp_bits;
+    const uint64_t nitems = (uint64_t)nchunks << gp_bits;
+    for (;;) {
+        uint32_t item0 = 0;
+        if (lane == 0) item0 = atomicAdd(e2.ctr + 4, SFQ_GR_BATCH);
+        item0 = __shfl_sync(FULL, item0, 0);
+        if (item0 >= nitems) break;
+        for (uint32_t item = item0; item < item0 + SFQ_GR_BATCH && item < nitems; item++) {
+            const uint32_t c = item >> gp_bits, p = item & (gp - 1u);
+            if (metas[c].status != SFQ_OK) continue;
+            const uint32_t *ends = e2.gcnt + (size_t)c * gp;
+            const uint32_t start = p ? (ends[p - 1] + 3u) & ~3u : 0u, end = ends[p];
+            if (end <= start) continue;
+            {   // empty table
+                uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+#pragma unroll 4
+                for (uint32_t k = lane; k < SFQ_GP_SLOTS / 2; k += 32) t4[k] = make_uint4(0, 0, 0, 0);
+                __syncwarp();
+            }
+            const uint2 *bins = reinterpret_cast<const uint2 *>(e2.gbins) + sfq_gbins_off(e2c[c].goff, c, gp_bits);
+            uint32_t *gsteps = e2.gsteps + e2c[c].goff;
+            uint32_t used = 0;
+            bool full = false;
+            uint2 nxt = start + lane < end ? bins[start + lane] : make_uint2(0, 0);
+            for (uint32_t w0 = start; w0 < end; w0 += 32) {
+                const bool active = w0 + lane < end;
+                const uint2 e = nxt;
+                if (w0 + 32 + lane < end) nxt = bins[w0 + 32 + lane];             // the next window's entries travel during this one
+                const uint32_t ctx = e.y, n = (e.x >> 24) & 3u, pos = e.x & 0xffffffu;
+                const uint32_t key = ctx + 1u;
+                // every lane finds or claims the slot of its context by itself
+                uint32_t slot = sfq_gp_slot(ctx, gp_bits);
+                bool fresh = false;
+                if (active) {
+                    for (uint32_t probes = 0;; probes++) {
+                        uint32_t k = reinterpret_cast<volatile uint2 *>(tab)[slot].x;
+                        if (k == 0u) { k = atomicCAS(&tab[slot].x, 0u, key); if (k == 0u) { fresh = true; break; } }
+                        if (k == key) break;
+                        if (probes >= SFQ_GP_SLOTS) { full = true; break; }
+                        slot = (slot + 1u) & (SFQ_GP_SLOTS - 1u);
+                    }
+                    owner[slot] = (uint8_t)lane;
+                }
+                used += (uint32_t)__popc(__ballot_sync(FULL, fresh));             // (warp-uniform count of occupied slots)
+                if (used > SFQ_GP_SLOTS - 64u) full = true;                         // nearly full: probes get long; rerun with more partitions
+                __syncwarp();
+                const bool meet = active && owner[slot] != (uint8_t)lane;         // somebody else of this window is in my slot: same context
+                uint32_t step;
+                if (!__any_sync(FULL, meet)) {
+                    uint32_t fv = fresh ? 0x03030303u : tab[slot].y;
+                    const uint32_t f0 = fv & 0xff, f1 = (fv >> 8) & 0xff, f2 = (fv >> 16) & 0xff, f3 = fv >> 24;
+                    const uint32_t cum = (n > 0 ? f0 : 0) + (n > 1 ? f1 : 0) + (n > 2 ? f2 : 0);
+                    step = sfq_gstep_pack(cum, (fv >> (8 * n)) & 0xffu, f0 + f1 + f2 + f3);
+                    if (active) tab[slot].y = sfq_b2_update(fv, n);
+                } else {
+                    // ordered path: lanes sharing a slot (= a context) form a group, replayed in lane order
+                    const unsigned am = __ballot_sync(FULL, active);
+                    const unsigned peers = active ? __match_any_sync(am, slot) : 1u << lane;
+                    const uint32_t rank = __popc(peers & lt), gsize = __popc(peers);
+                    // the group's start state: the table's, or the initial one if the slot was claimed in this window
+                    const unsigned freshb = __ballot_sync(FULL, fresh);
+                    uint32_t fv = (freshb & peers) ? 0x03030303u : (active ? tab[slot].y : 0u);
+                    const uint32_t maxrank = __reduce_max_sync(FULL, active ? rank : 0u);
+                    step = 0;
+                    for (uint32_t rr = 0; rr <= maxrank; rr++) {
+                        if (rank == rr) {
+                            const uint32_t f0 = fv & 0xff, f1 = (fv >> 8) & 0xff, f2 = (fv >> 16) & 0xff, f3 = fv >> 24;
+                            const uint32_t cum = (n > 0 ? f0 : 0) + (n > 1 ? f1 : 0) + (n > 2 ? f2 : 0);
+                            step = sfq_gstep_pack(cum, (fv >> (8 * n)) & 0xffu, f0 + f1 + f2 + f3);
+                            fv = sfq_b2_update(fv, n);
+                        }
+                        if (rr < maxrank) {
+                            const int src = __fns(peers, 0, rr + 1);               // lane holding rank rr of my group
+                            const uint32_t nv = __shfl_sync(FULL, fv, src < 0 ? 0 : src);
+                            if (rank > rr) fv = nv;
+                        }
+                    }
+                    if (active && rank + 1 == gsize) tab[slot].y = fv;
+                }
+                if (active) gsteps[pos] = step;
+                __syncwarp();
+            }
+            if (__any_sync(FULL, full)) { if (lane == 0) atomicCAS(&metas[c].status, (uint32_t)SFQ_OK, (uint32_t)SFQ_E_TABLE); }
+            else if (lane == 0) atomicAdd(&metas[c].g_used, used);
+        }
+    }
+}
+
 // ============================================================================ qlt, phase 1
 // Context of position i from b[i-1], b[i-2], b[i-3] and the running sum of drops (qlts.hpp:52-74,
 // qlts.cpp:109-134).  Lanes = 32 consecutive positions of a record.
@@ -525,6 +862,138 @@ k_qlt_scatter(const SfqChunkMeta *__restrict__ metas, SfqEnc2Ws e2, const SfqEnc
                 const unsigned eb = __ballot_sync(FULL, active && b >= 63u);
                 if (active && b >= 63u) esorted[ecur + __popc(eb & lt)] = p | (b << 24);
                 ecur += __popc(eb);
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// The same stable counting sort in two levels, each of which writes few, short-lived streams:
+//   k_qlt_part1   one warp per chunk walks the positions in order and appends (position | symbol << 24, context >> 8)
+//                 to the list of the context's LOW byte - 256 lists whose starts k_qlt_scan has already laid out
+//                 (thread t of the scan owns contexts t, t + 256, ...: their segments are contiguous).  Entries are
+//                 staged four at a time in shared memory, so DRAM sees whole 32-byte rows.  The lists live in the
+//                 memory of the coding steps (8 bytes per quality), which are only written after level 2 has read them
+//   k_qlt_part2   one warp per (chunk, low byte): 256 cursors (the segments of the contexts with this low byte) in
+//                 shared memory; the list's entries reach their final places inside the list's own region of `sorted`
+// Against k_qlt_scatter's one pass over 65 536 cursors in global memory (a DRAM round trip and two partial sectors
+// per quality) this moves 23 bytes per quality in streams.
+#define SFQ_QP_BATCH 8u
+__global__ void __launch_bounds__(32)
+k_qlt_part1(const SfqChunkMeta *__restrict__ metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, uint32_t nchunks) {
+    __shared__ uint2 stage[256 * 4];
+    __shared__ uint32_t cur[256], lo[256];
+    const uint32_t c = blockIdx.x, lane = threadIdx.x;
+    if (c >= nchunks) return;
+    const SfqChunkMeta *meta = &metas[c];
+    if (meta->status != SFQ_OK) return;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint16_t *qkey = e2.qkey + e2c[c].qoff;
+    const uint8_t *qb = e2.qb + e2c[c].qoff;
+    uint2 *tmp = reinterpret_cast<uint2 *>(e2.qsteps + e2c[c].qoff);
+    uint32_t *esorted = e2.esorted + e2c[c].eoff;
+    const uint32_t *cnt = e2.cnt + (size_t)c * SFQ_Q_CNT;
+    for (uint32_t t = lane; t < 256; t += 32) { const uint32_t v = cnt[t]; cur[t] = v; lo[t] = v; }     // start of context t = start of list t
+    __syncwarp();
+    const uint32_t n = meta->nquals;
+    uint32_t ecur = 0;
+    constexpr int B = 8;
+    for (uint32_t p0 = 0; p0 < n; p0 += 32 * B) {
+        uint32_t keys[B], bs[B];
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            const uint32_t p = p0 + 32u * j + lane;
+            keys[j] = p < n ? (uint32_t)qkey[p] : 0u;
+            bs[j] = p < n ? (uint32_t)qb[p] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            const uint32_t p = p0 + 32u * j + lane;
+            if (p0 + 32u * j < n) {
+                const bool active = p < n;
+                const uint32_t ctx = keys[j], b = bs[j], t = ctx & 255u;
+                const unsigned am = __ballot_sync(FULL, active);
+                unsigned peers = sfq_match_bits(t, 8, am);
+                if (!active) peers = 1u << lane;
+                const uint32_t rank = __popc(peers & lt), k = __popc(peers);
+                uint32_t at0 = 0;
+                if (active && rank == 0) { at0 = cur[t]; cur[t] = at0 + k; }
+                at0 = __shfl_sync(FULL, at0, __ffs(peers) - 1);
+                const uint32_t at = at0 + rank;
+                const uint2 e = make_uint2(p | ((b < 63u ? b : 63u) << 24), ctx >> 8);
+                // rows of four entries (one sector), as in k_gen_scatter; a list may start or end inside a row
+                const uint32_t row = at >> 2, first = at0 >> 2, last = (at0 + k - 1u) >> 2;
+                const bool last_done = ((at0 + k - 1u) & 3u) == 3u;
+                const bool in_first = active && row == first;
+                const bool direct = active && row != first && (row != last || last_done);
+                const bool in_last = active && row != first && !direct;
+                if (in_first) stage[4u * t + (at & 3u)] = e;
+                if (direct) tmp[at] = e;
+                __syncwarp();
+                if (in_first && (at & 3u) == 3u) {
+                    const uint32_t from = max(at - 3u, lo[t]);
+                    if (from == at - 3u) {
+                        const uint4 *rowp = reinterpret_cast<const uint4 *>(stage + 4u * t);
+                        uint4 *dst = reinterpret_cast<uint4 *>(tmp + from);
+                        dst[0] = rowp[0]; dst[1] = rowp[1];
+                    } else for (uint32_t q = from; q <= at; q++) tmp[q] = stage[4u * t + (q & 3u)];
+                }
+                __syncwarp();
+                if (in_last) stage[4u * t + (at & 3u)] = e;
+                const unsigned eb = __ballot_sync(FULL, active && b >= 63u);          // escapes, in stream order (qlts.cpp:120-125)
+                if (active && b >= 63u) esorted[ecur + __popc(eb & lt)] = p | (b << 24);
+                ecur += __popc(eb);
+                __syncwarp();
+            }
+        }
+    }
+    for (uint32_t t = lane; t < 256; t += 32) {                                       // unfinished rows
+        const uint32_t endt = cur[t];
+        for (uint32_t q = max(endt & ~3u, lo[t]); q < endt; q++) tmp[q] = stage[4u * t + (q & 3u)];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_qlt_part2(const SfqChunkMeta *__restrict__ metas, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, uint32_t nchunks) {
+    __shared__ uint32_t curs[8][256];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t *cur = curs[warp];
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint64_t nitems = (uint64_t)nchunks << 8;
+    for (;;) {
+        uint32_t item0 = 0;
+        if (lane == 0) item0 = atomicAdd(e2.ctr + 5, SFQ_QP_BATCH);
+        item0 = __shfl_sync(FULL, item0, 0);
+        if (item0 >= nitems) break;
+        for (uint32_t item = item0; item < item0 + SFQ_QP_BATCH && item < nitems; item++) {
+            const uint32_t c = item >> 8, t = item & 255u;
+            if (metas[c].status != SFQ_OK) continue;
+            const uint32_t *cnt = e2.cnt + (size_t)c * SFQ_Q_CNT;
+            // list t = the segments of contexts t, t + 256, ...: it starts where context t starts and ends where list t + 1
+            // starts (the last one at the chunk's quality count)
+            const uint32_t start = cnt[t], end = t == 255u ? metas[c].nquals : cnt[t + 1u];
+            if (end <= start) continue;
+            __syncwarp();
+            for (uint32_t k = lane; k < 256; k += 32) cur[k] = cnt[(k << 8) + t];
+            __syncwarp();
+            const uint2 *tmp = reinterpret_cast<const uint2 *>(e2.qsteps + e2c[c].qoff);
+            uint32_t *sorted = e2.sorted + e2c[c].qoff;
+            uint2 nxt = start + lane < end ? tmp[start + lane] : make_uint2(0, 0);
+            for (uint32_t w0 = start; w0 < end; w0 += 32) {
+                const bool active = w0 + lane < end;
+                const uint2 e = nxt;
+                if (w0 + 32 + lane < end) nxt = tmp[w0 + 32 + lane];
+                const uint32_t k = e.y & 255u;
+                const unsigned am = __ballot_sync(FULL, active);
+                unsigned peers = sfq_match_bits(k, 8, am);
+                if (!active) peers = 1u << lane;
+                const uint32_t rank = __popc(peers & lt);
+                uint32_t at = 0;
+                if (active && rank == 0) { at = cur[k]; cur[k] = at + (uint32_t)__popc(peers); }
+                at = __shfl_sync(FULL, at, __ffs(peers) - 1) + rank;
+                if (active) sorted[at] = e.x;
                 __syncwarp();
             }
         }

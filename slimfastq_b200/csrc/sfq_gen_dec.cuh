@@ -64,7 +64,7 @@ k_gen_decode32(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ d
             if (w_) {                                                                                        \
                 if (r >= nrec) { live = false; w_ = false; }                                                 \
                 else {                                                                                       \
-                    llen = llen_tab[r];                                                                      \
+                    llen = sfq_coded_len(llen_tab[r]);                                                       \
                     if (llen) {                                                                              \
                         i = 0; g = bases + boff_tab[r]; last = 0x007616c7u; pj = 4; w_ = false;               \
                         if (!dense) {                                                                        \

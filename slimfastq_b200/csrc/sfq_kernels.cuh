@@ -159,6 +159,12 @@ k_encode(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqC
     else sfq_rec_encode_chunk(text, ls, m, pw, arena_buf, &arenas[c]);
 }
 
+// `rec.first` (recs.cpp:68-75) = id line of the first record that went through the models; none if every record was oversized
+__device__ __forceinline__ uint32_t sfq_rec_first_len(const SfqChunkMeta &m, const uint64_t *ls) {
+    if (m.first_coded >= m.nrec) return 0;
+    const uint64_t *l = ls + m.line0 + 4ull * m.first_coded;
+    return (uint32_t)(l[1] - l[0] - 2);
+}
 // Blob sizes of a wave and their exclusive prefix from *cursor (single CTA).
 __global__ void __launch_bounds__(1024)
 k_blob_offsets(const SfqChunkMeta *__restrict__ metas, const SfqArena *__restrict__ arenas,
@@ -168,7 +174,7 @@ k_blob_offsets(const SfqChunkMeta *__restrict__ metas, const SfqArena *__restric
     const uint32_t lo = threadIdx.x * per, hi = lo + per < nchunks ? lo + per : nchunks;
     uint64_t s = 0;
     for (uint32_t c = lo; c < hi; c++) {
-        uint64_t b = sizeof(SfqBlobHeader) + (ls[metas[c].line0 + 1] - ls[metas[c].line0] - 2);
+        uint64_t b = sizeof(SfqBlobHeader) + sfq_rec_first_len(metas[c], ls);
         for (int k = 0; k < SFQ_NSTREAMS; k++) b += arenas[c].size[k];
         blob_off[c] = b;
         s += b;
@@ -194,12 +200,13 @@ k_pack(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, const 
     const SfqChunkMeta &m = metas[c];
     const SfqArena &a = arenas[c];
     __shared__ SfqBlobHeader h;
-    const uint32_t rfl = (uint32_t)(ls[m.line0 + 1] - ls[m.line0] - 2);
+    const uint32_t rfl = sfq_rec_first_len(m, ls);
     if (threadIdx.x == 0) {
         h.magic = SFQ_BLOB_MAGIC; h.level = (uint32_t)level; h.text_len = m.text_len; h.out_len = m.out_len;
         h.nrec = m.nrec; h.nbases = m.nbases; h.nquals = m.nquals; h.hdr_bytes = m.hdr_bytes; h.llen = m.llen;
         h.solid = m.solid; h.two_id = m.two_id; h.n_byte = m.n_byte; h.pad = 0; h.extra_hi = m.extra_hi;
         h.rec_first_len = rfl; h.q_used = m.q_used; h.g_used = m.g_used;
+        h.nbig = m.nbig; h.big_bases = m.big_bases; h.big_quals = m.big_quals; h.big_hdr = m.big_hdr;
         for (int k = 0; k < SFQ_NSTREAMS; k++) h.ssize[k] = a.size[k];
     }
     __syncthreads();
@@ -210,7 +217,7 @@ k_pack(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, const 
     const uint8_t *hp = reinterpret_cast<const uint8_t *>(&h);
     for (uint32_t i = threadIdx.x; i < sizeof(SfqBlobHeader); i += blockDim.x) out[o + i] = hp[i];
     o += sizeof(SfqBlobHeader);
-    const uint8_t *rf = text + ls[m.line0] + 1;
+    const uint8_t *rf = text + (rfl ? ls[m.line0 + 4ull * m.first_coded] + 1 : 0);
     for (uint32_t i = threadIdx.x; i < rfl; i += blockDim.x) out[o + i] = rf[i];
     o += rfl;
     for (int k = 0; k < SFQ_NSTREAMS; k++) {
@@ -231,6 +238,7 @@ struct SfqDecChunk {
     int32_t  level;
     uint64_t rec_base;              // first slot of the chunk in the per-record tables
     uint64_t base_plane, qual_plane, hdr_plane;   // plane offsets of the chunk
+    uint64_t base_cap, qual_cap, hdr_cap;         // bytes of each plane that belong to the chunk
 };
 struct SfqRecTables {
     uint32_t *llen, *qlen, *hlen;
@@ -243,19 +251,24 @@ struct SfqRecTables {
 
 __global__ void __launch_bounds__(32)
 k_decode_usr(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
-             SfqWorkspace ws, SfqRecTables t, uint32_t nchunks) {
+             SfqWorkspace ws, SfqRecTables t, uint8_t *bases, uint8_t *quals, uint8_t *hdrs, uint32_t nchunks) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     const SfqDecChunk &d = dc[c];
     SfqChunkMeta *m = &metas[c];
     uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
     sfq_usr_decode_chunk(in, d.ssize, d.soff, m, pw, t.llen + d.rec_base, t.qlen + d.rec_base,
-                         t.pfg + d.rec_base, t.pfq + d.rec_base);
-    uint64_t b = d.base_plane, q = d.qual_plane;
+                         t.pfg + d.rec_base, t.pfq + d.rec_base, t.hlen + d.rec_base, t.hoff + d.rec_base, t.boff + d.rec_base, t.qoff + d.rec_base,
+                         hdrs + d.hdr_plane, d.hdr_cap, bases + d.base_plane, d.base_cap, quals + d.qual_plane, d.qual_cap);
+    // oversized records' lines lie at the front of the chunk's planes, the coded records follow
+    uint64_t b = d.base_plane + m->big_bases, q = d.qual_plane + m->big_quals;
     for (uint32_t r = 0; r < m->nrec; r++) {
-        t.boff[d.rec_base + r] = b; t.qoff[d.rec_base + r] = q;
-        b += t.llen[d.rec_base + r]; q += t.qlen[d.rec_base + r];
+        const uint64_t k = d.rec_base + r;
+        if (t.llen[k] & SFQ_BIG_BIT) { t.boff[k] += d.base_plane; t.qoff[k] += d.qual_plane; continue; }
+        t.boff[k] = b; t.qoff[k] = q;
+        b += t.llen[k]; q += t.qlen[k];
     }
+    if (m->status == SFQ_OK && (b > d.base_plane + d.base_cap || q > d.qual_plane + d.qual_cap)) m->status = SFQ_E_CORRUPT;
 }
 
 // After the base decoder of a wave: apply gen.Ns / gen.Nn to the decoded base planes (one thread per chunk).
@@ -266,7 +279,8 @@ k_gen_exceptions(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__
     if (c >= nchunks || metas[c].status != SFQ_OK) return;
     const SfqDecChunk &d = dc[c];
     if (d.ssize[SFQ_S_GEN_NS] == 0 && d.ssize[SFQ_S_GEN_NN] == 0) return;
-    sfq_gen_apply_exceptions(in, d.ssize, d.soff, &metas[c], ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS, bases + d.base_plane);
+    // (positions count coded bases; the coded records' lines follow the oversized records' at the front of the plane)
+    sfq_gen_apply_exceptions(in, d.ssize, d.soff, &metas[c], ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS, bases + d.base_plane + metas[c].big_bases);
 }
 
 #define SFQ_DEC_MAXW 4                 // warps per CTA of the thread-per-chunk decoders (1..4; more per CTA = fewer, fatter CTAs)
@@ -314,6 +328,8 @@ k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, Sfq
 // chunk, exclusive prefix over all chunks of the container, then the offset of every record.
 __device__ __forceinline__ uint64_t sfq_rec_out_len(const SfqChunkMeta &m, const SfqRecTables &t, uint64_t k) {
     const uint32_t s = m.solid ? 1 : 0;
+    // oversized: '@' id '\n' bases '\n' '+'line '\n' quals '\n', where hlen counts id + '\n' + '+'line
+    if (t.hlen[k] & SFQ_BIG_BIT) return 4ull + (t.hlen[k] & ~SFQ_BIG_BIT) + (t.llen[k] & ~SFQ_BIG_BIT) + (t.qlen[k] & ~SFQ_BIG_BIT);
     return 1ull + t.hlen[k] + 1 + s + t.llen[k] + 1 + 1 + (m.two_id ? t.hlen[k] : 0) + 1 + s + t.qlen[k] + 1;
 }
 __global__ void __launch_bounds__(32)
@@ -372,6 +388,28 @@ k_assemble(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ 
     const uint8_t *h = hdrs + t.hoff[k], *b = bases + t.boff[k], *q = quals + t.qoff[k];
     const uint8_t nbyte = m.n_byte ? m.n_byte : (uint8_t)'N';
     uint8_t *o = out + t.ooff[k];
+    if (hlen & SFQ_BIG_BIT) {
+        // an oversized record, verbatim (usrs.cpp:473-485): the block holds the id line, '\n', the '+' line
+        const uint32_t hb = hlen & ~SFQ_BIG_BIT, bl = llen & ~SFQ_BIG_BIT, ql = qlen & ~SFQ_BIG_BIT;
+        uint32_t cut = hb;                                   // position of the '\n' that ends the id line
+        for (uint32_t i0 = 0; i0 < hb && cut == hb; i0 += 32) {
+            const unsigned nl = __ballot_sync(0xffffffffu, i0 + lane < hb && h[i0 + lane] == '\n');
+            if (nl) cut = i0 + (uint32_t)__ffs(nl) - 1;
+        }
+        if (lane == 0) o[0] = '@';
+        for (uint32_t i = lane; i <= cut && i < hb; i += 32) o[1 + i] = h[i];       // id and its newline
+        o += 1 + cut + 1;
+        for (uint32_t i = lane; i < bl; i += 32) o[i] = b[i];
+        if (lane == 0) o[bl] = '\n';
+        o += bl + 1;
+        const uint32_t pl = hb - cut - 1;
+        for (uint32_t i = lane; i < pl; i += 32) o[i] = h[cut + 1 + i];
+        if (lane == 0) o[pl] = '\n';
+        o += pl + 1;
+        for (uint32_t i = lane; i < ql; i += 32) o[i] = q[i];
+        if (lane == 0) o[ql] = '\n';
+        return;
+    }
     if (lane == 0) o[0] = '@';
     for (uint32_t i = lane; i < hlen; i += 32) o[1 + i] = h[i];
     o += 1 + hlen;

@@ -33,6 +33,12 @@ static inline uint32_t sfq_gen_hbits(int level, uint64_t max_bases, uint32_t gro
     uint32_t b = sfq_ceil_log2(max_bases * 2 + 16) + grow;
     return b < 10 ? 10 : b > 27 ? 27 : b;
 }
+// Two-phase encoder: partitions of the base-context space per chunk, for at most ~768 bases per partition (k_gen_replay keeps
+// a partition's contexts in a 2048-slot table in shared memory); a table that still fills up reruns with twice as many.
+static inline uint32_t sfq_gen_gp_bits(uint64_t max_bases, uint32_t grow) {
+    uint32_t b = sfq_ceil_log2((max_bases + 767) / 768) + grow;
+    return b > 14 ? 14 : b;
+}
 static inline uint64_t sfq_gtable_bytes(int level, uint32_t hbits) {
     return level <= 1 ? (1ull << 18) * 4 : (1ull << hbits) * 8;
 }
@@ -64,6 +70,10 @@ static inline void sfq_arena_layout(const SfqChunkMeta *m, uint32_t grow, uint64
     cap[SFQ_S_USR_XQ] = 8ull * m->nrec * g + 256;
     cap[SFQ_S_USR_PFG] = 4ull * m->nrec * g + 256;
     cap[SFQ_S_USR_PFQ] = 4ull * m->nrec * g + 256;
+    // oversized records, character by character through an adaptive 256-symbol model: rarely more than a byte per character
+    cap[SFQ_S_USR_LREC] = m->nbig ? ((uint64_t)m->big_hdr + 16ull * m->nbig) * g * 2 + 256 : 64;
+    cap[SFQ_S_USR_LGEN] = m->nbig ? ((uint64_t)m->big_bases + 2ull * m->nbig) * g * 2 + 256 : 64;
+    cap[SFQ_S_USR_LQLT] = m->nbig ? ((uint64_t)m->big_quals + 2ull * m->nbig) * g * 2 + 256 : 64;
     uint64_t o = base;
     for (int k = 0; k < SFQ_NSTREAMS; k++) {
         a->off[k] = o;

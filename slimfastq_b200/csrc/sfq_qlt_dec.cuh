@@ -206,7 +206,7 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
         while (__any_sync(FULL, w_)) {                                                       \
             if (w_) {                                                                        \
                 if (r >= nrec) { live = false; w_ = false; }                                 \
-                else { qlen = qlen_tab[r]; if (qlen) { i = 0; w_ = false; } else r++; }       \
+                else { qlen = sfq_coded_len(qlen_tab[r]); if (qlen) { i = 0; w_ = false; } else r++; } \
             }                                                                                \
         }                                                                                    \
     }

@@ -277,7 +277,7 @@ __device__ __forceinline__ void sfq_qlt_decode_group(const uint8_t *in, const ui
     tab.init(qtable, nent, level <= 1 || nent >= 65536u);
     bool full = false;
     for (uint32_t r = 0; r < meta->nrec && !full; r++) {
-        const uint32_t qlen = qlen_tab[r];
+        const uint32_t qlen = sfq_coded_len(qlen_tab[r]);
         uint8_t *q = quals + qoff_tab[r];
         SfqQCtx c; c.reset();
         for (uint32_t i = 0; i < qlen; i++) {

@@ -10,14 +10,21 @@
 #pragma once
 #include "sfq_coder.cuh"
 
+// Decoder-side per-record length tables: an oversized record (decoded verbatim by sfq_usr_decode_chunk) carries this bit in
+// its three length entries; the model decoders see length 0 for it.
+#define SFQ_BIG_BIT 0x80000000u
+SFQ_HD uint32_t sfq_coded_len(uint32_t table_entry) { return (table_entry & SFQ_BIG_BIT) ? 0u : table_entry; }
+
 // Geometry of record r of a chunk, read from the line-start table built by the scan kernel.
 // line_start[L] = offset of the first byte of line L; line_start[nlines] = end of text.
 struct SfqRecView {
     const uint8_t *hdr;  uint32_t hlen;     // header without '@' and '\n'
-    const uint8_t *seq;  uint32_t llen;     // coded bases (SOLiD prefix stripped)
-    const uint8_t *qual; uint32_t qlen;     // coded qualities (SOLiD prefix stripped)
+    const uint8_t *seq;  uint32_t llen;     // coded bases (SOLiD prefix stripped); 0 for an oversized record
+    const uint8_t *qual; uint32_t qlen;     // coded qualities (SOLiD prefix stripped); 0 for an oversized record
     uint32_t plus_len;                      // '+' line length including the '+'
     uint8_t pf_gen, pf_qlt;                 // SOLiD prefix chars (usrs.cpp:324-329,358-363)
+    bool big;                               // oversized (usrs.hpp:34-36): not coded by the models; raw_llen / raw_qlen = what the lines measure
+    uint32_t raw_llen, raw_qlen;
 };
 SFQ_HD SfqRecView sfq_rec_view(const uint8_t *text, const uint64_t *ls, uint64_t line0, uint32_t r, uint32_t solid) {
     const uint64_t *l = ls + line0 + 4ull * r;
@@ -33,7 +40,9 @@ SFQ_HD SfqRecView sfq_rec_view(const uint8_t *text, const uint64_t *ls, uint64_t
         v.seq++; v.qual++;
         sl = sl ? sl - 1 : 0; ql = ql ? ql - 1 : 0;
     }
-    v.llen = sl; v.qlen = ql;
+    v.raw_llen = sl; v.raw_qlen = ql;
+    v.big = v.hlen >= SFQ_MAX_ID_LLEN - 1 || sl >= SFQ_MAX_GN_LLEN - 1 || ql >= SFQ_MAX_GN_LLEN - 1;
+    v.llen = v.big ? 0u : sl; v.qlen = v.big ? 0u : ql;
     return v;
 }
 
@@ -333,7 +342,7 @@ SFQ_HD uint32_t sfq_gen_decode_loop(SfqByteSrc &src, SfqGenBuckets &tab, uint32_
     for (int i = 0; i < 8; i++) code = (code << 8) | src.next();               // coder.hpp:44-48
     const uint32_t nrec = meta->nrec;
     for (uint32_t r = 0; r < nrec; r++) {
-        const uint32_t llen = llen_tab[r];
+        const uint32_t llen = sfq_coded_len(llen_tab[r]);
         uint8_t *g = bases + boff_tab[r];
         uint32_t last = 0x007616c7u;
         uint32_t bk = DENSE ? 0u : tab.home(last & mask), bkn = 0;
@@ -490,7 +499,7 @@ SFQ_HDN void sfq_qlt_decode_chunk(const uint8_t *in, const uint32_t *ssize, cons
     rc.start(in + soff[SFQ_S_QLT], ssize[SFQ_S_QLT]);
     SfqPower ex; ex.m = pwpool + (size_t)SFQ_PW_QEX * SFQ_PW_WORDS;
     for (uint32_t r = 0; r < meta->nrec; r++) {
-        const uint32_t qlen = qlen_tab[r];
+        const uint32_t qlen = sfq_coded_len(qlen_tab[r]);
         uint8_t *q = quals + qoff_tab[r];
         SfqQCtx c; c.reset();
         for (uint32_t i = 0; i < qlen; i++) {
@@ -580,7 +589,10 @@ SFQ_HDN void sfq_rec_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
                                   uint32_t *pwpool, uint8_t *arena, SfqArena *ar) {
     SfqEnc rc;
     rc.start(arena + ar->off[SFQ_S_REC], ar->cap[SFQ_S_REC]);
-    SfqXSave x_rec, x_llen, x_qlen, x_sgen, x_sqlt;
+    SfqXSave x_rec, x_llen, x_qlen, x_sgen, x_sqlt, x_lrec, x_lgen, x_lqlt;
+    x_lrec.init(pwpool, SFQ_X_LREC, arena + ar->off[SFQ_S_USR_LREC], ar->cap[SFQ_S_USR_LREC]);
+    x_lgen.init(pwpool, SFQ_X_LGEN, arena + ar->off[SFQ_S_USR_LGEN], ar->cap[SFQ_S_USR_LGEN]);
+    x_lqlt.init(pwpool, SFQ_X_LQLT, arena + ar->off[SFQ_S_USR_LQLT], ar->cap[SFQ_S_USR_LQLT]);
     x_rec.init(pwpool, SFQ_X_REC, arena + ar->off[SFQ_S_REC_X], ar->cap[SFQ_S_REC_X]);
     x_llen.init(pwpool, SFQ_X_LLEN, arena + ar->off[SFQ_S_USR_X], ar->cap[SFQ_S_USR_X]);
     x_qlen.init(pwpool, SFQ_X_QLEN, arena + ar->off[SFQ_S_USR_XQ], ar->cap[SFQ_S_USR_XQ]);
@@ -596,14 +608,32 @@ SFQ_HDN void sfq_rec_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
     uint64_t x_index = 0;                              // RecBase::m_last.index
     const uint32_t solid = meta->solid;
     uint32_t m_llen = (uint32_t)meta->llen;            // UsrSave::m_llen (sticky), usrs.cpp:126-131
-    uint64_t i_llen = 0, i_qlen = 0, i_sgen = 0, i_sqlt = 0;
+    uint64_t i_llen = 0, i_qlen = 0, i_sgen = 0, i_sqlt = 0, i_long = 0;
     uint8_t pf_gen = 0, pf_qlt = 0;
     const uint8_t *prev = nullptr;
+    bool have_first = false;                           // RecBase::m_last.initilized
     uint32_t status = SFQ_OK, status_arg = 0;
 
     for (uint32_t r = 0; r < meta->nrec; r++) {
         const uint64_t recno = (uint64_t)r + 1;        // g_record_count
         const SfqRecView v = sfq_rec_view(text, ls, meta->line0, r, solid);
+        if (v.big) {
+            // get_oversized_record (usrs.cpp:269-301): the four lines, newlines included, verbatim: id line (without '@')
+            // and '+' line to usr.lrec, base line to usr.lgen, quality line to usr.lqlt.  When only the quality line is too
+            // long, get_record has already issued this record's prefix / length updates (usrs.cpp:337-364).
+            if (v.hlen < SFQ_MAX_ID_LLEN - 1 && v.raw_llen < SFQ_MAX_GN_LLEN - 1) {
+                if (solid && pf_gen != v.pf_gen && v.pf_gen) { x_sgen.put(recno - i_sgen); x_sgen.put_chr(v.pf_gen); i_sgen = recno; pf_gen = v.pf_gen; }
+                if (m_llen != v.raw_llen) { x_llen.put(recno - i_llen); x_llen.put((uint16_t)v.raw_llen); i_llen = recno; m_llen = (uint16_t)v.raw_llen; }
+                if (solid && pf_qlt != v.pf_qlt) { x_sqlt.put(recno - i_sqlt); x_sqlt.put_chr(v.pf_qlt); i_sqlt = recno; pf_qlt = v.pf_qlt; }
+            }
+            x_lrec.put(recno - i_long); i_long = recno;
+            const uint64_t *l = ls + meta->line0 + 4ull * r;
+            for (uint64_t k = l[0] + 1; k < l[1]; k++) x_lrec.put_chr(text[k]);
+            for (uint64_t k = l[1]; k < l[2]; k++) x_lgen.put_chr(text[k]);
+            for (uint64_t k = l[2]; k < l[3]; k++) x_lrec.put_chr(text[k]);
+            for (uint64_t k = l[3]; k < l[4]; k++) x_lqlt.put_chr(text[k]);
+            continue;
+        }
         // ---- framing exceptions, in get_record order (usrs.cpp:320-372)
         if (solid && pf_gen != v.pf_gen && v.pf_gen) {
             x_sgen.put(recno - i_sgen); x_sgen.put_chr(v.pf_gen); i_sgen = recno; pf_gen = v.pf_gen;
@@ -618,11 +648,12 @@ SFQ_HDN void sfq_rec_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
 
         // ---- header model (recs.cpp:277-372)
         const uint8_t *buf = v.hdr;
-        if (r == 0) {
+        if (!have_first) {
             // first header travels in clear as the `rec.first` info key (recs.cpp:68-75)
             if (v.hlen > 399) { status = SFQ_E_FIRSTHDR; break; }
+            have_first = true;
             imap = 0;
-            if (!sfq_map_space(smap[0], buf)) { status = SFQ_E_SEPS; status_arg = 1; break; }
+            if (!sfq_map_space(smap[0], buf)) { status = SFQ_E_SEPS; status_arg = (uint32_t)recno; break; }
             prev = buf;
             continue;
         }
@@ -686,6 +717,9 @@ SFQ_HDN void sfq_rec_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
     ar->size[SFQ_S_USR_XQ] = x_qlen.close(ovf);
     ar->size[SFQ_S_USR_PFG] = x_sgen.close(ovf);
     ar->size[SFQ_S_USR_PFQ] = x_sqlt.close(ovf);
+    ar->size[SFQ_S_USR_LREC] = x_lrec.close(ovf);
+    ar->size[SFQ_S_USR_LGEN] = x_lgen.close(ovf);
+    ar->size[SFQ_S_USR_LQLT] = x_lqlt.close(ovf);
     if (status == SFQ_OK && ovf) status = SFQ_E_CAP;
     if (status != SFQ_OK && meta->status == SFQ_OK) { meta->status = status; meta->status_arg = status_arg; }
 }
@@ -693,9 +727,62 @@ SFQ_HDN void sfq_rec_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
 // ---------------------------------------------------------------------------- usr decode
 // UsrLoad::update (usrs.cpp:471-510): replays usr.x / usr.x.q / usr.pfg / usr.pfq into per-record
 // tables so that the qlt, gen and rec decoders of the chunk can run concurrently afterwards.
+//
+// Oversized records (usr.lrec / usr.lgen / usr.lqlt, usrs.cpp:473-485) are decoded here, before anything else: their
+// lines go to the FRONT of the chunk's three planes (id line + '\n' + '+' line as one block in the header plane), their
+// table entries carry the lines' lengths with SFQ_BIG_BIT set - the model decoders skip such records, the assemble
+// kernel prints them verbatim.  `hdrs` / `bases` / `quals` = the chunk's plane regions, caps = bytes available there.
 SFQ_HDN void sfq_usr_decode_chunk(const uint8_t *in, const uint32_t *ssize, const uint64_t *soff,
                                   SfqChunkMeta *meta, uint32_t *pwpool,
-                                  uint32_t *llen_tab, uint32_t *qlen_tab, uint8_t *pfg_tab, uint8_t *pfq_tab) {
+                                  uint32_t *llen_tab, uint32_t *qlen_tab, uint8_t *pfg_tab, uint8_t *pfq_tab,
+                                  uint32_t *hlen_tab = nullptr, uint64_t *hoff_tab = nullptr, uint64_t *boff_tab = nullptr, uint64_t *qoff_tab = nullptr,
+                                  uint8_t *hdrs = nullptr, uint64_t hcap = 0, uint8_t *bases = nullptr, uint64_t bcap = 0,
+                                  uint8_t *quals = nullptr, uint64_t qcap = 0) {
+    uint32_t status = SFQ_OK;
+    uint64_t gh = 0, gb = 0, gq = 0;
+    uint32_t nbig = 0;
+    if (ssize[SFQ_S_USR_LREC]) {
+        if (!hlen_tab) status = SFQ_E_CORRUPT;
+        else {
+            SfqXLoad x_lrec;
+            x_lrec.init(pwpool, SFQ_X_LREC, in + soff[SFQ_S_USR_LREC], ssize[SFQ_S_USR_LREC]);
+            uint64_t i_long = x_lrec.get();
+            for (uint32_t r = 0; r < meta->nrec; r++) hlen_tab[r] = 0;
+            while (i_long && status == SFQ_OK) {
+                if (i_long > meta->nrec) { status = SFQ_E_CORRUPT; break; }
+                const uint32_t r = (uint32_t)(i_long - 1);
+                const uint64_t start = gh;
+                for (int line = 0; line < 2 && status == SFQ_OK; line++) {          // id line, '+' line
+                    for (;;) {
+                        const uint8_t c = x_lrec.get_chr();
+                        if (c == '\n' && line == 1) break;
+                        if (gh >= hcap) { status = SFQ_E_CORRUPT; break; }
+                        hdrs[gh++] = c;
+                        if (c == '\n') break;
+                    }
+                }
+                hlen_tab[r] = (uint32_t)(gh - start) | SFQ_BIG_BIT;
+                hoff_tab[r] = start;
+                nbig++;
+                const uint64_t d = x_lrec.get();
+                if (!d) break;
+                i_long += d;
+            }
+            SfqXLoad x_lgen, x_lqlt;
+            x_lgen.init(pwpool, SFQ_X_LGEN, in + soff[SFQ_S_USR_LGEN], ssize[SFQ_S_USR_LGEN]);
+            x_lqlt.init(pwpool, SFQ_X_LQLT, in + soff[SFQ_S_USR_LQLT], ssize[SFQ_S_USR_LQLT]);
+            if (nbig && (!x_lgen.rc.valid || !x_lqlt.rc.valid)) status = SFQ_E_CORRUPT;
+            for (uint32_t r = 0; r < meta->nrec && status == SFQ_OK; r++) {
+                if (!(hlen_tab[r] & SFQ_BIG_BIT)) continue;
+                uint64_t start = gb;
+                for (;;) { const uint8_t c = x_lgen.get_chr(); if (c == '\n') break; if (gb >= bcap) { status = SFQ_E_CORRUPT; break; } bases[gb++] = c; }
+                llen_tab[r] = (uint32_t)(gb - start) | SFQ_BIG_BIT; boff_tab[r] = start;
+                start = gq;
+                for (;;) { const uint8_t c = x_lqlt.get_chr(); if (c == '\n') break; if (gq >= qcap) { status = SFQ_E_CORRUPT; break; } quals[gq++] = c; }
+                qlen_tab[r] = (uint32_t)(gq - start) | SFQ_BIG_BIT; qoff_tab[r] = start;
+            }
+        }
+    }
     SfqXLoad x_llen, x_qlen, x_sgen, x_sqlt;
     x_llen.init(pwpool, SFQ_X_LLEN, in + soff[SFQ_S_USR_X], ssize[SFQ_S_USR_X]);
     x_qlen.init(pwpool, SFQ_X_QLEN, in + soff[SFQ_S_USR_XQ], ssize[SFQ_S_USR_XQ]);
@@ -706,9 +793,10 @@ SFQ_HDN void sfq_usr_decode_chunk(const uint8_t *in, const uint32_t *ssize, cons
     uint64_t i_llen = x_llen.get(), i_qlen = x_qlen.get(), i_sgen = x_sgen.get(), i_sqlt = x_sqlt.get();
     uint8_t pf_gen = 0, pf_qlt = 0;
     uint64_t nb = 0, nq = 0;
-    uint32_t status = SFQ_OK;
-    for (uint32_t r = 0; r < meta->nrec; r++) {
+    for (uint32_t r = 0; r < meta->nrec && status == SFQ_OK; r++) {
         const uint64_t recno = (uint64_t)r + 1;
+        if (nbig && (hlen_tab[r] & SFQ_BIG_BIT)) { pfg_tab[r] = 0; pfq_tab[r] = 0; continue; }   // (update() starts over at the next record number)
+        if (hlen_tab) hlen_tab[r] = 0;
         if (i_llen == recno) { m_llen = x_llen.get(); m_qlen = m_llen; i_llen += x_llen.get(); }
         if (i_qlen == recno) { m_qlen = x_qlen.get(); i_qlen += x_qlen.get(); }
         else if (m_qlen != m_llen) m_qlen = m_llen;
@@ -724,7 +812,8 @@ SFQ_HDN void sfq_usr_decode_chunk(const uint8_t *in, const uint32_t *ssize, cons
     if (meta->pad & 1u) {                     // imported from a reference file: the header holds upper bounds
         if (nb > meta->nbases || nq > meta->nquals) status = SFQ_E_CORRUPT;
         else { meta->nbases = (uint32_t)nb; meta->nquals = (uint32_t)nq; }
-    } else if (nb != meta->nbases || nq != meta->nquals) status = SFQ_E_CORRUPT;
+    } else if (nb != meta->nbases || nq != meta->nquals || nbig != meta->nbig) status = SFQ_E_CORRUPT;
+    meta->nbig = nbig; meta->big_bases = (uint32_t)gb; meta->big_quals = (uint32_t)gq; meta->big_hdr = (uint32_t)gh;
     if (status != SFQ_OK && meta->status == SFQ_OK) meta->status = status;
 }
 
@@ -760,17 +849,20 @@ SFQ_HDN void sfq_rec_decode_chunk(const uint8_t *in, const uint32_t *ssize, cons
     for (int a = 0; a < 2; a++) for (int b = 0; b < 65; b++) { ctype[a][b] = 0; cnumb[a][b] = 0; }
     uint32_t imap = 0;
     uint64_t x_index = x_rec.get();                                             // recs.cpp:104-105
-    uint64_t pos = 0;
+    uint64_t pos = meta->nbig ? meta->big_hdr : 0;                              // oversized records' lines sit at the front of the plane
     const uint8_t *prev = nullptr;
+    bool have_first = false;
     uint32_t status = SFQ_OK;
 
     for (uint32_t r = 0; r < meta->nrec; r++) {
         const uint64_t recno = (uint64_t)r + 1;
+        if (meta->nbig && (hlen_tab[r] & SFQ_BIG_BIT)) continue;                // (UsrLoad::update prints it and moves on, usrs.cpp:473-485)
         uint8_t *buf = hdrs + pos;
         // every branch below checks room before it writes; a valid container never trips it
         uint64_t room = hcap - pos;
         uint32_t n = 0;
-        if (r == 0) {                                                           // recs.cpp:375-381
+        if (!have_first) {                                                      // recs.cpp:375-381
+            have_first = true;
             if (rec_first_len + 1ull > room) { status = SFQ_E_CORRUPT; break; }
             for (uint32_t k = 0; k < rec_first_len; k++) buf[k] = rec_first[k];
             n = rec_first_len;

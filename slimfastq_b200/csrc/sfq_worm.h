@@ -30,7 +30,8 @@
 struct SfqWormEntry { uint64_t name, size; uint32_t first, node; };
 #pragma pack(pop)
 
-static const char *const kSfqStreamNames[SFQ_NSTREAMS] = {"rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq"};
+static const char *const kSfqStreamNames[SFQ_NSTREAMS] = {"rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq",
+                                                          "usr.lrec", "usr.lgen", "usr.lqlt"};
 
 // pages a stream of n bytes occupies: data pages + node pages
 static inline uint64_t sfq_worm_pages(uint64_t n) {
@@ -82,9 +83,11 @@ static inline bool sfq_worm_write(const SfqBlobHeader &b, const uint8_t *rec_fir
     add("orig.filename", orig_filename && *orig_filename ? orig_filename : "<< stdin >>");
     add("orig.size", std::to_string((unsigned long long)b.text_len));
     if (b.solid) add("usr.solid", "1");
-    add("llen", std::to_string(b.llen));
-    add("usr.2id", b.two_id ? "1" : "0");
-    add("rec.first", std::string((const char *)rec_first, b.rec_first_len));
+    if (b.nbig < b.nrec || b.llen) {               // (a file of oversized records only has neither key, usrs.cpp:190-198)
+        add("llen", std::to_string(b.llen));
+        add("usr.2id", b.two_id ? "1" : "0");
+    }
+    if (b.nbig < b.nrec) add("rec.first", std::string((const char *)rec_first, b.rec_first_len));
     if (b.n_byte) add("gen.N_byte", std::to_string((unsigned)b.n_byte));
     add("num_records", std::to_string(b.nrec));
     uint64_t pages = 0;

@@ -103,12 +103,12 @@ def illumina(n_reads: int, seed: int = SEED0 + 1, read_len: int = 150, bins8: bo
     return _assemble(headers, bases, qual)
 
 
-def ont(n_reads: int, seed: int = SEED0 + 4, max_len: int = 50000) -> bytes:
-    """ONT-style long reads: log-normal lengths clipped to 1 000..max_len (< 65 535), UUID/hex
+def ont(n_reads: int, seed: int = SEED0 + 4, max_len: int = 50000, mu: float = 8.9) -> bytes:
+    """ONT-style long reads: log-normal lengths clipped to 1 000..max_len (above 65 534 a read is an oversized record), UUID/hex
     headers like fast5.to.fq, qualities over Phred 1..60 with occasional values >= 63 (escape path,
     qlts.cpp:120-125), N runs of 1..50 under non-'!' quality (gen.Ns)."""
     rng = np.random.default_rng(seed)
-    lens = np.clip(rng.lognormal(8.9, 0.8, n_reads), 1000, max_len).astype(np.int64)
+    lens = np.clip(rng.lognormal(mu, 0.8, n_reads), 1000, max_len).astype(np.int64)
     run_id = "%040x" % int(rng.integers(0, 2**62))
     headers, seqs, quals = [], [], []
     t0 = 1000
@@ -208,4 +208,33 @@ def edge_cases(seed: int = SEED0 + 9) -> dict[str, bytes]:
     # tiny single-record and two-record files
     out["one_record"] = b"@r1\nACGTN\n+\nIIII#\n"
     out["two_records"] = b"@r.1 a:1\nACGTNACGT\n+\nIIII!IIII\n@r.2 a:2\nACGTTACGTAA\n+\nIIIIIIIII##\n"
+    return out
+
+
+def oversized_cases(seed: int = SEED0 + 11) -> dict[str, bytes]:
+    """Inputs with oversized records (id of 8 191+ chars, base or quality line of 65 535+ chars: usrs.hpp:34-36,
+    usrs.cpp:269-301), which the reference stores verbatim in usr.lrec / usr.lgen / usr.lqlt: in the middle of a
+    file, at its start (determine_record, usrs.cpp:186-267), at the exact limits, with only the quality line too
+    long (the length exception of the record is written before the record is put away), in a SOLiD file, alone."""
+    rng = np.random.default_rng(seed)
+
+    def rec(i, L, ql=None, hdr=None, alphabet=b"ACGT", pfx=b""):
+        ql = L if ql is None else ql
+        h = hdr if hdr is not None else b"@ont.%d ch=%d start=%d" % (i, 1 + i % 512, 1000 + 37 * i)
+        s = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), L)].tobytes()
+        q = rng.integers(35, 74, ql).astype(np.uint8).tobytes()
+        return h + b"\n" + pfx + s + b"\n+\n" + (pfx and b"!") + q + b"\n"
+
+    long_id = b"@" + b"x".join(b"%d" % (i * 7919) for i in range(1600))[:8700]
+    out = {}
+    out["oversize_mid"] = b"".join(
+        [rec(i, 150) for i in range(20)] + [rec(20, 70000)] + [rec(i, 150) for i in range(21, 31)] + [rec(31, 100, hdr=long_id)] +
+        [rec(i, 151) for i in range(32, 37)] + [rec(37, 65535), rec(38, 65534), rec(39, 150), rec(40, 65534, hdr=b"@" + b"y" * 8190),
+                                               rec(41, 150, hdr=b"@" + b"z" * 8191), rec(42, 150)])
+    out["oversize_first"] = b"".join([rec(0, 70000), rec(1, 90, hdr=long_id), rec(2, 65536)] + [rec(i, 120) for i in range(3, 30)])
+    out["oversize_qual_only"] = b"".join([rec(i, 150) for i in range(8)] + [rec(8, 120, ql=66000)] + [rec(i, 150) for i in range(9, 16)] +
+                                         [rec(16, 150, ql=65535)] + [rec(i, 150) for i in range(17, 20)])
+    out["oversize_all"] = rec(0, 66000) + rec(1, 80, hdr=long_id)
+    out["oversize_solid"] = b"".join([rec(i, 50, alphabet=b"0123", pfx=b"T") for i in range(12)] + [rec(12, 65535, alphabet=b"0123", pfx=b"T"),
+                                      rec(13, 65534, alphabet=b"0123", pfx=b"G")] + [rec(i, 50, alphabet=b"0123", pfx=b"T") for i in range(14, 20)])
     return out

@@ -140,12 +140,14 @@ extern "C" int sfq_emul_compress(const uint8_t *text_in, size_t n, int level, ui
             b.magic = SFQ_BLOB_MAGIC; b.level = level; b.text_len = m.text_len; b.out_len = m.out_len; b.nrec = m.nrec;
             b.nbases = m.nbases; b.nquals = m.nquals; b.hdr_bytes = m.hdr_bytes; b.llen = m.llen;
             b.solid = m.solid; b.two_id = m.two_id; b.n_byte = m.n_byte; b.extra_hi = m.extra_hi;
-            b.rec_first_len = (uint32_t)(ls[m.line0 + 1] - ls[m.line0] - 2); b.g_used = m.g_used;
+            const uint64_t fl = m.line0 + 4ull * m.first_coded;
+            b.rec_first_len = m.first_coded < m.nrec ? (uint32_t)(ls[fl + 1] - ls[fl] - 2) : 0; b.g_used = m.g_used;
+            b.nbig = m.nbig; b.big_bases = m.big_bases; b.big_quals = m.big_quals; b.big_hdr = m.big_hdr;
             for (int k = 0; k < SFQ_NSTREAMS; k++) b.ssize[k] = ar.size[k];
             index.push_back(file.size());
             out_total += m.out_len;
             put_bytes(file, &b, sizeof b);
-            put_bytes(file, text + ls[m.line0] + 1, b.rec_first_len);
+            put_bytes(file, text + ls[fl] + 1, b.rec_first_len);
             for (int k = 0; k < SFQ_NSTREAMS; k++) put_bytes(file, arena.data() + ar.off[k], ar.size[k]);
             break;
         }
@@ -174,6 +176,7 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **ou
         SfqChunkMeta m; memset(&m, 0, sizeof m);
         m.nrec = b.nrec; m.nbases = b.nbases; m.nquals = b.nquals; m.hdr_bytes = b.hdr_bytes; m.llen = b.llen;
         m.solid = b.solid; m.two_id = b.two_id; m.n_byte = b.n_byte; m.text_len = b.text_len; m.out_len = b.out_len;
+        m.nbig = b.nbig; m.big_bases = b.big_bases; m.big_quals = b.big_quals; m.big_hdr = b.big_hdr;
         const int level = (int)b.level;
         uint64_t soff[SFQ_NSTREAMS]; uint32_t ssize[SFQ_NSTREAMS];
         uint64_t o = off + sizeof b + b.rec_first_len;
@@ -187,13 +190,14 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **ou
         std::vector<uint32_t> llen(m.nrec), qlen(m.nrec), hlen(m.nrec);
         std::vector<uint8_t> pfg(m.nrec), pfq(m.nrec);
         std::vector<uint64_t> boff(m.nrec), qoff(m.nrec), hoff(m.nrec);
-        sfq_usr_decode_chunk(sfq, ssize, soff, &m, pw, llen.data(), qlen.data(), pfg.data(), pfq.data());
+        std::vector<uint8_t> bases((size_t)b.nbases + b.big_bases + 1), quals((size_t)b.nquals + b.big_quals + 1), hdrs((size_t)SFQ_HDR_PLANE(&m));
+        sfq_usr_decode_chunk(sfq, ssize, soff, &m, pw, llen.data(), qlen.data(), pfg.data(), pfq.data(), hlen.data(), hoff.data(), boff.data(), qoff.data(),
+                             hdrs.data(), hdrs.size(), bases.data(), bases.size() - 1, quals.data(), quals.size() - 1);
         if (m.status) { *status_out = m.status; return 1; }
-        uint64_t nb = 0, nq = 0;
-        for (uint32_t r = 0; r < m.nrec; r++) { boff[r] = nb; qoff[r] = nq; nb += llen[r]; nq += qlen[r]; }
-        std::vector<uint8_t> bases(nb + 1), quals(nq + 1), hdrs((size_t)SFQ_HDR_PLANE(&m));
+        uint64_t nb = m.big_bases, nq = m.big_quals;
+        for (uint32_t r = 0; r < m.nrec; r++) { if (llen[r] & SFQ_BIG_BIT) continue; boff[r] = nb; qoff[r] = nq; nb += llen[r]; nq += qlen[r]; }
         sfq_gen_decode_chunk(sfq, ssize, soff, &m, level, gt, hbits, pw, llen.data(), boff.data(), bases.data(), lut, SfqStage());
-        sfq_gen_apply_exceptions(sfq, ssize, soff, &m, pw, bases.data());
+        sfq_gen_apply_exceptions(sfq, ssize, soff, &m, pw, bases.data() + m.big_bases);
         sfq_qlt_decode_chunk(sfq, ssize, soff, &m, level, qt, pw, qlen.data(), qoff.data(), quals.data());
         sfq_rec_decode_chunk(sfq, ssize, soff, &m, pw, sfq + off + sizeof b, b.rec_first_len, hdrs.data(),
                              hdrs.size(), hlen.data(), hoff.data());
@@ -202,6 +206,17 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **ou
         const uint8_t nbyte = m.n_byte ? m.n_byte : 'N';
         size_t before = text.size();
         for (uint32_t r = 0; r < m.nrec; r++) {       // UsrLoad::save, usrs.cpp:512-529 (the assemble kernel)
+            if (hlen[r] & SFQ_BIG_BIT) {              // oversized: verbatim
+                const uint32_t hb = hlen[r] & ~SFQ_BIG_BIT;
+                const uint8_t *h = hdrs.data() + hoff[r];
+                uint32_t cut = 0;
+                while (cut < hb && h[cut] != '\n') cut++;
+                text.push_back('@'); put_bytes(text, h, cut); text.push_back('\n');
+                put_bytes(text, bases.data() + boff[r], llen[r] & ~SFQ_BIG_BIT); text.push_back('\n');
+                put_bytes(text, h + cut + 1, hb - cut - 1); text.push_back('\n');
+                put_bytes(text, quals.data() + qoff[r], qlen[r] & ~SFQ_BIG_BIT); text.push_back('\n');
+                continue;
+            }
             text.push_back('@'); put_bytes(text, hdrs.data() + hoff[r], hlen[r]); text.push_back('\n');
             if (m.solid) text.push_back(pfg[r]);
             for (uint32_t i = 0; i < llen[r]; i++) {

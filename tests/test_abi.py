@@ -53,4 +53,4 @@ def test_product_does_not_reference_the_oracle():
 def test_container_struct_sizes_match_python():
     from slimfastq_b200 import container as K
 
-    assert K.FILE_HDR.size == 80 and K.BLOB_HDR.size == 104
+    assert K.FILE_HDR.size == 80 and K.BLOB_HDR.size == 132

@@ -21,6 +21,24 @@ def test_edge_cases(oracle, name):
         assert emul.decompress(blob) == oracle.decode(oracle.encode(data, level))
 
 
+@pytest.mark.parametrize("name", sorted(synth.oversized_cases()))
+def test_oversized_records(oracle, name):
+    """usr.lrec / usr.lgen / usr.lqlt through the planner, the header coder and the usr decoder (whole file and in chunks)."""
+    data = synth.oversized_cases()[name]
+    for level, chunk, two in ((3, 1 << 40, False), (1, 1 << 40, True), (3, 1 << 16, True)):
+        blob = emul.compress(data, level, chunk, two_phase=two)
+        check_container_against_oracle(oracle, data, blob, level)
+        assert emul.decompress(blob) == data
+
+
+def test_long_reads_beyond_64k_in_chunks(oracle):
+    data = synth.ont(40, max_len=150000, mu=10.6)                # 15 of the 40 reads are oversized records; N runs in both kinds
+    blob = emul.compress(data, 3, 1 << 20, two_phase=True)
+    ct = check_container_against_oracle(oracle, data, blob, 3)
+    assert len(ct.chunks) > 2 and sum("usr.lgen" in c.streams for c in ct.chunks) > 2
+    assert emul.decompress(blob) == data
+
+
 def test_synthetic_shapes_chunked(oracle):
     for data, level in ((synth.illumina(7000), 3), (synth.illumina(3000, bins8=True), 4), (synth.ont(40), 3), (synth.illumina(3000), 1)):
         blob = emul.compress(data, level, 1 << 19)

@@ -36,6 +36,30 @@ def test_edge_cases_bit_exact(codec, oracle, name, level):
     assert codec.decompress(blob) == oracle.decode(oracle.encode(data, level))
 
 
+@pytest.mark.parametrize("name", sorted(synth.oversized_cases()))
+def test_oversized_records_bit_exact(codec, oracle, name):
+    """Records the reference stores verbatim in usr.lrec / usr.lgen / usr.lqlt (id of 8 191+ characters, line of 65 535+)."""
+    data = synth.oversized_cases()[name]
+    for level, chunk in ((3, 1 << 40), (1, 1 << 16), (4, 1 << 18)):
+        blob = codec.compress(data, level, chunk)
+        check_container_against_oracle(oracle, data, blob, level)
+        assert codec.decompress(blob) == data
+    if oracle.have_ref():
+        from slimfastq_b200 import container as K
+
+        ref = oracle.ref_encode(data, 3)                          # the binary itself, not its restatement
+        ch = K.parse(codec.compress(data, 3, 1 << 40)).chunks[0]
+        assert ch.streams == ref.streams and ch.info_tuple() == ref.info_tuple()
+
+
+def test_long_read_workload_with_reads_beyond_64k(codec, oracle):
+    data = synth.ont(40, max_len=150000, mu=10.6)
+    assert max(len(l) for l in data.split(b"\n")[1::4]) > 65535
+    blob = codec.compress(data, 3, 1 << 20)
+    check_container_against_oracle(oracle, data, blob, 3)
+    assert codec.decompress(blob) == data
+
+
 @pytest.mark.parametrize("level", [1, 2, 3, 4])
 def test_illumina_chunks_bit_exact(codec, oracle, level):
     data = synth.illumina(12000)                     # ~4.3 MB -> five 1 MiB chunks
@@ -90,7 +114,7 @@ def test_decoder_survives_wrong_table_hints(codec):
     data = synth.illumina(7000)
     blob = bytearray(codec.compress(data, 3, 1 << 20))
     _, _, _, _, _, nchunks, _, index_off, _ = K.FILE_HDR.unpack_from(blob, 0)
-    hint_off = K.BLOB_HDR.size - 4 * 10 - 8                     # q_used, g_used sit right before ssize[10]
+    hint_off = K.BLOB_HDR.size - 4 * len(K.STREAM_NAMES) - 16 - 8      # q_used, g_used sit before the four oversized-record counts and ssize[]
     for off in struct.unpack_from(f"<{nchunks}Q", blob, index_off):
         q_used, g_used = struct.unpack_from("<II", blob, off + hint_off)
         assert q_used > 1000 and g_used > 100000

@@ -53,6 +53,24 @@ def test_oracle_equals_reference_binary_on_its_samples(oracle, path):
             assert oracle.decode(mine) == oracle.ref_roundtrip(data, level)
 
 
+@pytest.mark.parametrize("name", sorted(__import__("slimfastq_b200.synth", fromlist=["x"]).oversized_cases()))
+def test_oracle_equals_reference_binary_on_oversized_records(oracle, name):
+    """usr.lrec / usr.lgen / usr.lqlt (usrs.cpp:269-301, 473-485): no reference sample has such records, so the pin
+    is the reference binary run here on synthetic ones (70 kb reads, 8.5 KiB ids, the exact limits, leading and
+    quality-only oversize, SOLiD, a file of nothing else)."""
+    if not oracle.have_ref():
+        pytest.skip("reference binary not built")
+    from slimfastq_b200 import synth
+
+    data = synth.oversized_cases()[name]
+    for level in (1, 3):
+        mine, ref = oracle.encode(data, level), oracle.ref_encode(data, level)
+        assert "usr.lrec" in ref.streams and "usr.lgen" in ref.streams and "usr.lqlt" in ref.streams
+        assert mine.info_tuple() == ref.info_tuple()
+        assert mine.streams == ref.streams
+        assert oracle.decode(mine) == oracle.ref_roundtrip(data, level) == data
+
+
 def test_oracle_rejects_what_the_reference_croaks_on(oracle):
     for bad in (b"", b"hello\n", b"@r1\nACGT\n-\nIIII\n", b"@r1\nACXT\n+\nIIII\n", b"@r1\nACGT\n+\nIIII"):
         with pytest.raises(oracle.OracleError):

@@ -44,10 +44,6 @@ def test_format_conversions_with_the_reference_binary(path):
         ref = ref_compress(data, 3, d)
         assert S.is_reference_file(ref)
         info, streams = sfq_extract.extract(ref)
-        if any(k in streams for k in ("usr.lrec", "usr.lgen", "usr.lqlt")):
-            with pytest.raises(S.SfqError):                       # oversized records are reported, never mis-read
-                S.import_reference(ref)
-            return
         blob = S.import_reference(ref)                            # reference file -> single-chunk container
         assert not S.is_reference_file(blob)
         ct = K.parse(blob)
@@ -63,6 +59,21 @@ def test_format_conversions_with_the_reference_binary(path):
             assert info2.get(k) == info.get(k), k
         assert int(info2["comp.size"]) == len(back)
         assert ref_decompress(back, d) == ref_decompress(ref, d)  # the reference decodes our pages like its own
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(synth.oversized_cases()))
+def test_format_conversions_keep_oversized_record_streams(name):
+    data = synth.oversized_cases()[name]
+    with tempfile.TemporaryDirectory() as d:
+        ref = ref_compress(data, 3, d)
+        info, streams = sfq_extract.extract(ref)
+        assert all(k in streams for k in ("usr.lrec", "usr.lgen", "usr.lqlt"))
+        blob = S.import_reference(ref)
+        assert K.parse(blob).chunks[0].streams == {k: v for k, v in streams.items() if v}
+        back = S.export_reference(blob, "in.fq")
+        assert sfq_extract.extract(back)[1] == streams
+        assert ref_decompress(back, d) == data
 
 
 @needs_ref
@@ -95,11 +106,9 @@ def test_conversions_reject_what_they_cannot_represent():
 @needs_ref
 @pytest.mark.parametrize("level", [1, 3])
 def test_gpu_output_is_decoded_by_the_reference_binary(codec, level):
-    cases = [open(p, "rb").read() for p in SAMPLES[:6]] + [synth.illumina(5000), synth.edge_cases()["badqlt"]]
+    cases = [open(p, "rb").read() for p in SAMPLES[:6]] + [synth.illumina(5000), synth.edge_cases()["badqlt"]] + list(synth.oversized_cases().values())
     with tempfile.TemporaryDirectory() as d:
         for data in cases:
-            if any(k in sfq_extract.extract(ref_compress(data, level, d))[1] for k in ("usr.lrec", "usr.lgen", "usr.lqlt")):
-                continue
             blob = codec.compress(data, level, 1 << 40)           # one chunk = one reference file
             ref_file = S.export_reference(blob, "in.fq")
             assert ref_decompress(ref_file, d) == O.ref_roundtrip(data, level)
@@ -109,10 +118,8 @@ def test_gpu_output_is_decoded_by_the_reference_binary(codec, level):
 @needs_ref
 @pytest.mark.parametrize("level", [2, 4])
 def test_reference_output_is_decoded_on_the_gpu(codec, level):
-    cases = [open(p, "rb").read() for p in SAMPLES] + [synth.illumina(5000), synth.ont(40), synth.edge_cases()["badqlt"]]
+    cases = [open(p, "rb").read() for p in SAMPLES] + [synth.illumina(5000), synth.ont(40), synth.edge_cases()["badqlt"]] + list(synth.oversized_cases().values())
     with tempfile.TemporaryDirectory() as d:
         for data in cases:
             ref = ref_compress(data, level, d)
-            if any(k in sfq_extract.extract(ref)[1] for k in ("usr.lrec", "usr.lgen", "usr.lqlt")):
-                continue
             assert codec.decompress(S.import_reference(ref)) == ref_decompress(ref, d)
