@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <new>
 #include <string>
 #include <utility>
 #include <vector>
@@ -83,7 +84,7 @@ struct sfq_ctx {
            blob_off, gtab, qtab, pw, dchunks, bhdrs, bases, quals, hdrs, rec_chunk,
            t_llen, t_qlen, t_hlen, t_pfg, t_pfq, t_boff, t_qoff, t_hoff, t_ooff,
            e2_gsteps, e2_qkey, e2_qb, e2_sorted, e2_qsteps, e2_cnt, e2_esorted, e2_esteps, e2_segs, e2_ctr, e2_chunks, rec_qoff,
-           e2_gbins, e2_gcnt;
+           e2_gbins, e2_gcnt, rec_boff;
     int spread = -1;                        // SFQ_SPREAD=0..3 (default: 3 for large waves, else 0; see decompress_on_device)
     unsigned spread_smem[3] = {0, 0, 0};    // dynamic shared memory reserved per CTA: base, quality, header decoder
     uint32_t dec_warps = 4;                 // SFQ_DEC_WARPS=1..4: warps per CTA of the thread-per-chunk decoders (one-warp CTAs each
@@ -110,7 +111,7 @@ struct sfq_ctx {
                          &arenas, &arena_buf, &blob_off, &gtab, &qtab, &pw, &dchunks, &bhdrs, &bases, &quals,
                          &hdrs, &rec_chunk, &t_llen, &t_qlen, &t_hlen, &t_pfg, &t_pfq, &t_boff, &t_qoff,
                          &t_hoff, &t_ooff, &e2_gsteps, &e2_qkey, &e2_qb, &e2_sorted, &e2_qsteps, &e2_cnt, &e2_esorted,
-                         &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks, &rec_qoff, &e2_gbins, &e2_gcnt};
+                         &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks, &rec_qoff, &e2_gbins, &e2_gcnt, &rec_boff};
         for (DevBuf *b : all) b->release();
         scratch.release();
         h_out.release(); h_out_d.release(); h_small.release();
@@ -162,7 +163,7 @@ int status_to_error(sfq_ctx *ctx, const SfqChunkMeta &m, uint64_t chunk, uint64_
     case SFQ_E_PLUS: return fail(ctx, SFQ_ERR_FASTQ, "fastq file: expecting '+' at record %llu (chunk %llu)", rec, (unsigned long long)chunk);
     case SFQ_E_TRUNC: return fail(ctx, SFQ_ERR_FASTQ, "fastq file: record seems truncated  after record %llu", rec);
     case SFQ_E_OVERSIZE: return fail(ctx, SFQ_ERR_FASTQ, "wierd second id at record %llu", rec);
-    case SFQ_E_BASE: return fail(ctx, SFQ_ERR_FASTQ, "unexpected genome char: %c", (int)m.status_arg);
+    case SFQ_E_BASE: return fail(ctx, SFQ_ERR_FASTQ, "unexpected genome char: %c", (int)(m.status_arg & 0xffu));
     case SFQ_E_NBYTE: return fail(ctx, SFQ_ERR_FASTQ, "switched N_byte: %c", (int)m.status_arg);
     case SFQ_E_SEPS: return fail(ctx, SFQ_ERR_FASTQ, "ERROR: irregulal record (over 64 non alpha non digit). Is it a valid fastq file?");
     case SFQ_E_FIRSTHDR: return fail(ctx, SFQ_ERR_UNSUPPORTED, "chunk %llu: first header longer than 399 chars", (unsigned long long)chunk);
@@ -289,8 +290,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     CK(cudaMemcpyAsync(ctx->r0.p, r0.data(), nchunks * 8ull, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->r1.p, r1.data(), nchunks * 8ull, cudaMemcpyHostToDevice, s));
     SfqChunkMeta *d_metas = ctx->metas.as<SfqChunkMeta>();
-    CK(ctx->rec_qoff.ensure(nrec_total * 4 + 64));
-    k_chunk_plan<<<(nchunks + 63) / 64, 64, 0, s>>>(d_text, d_ls, ctx->r0.as<uint64_t>(), ctx->r1.as<uint64_t>(), d_metas, nchunks, ctx->rec_qoff.as<uint32_t>()); LAUNCHED();
+    CK(ctx->rec_qoff.ensure(nrec_total * 4 + 64)); CK(ctx->rec_boff.ensure(nrec_total * 4 + 64));
+    k_chunk_plan<<<(nchunks + 63) / 64, 64, 0, s>>>(d_text, d_ls, ctx->r0.as<uint64_t>(), ctx->r1.as<uint64_t>(), d_metas, nchunks, ctx->rec_qoff.as<uint32_t>(), ctx->rec_boff.as<uint32_t>()); LAUNCHED();
     std::vector<SfqChunkMeta> metas(nchunks);
     CK(cudaMemcpyAsync(metas.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[EV_PLAN], s));
@@ -416,8 +417,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
                 if (two_phase && !gm_table) {
                     const bool gp_smem = (1u << gp_bits) <= SFQ_GP_SMEM_MAX;
-                    TRACED("k_gen_count", s, (k_gen_count<<<dim3((wave_max_nrec + SFQ_GC_RECS - 1) / SFQ_GC_RECS, nc), 128, gp_smem ? (size_t)4 << gp_bits : 0, s>>>(d_text, d_ls, d_metas + c0, e2.gcnt, gp_bits, level, nc))); LAUNCHED();
-                    TRACED("k_gen_scatter", s, (k_gen_scatter<8><<<nc, 32, gp_smem ? (size_t)36 << gp_bits : 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc))); LAUNCHED();
+                    TRACED("k_gen_keys", s, (k_gen_keys<<<dim3((wave_max_nrec + SFQ_GC_RECS - 1) / SFQ_GC_RECS, nc), 128, 0, s>>>(d_text, d_ls, d_metas + c0, ctx->rec_boff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
+                    TRACED("k_gen_part", s, (k_gen_part<<<nc, 32, gp_smem ? (size_t)36 << gp_bits : 0, s>>>(d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, nc))); LAUNCHED();
                     TRACED("k_gen_replay", s, (k_gen_replay<<<ctx->sm_count, 32 * SFQ_GR_WARPS, SFQ_GR_SMEM, s>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
                     TRACED("k_rc_encode<0>", s, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else if (two_phase) {
@@ -796,7 +797,7 @@ int sfq_create(sfq_ctx **out, int device) {
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->head_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaFuncSetAttribute(k_gen_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SFQ_GR_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_gen_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(36u * SFQ_GP_SMEM_MAX)) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+        cudaFuncSetAttribute(k_gen_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(36u * SFQ_GP_SMEM_MAX)) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     {   // shared memory the decoders' CTAs reserve when they are spread (one of each kind per SM fits, two of a kind barely)
         int smem_sm = 0;
         cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
@@ -842,40 +843,44 @@ size_t sfq_compress_bound(size_t n, uint64_t chunk_bytes) {
 
 int sfq_compress_device(sfq_ctx *ctx, const void *d_fastq, size_t n, int level, uint64_t chunk_bytes,
                         void *d_out, size_t out_cap, size_t *out_n) {
-    if (!ctx || !d_fastq || !d_out || !out_n) return SFQ_ERR_ARG;
-    begin_call(ctx);
-    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
-    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-    int rc = compress_on_device(ctx, (const uint8_t *)d_fastq, n, level, chunk_bytes, (uint8_t *)d_out, out_cap, out_n);
-    if (rc) return rc;
-    ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_CODE_END]);
-    return 0;
+    try {
+        if (!ctx || !d_fastq || !d_out || !out_n) return SFQ_ERR_ARG;
+        begin_call(ctx);
+        CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+        CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+        int rc = compress_on_device(ctx, (const uint8_t *)d_fastq, n, level, chunk_bytes, (uint8_t *)d_out, out_cap, out_n);
+        if (rc) return rc;
+        ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_CODE_END]);
+        return 0;
+    } catch (const std::bad_alloc &) { return ctx ? fail(ctx, SFQ_ERR_NOMEM, "out of host memory") : SFQ_ERR_NOMEM; }
 }
 
 int sfq_compress(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes,
                  const uint8_t **out, size_t *out_n) {
-    if (!ctx || !fastq || !out || !out_n) return SFQ_ERR_ARG;
-    begin_call(ctx);
-    if (n == 0) return fail(ctx, SFQ_ERR_FASTQ, "no records were found");
-    const size_t cap = sfq_compress_bound(n, chunk_bytes);
-    CK(ensure_big(ctx, ctx->text, n + 16));
-    CK(ensure_big(ctx, ctx->out, cap));
-    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
-    CK(cudaMemcpyAsync(ctx->text.p, fastq, n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-    size_t on = 0;
-    int rc = compress_on_device(ctx, ctx->text.as<uint8_t>(), n, level, chunk_bytes, ctx->out.as<uint8_t>(), cap, &on);
-    if (rc) return rc;
-    CK(ctx->h_out.ensure(on));
-    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->out.p, on, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->st.ms_h2d = ev_ms(ctx->ev[EV_START], ctx->ev[EV_H2D]);
-    ctx->st.ms_d2h = ev_ms(ctx->ev[EV_CODE_END], ctx->ev[EV_D2H]);
-    ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_D2H]);
-    *out = ctx->h_out.as<uint8_t>();
-    *out_n = on;
-    return 0;
+    try {
+        if (!ctx || !fastq || !out || !out_n) return SFQ_ERR_ARG;
+        begin_call(ctx);
+        if (n == 0) return fail(ctx, SFQ_ERR_FASTQ, "no records were found");
+        const size_t cap = sfq_compress_bound(n, chunk_bytes);
+        CK(ensure_big(ctx, ctx->text, n + 16));
+        CK(ensure_big(ctx, ctx->out, cap));
+        CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+        CK(cudaMemcpyAsync(ctx->text.p, fastq, n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+        size_t on = 0;
+        int rc = compress_on_device(ctx, ctx->text.as<uint8_t>(), n, level, chunk_bytes, ctx->out.as<uint8_t>(), cap, &on);
+        if (rc) return rc;
+        CK(ctx->h_out.ensure(on));
+        CK(cudaMemcpyAsync(ctx->h_out.p, ctx->out.p, on, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->st.ms_h2d = ev_ms(ctx->ev[EV_START], ctx->ev[EV_H2D]);
+        ctx->st.ms_d2h = ev_ms(ctx->ev[EV_CODE_END], ctx->ev[EV_D2H]);
+        ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_D2H]);
+        *out = ctx->h_out.as<uint8_t>();
+        *out_n = on;
+        return 0;
+    } catch (const std::bad_alloc &) { return ctx ? fail(ctx, SFQ_ERR_NOMEM, "out of host memory") : SFQ_ERR_NOMEM; }
 }
 
 int sfq_decompressed_size(const uint8_t *sfq, size_t n, uint64_t *out_n, int *level) {
@@ -888,67 +893,71 @@ int sfq_decompressed_size(const uint8_t *sfq, size_t n, uint64_t *out_n, int *le
 }
 
 int sfq_decompress(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **out, size_t *out_n) {
-    if (!ctx || !sfq || !out || !out_n) return SFQ_ERR_ARG;
-    begin_call(ctx);
-    SfqFileHeader fh;
-    std::vector<uint64_t> index;
-    std::vector<SfqBlobHeader> blobs;
-    int rc = parse_host_container(ctx, sfq, n, fh, index, blobs);
-    if (rc) return rc;
-    uint64_t total = 4096;
-    for (auto &b : blobs) total += b.out_len + 8ull * b.nrec;      // slack: see SFQ_HDR_PLANE
-    CK(ensure_big(ctx, ctx->text, n + 16));          // container bytes
-    CK(ensure_big(ctx, ctx->out, total + 16));
-    CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
-    CK(cudaMemcpyAsync(ctx->text.p, sfq, n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-    size_t on = 0;
-    rc = decompress_on_device(ctx, ctx->text.as<uint8_t>(), n, fh, index, blobs, ctx->out.as<uint8_t>(), total, &on);
-    if (rc) return rc;
-    CK(ctx->h_out_d.ensure(on + 1));
-    CK(cudaMemcpyAsync(ctx->h_out_d.p, ctx->out.p, on, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->st.ms_h2d = ev_ms(ctx->ev[EV_START], ctx->ev[EV_H2D]);
-    ctx->st.ms_d2h = ev_ms(ctx->ev[EV_CODE_END], ctx->ev[EV_D2H]);
-    ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_D2H]);
-    *out = ctx->h_out_d.as<uint8_t>();
-    *out_n = on;
-    return 0;
+    try {
+        if (!ctx || !sfq || !out || !out_n) return SFQ_ERR_ARG;
+        begin_call(ctx);
+        SfqFileHeader fh;
+        std::vector<uint64_t> index;
+        std::vector<SfqBlobHeader> blobs;
+        int rc = parse_host_container(ctx, sfq, n, fh, index, blobs);
+        if (rc) return rc;
+        uint64_t total = 4096;
+        for (auto &b : blobs) total += b.out_len + 8ull * b.nrec;      // slack: see SFQ_HDR_PLANE
+        CK(ensure_big(ctx, ctx->text, n + 16));          // container bytes
+        CK(ensure_big(ctx, ctx->out, total + 16));
+        CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+        CK(cudaMemcpyAsync(ctx->text.p, sfq, n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+        size_t on = 0;
+        rc = decompress_on_device(ctx, ctx->text.as<uint8_t>(), n, fh, index, blobs, ctx->out.as<uint8_t>(), total, &on);
+        if (rc) return rc;
+        CK(ctx->h_out_d.ensure(on + 1));
+        CK(cudaMemcpyAsync(ctx->h_out_d.p, ctx->out.p, on, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->st.ms_h2d = ev_ms(ctx->ev[EV_START], ctx->ev[EV_H2D]);
+        ctx->st.ms_d2h = ev_ms(ctx->ev[EV_CODE_END], ctx->ev[EV_D2H]);
+        ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_D2H]);
+        *out = ctx->h_out_d.as<uint8_t>();
+        *out_n = on;
+        return 0;
+    } catch (const std::bad_alloc &) { return ctx ? fail(ctx, SFQ_ERR_NOMEM, "out of host memory") : SFQ_ERR_NOMEM; }
 }
 
 int sfq_decompress_device(sfq_ctx *ctx, const void *d_sfq, size_t n, void *d_out, size_t out_cap, size_t *out_n) {
-    if (!ctx || !d_sfq || !d_out || !out_n) return SFQ_ERR_ARG;
-    begin_call(ctx);
-    cudaStream_t s = ctx->stream;
-    if (n < sizeof(SfqFileHeader)) return fail(ctx, SFQ_ERR_FORMAT, "not a b200 chunked .sfq container");
-    CK(cudaEventRecord(ctx->ev[EV_START], s));
-    CK(cudaEventRecord(ctx->ev[EV_H2D], s));
-    SfqFileHeader fh;
-    CK(cudaMemcpyAsync(&fh, d_sfq, sizeof fh, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (!sfq_is_chunked_container(reinterpret_cast<const uint8_t *>(&fh), sizeof fh)) return fail(ctx, SFQ_ERR_FORMAT, "not a b200 chunked .sfq container");
-    if (fh.nchunks == 0 || fh.nchunks > 0x7fffffffull || fh.index_off > n || n - fh.index_off < fh.nchunks * 8)
-        return fail(ctx, SFQ_ERR_FORMAT, "corrupt container index");
-    std::vector<uint64_t> index(fh.nchunks);
-    std::vector<SfqBlobHeader> blobs(fh.nchunks);
-    CK(ctx->bhdrs.ensure(fh.nchunks * sizeof(SfqBlobHeader)));
-    const uint64_t *d_index = reinterpret_cast<const uint64_t *>((const uint8_t *)d_sfq + fh.index_off);
-    if (fh.index_off & 7) {     // unaligned index: stage it through the blob_off buffer
-        CK(ctx->blob_off.ensure(fh.nchunks * 8));
-        CK(cudaMemcpyAsync(ctx->blob_off.p, (const uint8_t *)d_sfq + fh.index_off, fh.nchunks * 8, cudaMemcpyDeviceToDevice, s));
-        d_index = ctx->blob_off.as<uint64_t>();
-    }
-    k_gather_blob_headers<<<(unsigned)((fh.nchunks + 127) / 128), 128, 0, s>>>((const uint8_t *)d_sfq, d_index, ctx->bhdrs.as<SfqBlobHeader>(), fh.nchunks, n); LAUNCHED();
-    CK(cudaMemcpyAsync(index.data(), d_index, fh.nchunks * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(blobs.data(), ctx->bhdrs.p, fh.nchunks * sizeof(SfqBlobHeader), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    for (uint64_t c = 0; c < fh.nchunks; c++)
-        if (index[c] > n || n - index[c] < sizeof(SfqBlobHeader)) return fail(ctx, SFQ_ERR_FORMAT, "corrupt container index");
-    int rc = decompress_on_device(ctx, (const uint8_t *)d_sfq, n, fh, index, blobs, (uint8_t *)d_out, out_cap, out_n);
-    if (rc) return rc;
-    ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_CODE_END]);
-    return 0;
+    try {
+        if (!ctx || !d_sfq || !d_out || !out_n) return SFQ_ERR_ARG;
+        begin_call(ctx);
+        cudaStream_t s = ctx->stream;
+        if (n < sizeof(SfqFileHeader)) return fail(ctx, SFQ_ERR_FORMAT, "not a b200 chunked .sfq container");
+        CK(cudaEventRecord(ctx->ev[EV_START], s));
+        CK(cudaEventRecord(ctx->ev[EV_H2D], s));
+        SfqFileHeader fh;
+        CK(cudaMemcpyAsync(&fh, d_sfq, sizeof fh, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (!sfq_is_chunked_container(reinterpret_cast<const uint8_t *>(&fh), sizeof fh)) return fail(ctx, SFQ_ERR_FORMAT, "not a b200 chunked .sfq container");
+        if (fh.nchunks == 0 || fh.nchunks > 0x7fffffffull || fh.index_off > n || n - fh.index_off < fh.nchunks * 8)
+            return fail(ctx, SFQ_ERR_FORMAT, "corrupt container index");
+        std::vector<uint64_t> index(fh.nchunks);
+        std::vector<SfqBlobHeader> blobs(fh.nchunks);
+        CK(ctx->bhdrs.ensure(fh.nchunks * sizeof(SfqBlobHeader)));
+        const uint64_t *d_index = reinterpret_cast<const uint64_t *>((const uint8_t *)d_sfq + fh.index_off);
+        if (fh.index_off & 7) {     // unaligned index: stage it through the blob_off buffer
+            CK(ctx->blob_off.ensure(fh.nchunks * 8));
+            CK(cudaMemcpyAsync(ctx->blob_off.p, (const uint8_t *)d_sfq + fh.index_off, fh.nchunks * 8, cudaMemcpyDeviceToDevice, s));
+            d_index = ctx->blob_off.as<uint64_t>();
+        }
+        k_gather_blob_headers<<<(unsigned)((fh.nchunks + 127) / 128), 128, 0, s>>>((const uint8_t *)d_sfq, d_index, ctx->bhdrs.as<SfqBlobHeader>(), fh.nchunks, n); LAUNCHED();
+        CK(cudaMemcpyAsync(index.data(), d_index, fh.nchunks * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(blobs.data(), ctx->bhdrs.p, fh.nchunks * sizeof(SfqBlobHeader), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (uint64_t c = 0; c < fh.nchunks; c++)
+            if (index[c] > n || n - index[c] < sizeof(SfqBlobHeader)) return fail(ctx, SFQ_ERR_FORMAT, "corrupt container index");
+        int rc = decompress_on_device(ctx, (const uint8_t *)d_sfq, n, fh, index, blobs, (uint8_t *)d_out, out_cap, out_n);
+        if (rc) return rc;
+        ctx->st.ms_total = ev_ms(ctx->ev[EV_START], ctx->ev[EV_CODE_END]);
+        return 0;
+    } catch (const std::bad_alloc &) { return ctx ? fail(ctx, SFQ_ERR_NOMEM, "out of host memory") : SFQ_ERR_NOMEM; }
 }
 
 
@@ -964,86 +973,90 @@ size_t sfq_export_reference_bound(const uint8_t *sfq, size_t n) {
 }
 
 int sfq_export_reference(const uint8_t *sfq, size_t n, const char *orig_filename, uint8_t *out, size_t out_cap, size_t *out_n) {
-    if (!sfq || !out || !out_n) return SFQ_ERR_ARG;
-    if (!sfq_is_chunked_container(sfq, n)) return SFQ_ERR_FORMAT;
-    SfqFileHeader fh;
-    memcpy(&fh, sfq, sizeof fh);
-    if (fh.nchunks != 1) return SFQ_ERR_UNSUPPORTED;               // one reference file = one chunk
-    if (fh.index_off > n || n - fh.index_off < 8) return SFQ_ERR_FORMAT;
-    uint64_t off;
-    memcpy(&off, sfq + fh.index_off, 8);
-    if (off > n || n - off < sizeof(SfqBlobHeader)) return SFQ_ERR_FORMAT;
-    SfqBlobHeader b;
-    memcpy(&b, sfq + off, sizeof b);
-    if (b.magic != SFQ_BLOB_MAGIC || off + sfq_blob_size(&b) > n) return SFQ_ERR_FORMAT;
-    const uint8_t *p = sfq + off + sizeof b;
-    const uint8_t *rec_first = p;
-    p += b.rec_first_len;
-    const uint8_t *stream[SFQ_NSTREAMS];
-    for (int k = 0; k < SFQ_NSTREAMS; k++) { stream[k] = p; p += b.ssize[k]; }
-    std::vector<uint8_t> file;
-    std::string err;
-    if (!sfq_worm_write(b, rec_first, stream, orig_filename, file, err)) return SFQ_ERR_FORMAT;
-    if (file.size() > out_cap) return SFQ_ERR_SPACE;
-    memcpy(out, file.data(), file.size());
-    *out_n = file.size();
-    return 0;
+    try {
+        if (!sfq || !out || !out_n) return SFQ_ERR_ARG;
+        if (!sfq_is_chunked_container(sfq, n)) return SFQ_ERR_FORMAT;
+        SfqFileHeader fh;
+        memcpy(&fh, sfq, sizeof fh);
+        if (fh.nchunks != 1) return SFQ_ERR_UNSUPPORTED;               // one reference file = one chunk
+        if (fh.index_off > n || n - fh.index_off < 8) return SFQ_ERR_FORMAT;
+        uint64_t off;
+        memcpy(&off, sfq + fh.index_off, 8);
+        if (off > n || n - off < sizeof(SfqBlobHeader)) return SFQ_ERR_FORMAT;
+        SfqBlobHeader b;
+        memcpy(&b, sfq + off, sizeof b);
+        if (b.magic != SFQ_BLOB_MAGIC || off + sfq_blob_size(&b) > n) return SFQ_ERR_FORMAT;
+        const uint8_t *p = sfq + off + sizeof b;
+        const uint8_t *rec_first = p;
+        p += b.rec_first_len;
+        const uint8_t *stream[SFQ_NSTREAMS];
+        for (int k = 0; k < SFQ_NSTREAMS; k++) { stream[k] = p; p += b.ssize[k]; }
+        std::vector<uint8_t> file;
+        std::string err;
+        if (!sfq_worm_write(b, rec_first, stream, orig_filename, file, err)) return SFQ_ERR_FORMAT;
+        if (file.size() > out_cap) return SFQ_ERR_SPACE;
+        memcpy(out, file.data(), file.size());
+        *out_n = file.size();
+        return 0;
+    } catch (const std::bad_alloc &) { return SFQ_ERR_NOMEM; }
 }
 
 size_t sfq_import_reference_bound(size_t n) { return n + sizeof(SfqFileHeader) + sizeof(SfqBlobHeader) + 0x200 + 64; }
 
 int sfq_import_reference(const uint8_t *ref, size_t n, uint8_t *out, size_t out_cap, size_t *out_n) {
-    if (!ref || !out || !out_n) return SFQ_ERR_ARG;
-    std::map<std::string, std::string> info;
-    std::map<std::string, std::vector<uint8_t>> streams;
-    std::string err;
-    if (!sfq_worm_read(ref, n, info, streams, err)) return SFQ_ERR_FORMAT;
-    auto num = [&](const char *k, long long dflt) { auto it = info.find(k); return it == info.end() || it->second.empty() ? dflt : atoll(it->second.c_str()); };
-    if (num("version", 0) > SFQ_INTERNAL_VERSION) return SFQ_ERR_FORMAT;         // config.cpp:373-377
-    const long long orig = num("orig.size", -1), nrec = num("num_records", 0);
-    if (orig <= 0 || orig >= 0xFFFFFFF0ll || nrec <= 0 || nrec > 0x7fffffffll) return SFQ_ERR_UNSUPPORTED;
-    SfqBlobHeader b;
-    memset(&b, 0, sizeof b);
-    b.magic = SFQ_BLOB_MAGIC;
-    long long level = num("config.level", 2);                                        // config.cpp:363
-    b.level = (uint32_t)(level > 4 ? 4 : level < 1 ? 1 : level);
-    b.text_len = (uint64_t)orig;
-    b.out_len = (uint64_t)orig + 16ull * (uint64_t)nrec + 4096;                      // an upper bound: see SFQ_BLOB_IMPORTED
-    b.nrec = (uint32_t)nrec;
-    b.nbases = b.nquals = b.hdr_bytes = (uint32_t)orig;                              // upper bounds
-    b.llen = (int32_t)num("llen", 0);
-    { auto it = info.find("usr.solid"); b.solid = it != info.end() && !it->second.empty() && it->second[0] != '0'; }   // get_bool, config.cpp:124-127
-    b.two_id = num("usr.2id", 0) != 0;
-    const long long nb = num("gen.N_byte", 'N');
-    b.n_byte = (nb && nb != 'N') ? (uint8_t)nb : 0;
-    b.pad = SFQ_BLOB_IMPORTED;
-    b.extra_hi = (uint32_t)num("qlt.extra.hi", 0);
-    // oversized records: their count is not recorded either; the planes' upper bounds (orig.size) cover them
-    b.nbig = 0; b.big_bases = b.big_quals = b.big_hdr = 0;
-    const std::string &first = info["rec.first"];
-    if (first.size() > 399) return SFQ_ERR_UNSUPPORTED;
-    b.rec_first_len = (uint32_t)first.size();
-    uint64_t total = sizeof(SfqFileHeader) + sizeof b + first.size();
-    for (int k = 0; k < SFQ_NSTREAMS; k++) {
-        auto it = streams.find(kSfqStreamNames[k]);
-        const size_t sz = it == streams.end() ? 0 : it->second.size();
-        if (sz > 0xFFFFFF00ull) return SFQ_ERR_UNSUPPORTED;
-        b.ssize[k] = (uint32_t)sz;
-        total += sz;
-    }
-    if (total + 8 > out_cap) return SFQ_ERR_SPACE;
-    SfqFileHeader fh;
-    sfq_file_header_init(&fh, (int)b.level, (uint64_t)orig, 1, (uint64_t)orig, total, b.out_len);
-    uint8_t *p = out;
-    memcpy(p, &fh, sizeof fh); p += sizeof fh;
-    const uint64_t blob_off = sizeof fh;
-    memcpy(p, &b, sizeof b); p += sizeof b;
-    memcpy(p, first.data(), first.size()); p += first.size();
-    for (int k = 0; k < SFQ_NSTREAMS; k++)
-        if (b.ssize[k]) { memcpy(p, streams[kSfqStreamNames[k]].data(), b.ssize[k]); p += b.ssize[k]; }
-    memcpy(p, &blob_off, 8); p += 8;
-    *out_n = (size_t)(p - out);
-    return 0;
+    try {
+        if (!ref || !out || !out_n) return SFQ_ERR_ARG;
+        std::map<std::string, std::string> info;
+        std::map<std::string, std::vector<uint8_t>> streams;
+        std::string err;
+        if (!sfq_worm_read(ref, n, info, streams, err)) return SFQ_ERR_FORMAT;
+        auto num = [&](const char *k, long long dflt) { auto it = info.find(k); return it == info.end() || it->second.empty() ? dflt : atoll(it->second.c_str()); };
+        if (num("version", 0) > SFQ_INTERNAL_VERSION) return SFQ_ERR_FORMAT;         // config.cpp:373-377
+        const long long orig = num("orig.size", -1), nrec = num("num_records", 0);
+        if (orig <= 0 || orig >= 0xFFFFFFF0ll || nrec <= 0 || nrec > 0x7fffffffll) return SFQ_ERR_UNSUPPORTED;
+        SfqBlobHeader b;
+        memset(&b, 0, sizeof b);
+        b.magic = SFQ_BLOB_MAGIC;
+        long long level = num("config.level", 2);                                        // config.cpp:363
+        b.level = (uint32_t)(level > 4 ? 4 : level < 1 ? 1 : level);
+        b.text_len = (uint64_t)orig;
+        b.out_len = (uint64_t)orig + 16ull * (uint64_t)nrec + 4096;                      // an upper bound: see SFQ_BLOB_IMPORTED
+        b.nrec = (uint32_t)nrec;
+        b.nbases = b.nquals = b.hdr_bytes = (uint32_t)orig;                              // upper bounds
+        b.llen = (int32_t)num("llen", 0);
+        { auto it = info.find("usr.solid"); b.solid = it != info.end() && !it->second.empty() && it->second[0] != '0'; }   // get_bool, config.cpp:124-127
+        b.two_id = num("usr.2id", 0) != 0;
+        const long long nb = num("gen.N_byte", 'N');
+        b.n_byte = (nb && nb != 'N') ? (uint8_t)nb : 0;
+        b.pad = SFQ_BLOB_IMPORTED;
+        b.extra_hi = (uint32_t)num("qlt.extra.hi", 0);
+        // oversized records: their count is not recorded either; the planes' upper bounds (orig.size) cover them
+        b.nbig = 0; b.big_bases = b.big_quals = b.big_hdr = 0;
+        const std::string &first = info["rec.first"];
+        if (first.size() > 399) return SFQ_ERR_UNSUPPORTED;
+        b.rec_first_len = (uint32_t)first.size();
+        uint64_t total = sizeof(SfqFileHeader) + sizeof b + first.size();
+        for (int k = 0; k < SFQ_NSTREAMS; k++) {
+            auto it = streams.find(kSfqStreamNames[k]);
+            const size_t sz = it == streams.end() ? 0 : it->second.size();
+            if (sz > 0xFFFFFF00ull) return SFQ_ERR_UNSUPPORTED;
+            b.ssize[k] = (uint32_t)sz;
+            total += sz;
+        }
+        if (total + 8 > out_cap) return SFQ_ERR_SPACE;
+        SfqFileHeader fh;
+        sfq_file_header_init(&fh, (int)b.level, (uint64_t)orig, 1, (uint64_t)orig, total, b.out_len);
+        uint8_t *p = out;
+        memcpy(p, &fh, sizeof fh); p += sizeof fh;
+        const uint64_t blob_off = sizeof fh;
+        memcpy(p, &b, sizeof b); p += sizeof b;
+        memcpy(p, first.data(), first.size()); p += first.size();
+        for (int k = 0; k < SFQ_NSTREAMS; k++)
+            if (b.ssize[k]) { memcpy(p, streams[kSfqStreamNames[k]].data(), b.ssize[k]); p += b.ssize[k]; }
+        memcpy(p, &blob_off, 8); p += 8;
+        *out_n = (size_t)(p - out);
+        return 0;
+    } catch (const std::bad_alloc &) { return SFQ_ERR_NOMEM; }
 }
 
 

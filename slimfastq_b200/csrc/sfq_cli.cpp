@@ -103,7 +103,7 @@ static void statistics_dump(const uint8_t *p, size_t n) {      // config.cpp:76-
     fprintf(stderr, ":::: Info ::::\n");
     fprintf(stderr, "%-16s = %s\n", "whoami", "slimfastq");
     fprintf(stderr, "%-16s = %u\n", "version", fh.version);
-    fprintf(stderr, "%-16s = %s\n", "format", "b200.c1 (chunked)");
+    fprintf(stderr, "%-16s = %s\n", "format", "b200.c2 (chunked)");
     fprintf(stderr, "%-16s = %u\n", "config.level", fh.level);
     fprintf(stderr, "%-16s = %llu\n", "orig.size", (unsigned long long)fh.orig_size);
     fprintf(stderr, "%-16s = %llu\n", "comp.size", (unsigned long long)n);
@@ -111,7 +111,7 @@ static void statistics_dump(const uint8_t *p, size_t n) {      // config.cpp:76-
     fprintf(stderr, "%-16s = %llu\n", "chunk.bytes", (unsigned long long)fh.chunk_bytes);
     static const char *names[SFQ_NSTREAMS] = {"rec", "gen", "qlt", "gen.Ns", "gen.Nn", "rec.x", "usr.x", "usr.x.q", "usr.pfg", "usr.pfq", "usr.lrec", "usr.lgen", "usr.lqlt"};
     unsigned long long tot[SFQ_NSTREAMS] = {0}, nrec = 0, extra = 0;
-    if (fh.index_off <= n && n - fh.index_off >= fh.nchunks * 8)
+    if (fh.index_off <= n && fh.nchunks <= (n - fh.index_off) / 8)
         for (uint64_t c = 0; c < fh.nchunks; c++) {
             uint64_t off;
             memcpy(&off, p + fh.index_off + 8 * c, 8);
@@ -124,7 +124,8 @@ static void statistics_dump(const uint8_t *p, size_t n) {      // config.cpp:76-
                 fprintf(stderr, "%-16s = %d\n", "llen", b.llen);
                 fprintf(stderr, "%-16s = %d\n", "usr.solid", b.solid);
                 fprintf(stderr, "%-16s = %d\n", "usr.2id", b.two_id);
-                fprintf(stderr, "%-16s = %.*s\n", "rec.first", (int)b.rec_first_len, (const char *)p + off + sizeof b);
+                const size_t room = n - off - sizeof b;
+                fprintf(stderr, "%-16s = %.*s\n", "rec.first", (int)(b.rec_first_len < room ? b.rec_first_len : room), (const char *)p + off + sizeof b);
             }
         }
     fprintf(stderr, "%-16s = %llu\n", "num_records", nrec);
@@ -148,7 +149,7 @@ struct StreamOut {                       // the container being assembled on dis
     void add(const uint8_t *part, size_t n) {      // a whole container: append its blobs
         SfqFileHeader h;
         memcpy(&h, part, sizeof h);
-        if (h.index_off > n || n - h.index_off < h.nchunks * 8) croak("internal error: bad part container");
+        if (h.index_off > n || h.nchunks > (n - h.index_off) / 8) croak("internal error: bad part container");
         for (uint64_t c = 0; c < h.nchunks; c++) { uint64_t o; memcpy(&o, part + h.index_off + 8 * c, 8); index.push_back(o - sizeof h + pos); }
         const size_t body = (size_t)(h.index_off - sizeof h);
         if (fwrite(part + sizeof h, 1, body, f) != body) croak("Error writing output: %s", strerror(errno));
@@ -320,7 +321,7 @@ int main(int argc, char **argv) {
         SfqFileHeader fh;
         memcpy(&fh, src, sizeof fh);
         const size_t seg = (size_t)seg_mib << 20;
-        const bool index_ok = fh.nchunks && fh.index_off <= n && n - fh.index_off >= fh.nchunks * 8;
+        const bool index_ok = fh.nchunks && fh.index_off <= n && fh.nchunks <= (n - fh.index_off) / 8;
         if (seg == 0 || fh.out_size <= seg || !index_ok) {                  // all at once
             const uint8_t *res = nullptr;
             size_t rn = 0;

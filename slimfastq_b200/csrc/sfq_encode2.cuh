@@ -378,7 +378,7 @@ k_gen_model(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, S
 //                  base2_ranger.hpp:74-84) - and writes each base's coding step to its stream position.
 // A context belongs to exactly one partition and a partition's list keeps stream order, so every model sees its
 // symbols in the reference's order: the steps, hence the bytes, are those of the single-pass coder.
-#define SFQ_GP_TARGET   768u           // bases per partition the partition count aims for (sfq_gen_gp_bits)
+#define SFQ_GP_TARGET   1024u          // most bases per partition, on average, the partition count aims for (sfq_gen_gp_bits)
 #define SFQ_GP_SLOTS    2048u          // hash slots per replay warp (8 bytes each) + one owner byte per slot
 #define SFQ_GP_SMEM_MAX 4096u          // the scatter warp keeps cursors and staging rows in shared memory up to this many partitions
 #define SFQ_GR_WARPS    12             // replay warps per CTA (12 x 18 KB)
@@ -414,52 +414,63 @@ __device__ __forceinline__ unsigned sfq_match_bits(uint32_t v, uint32_t bits, un
     return peers;
 }
 
-// gcnt[c * gp + p] += bases of chunk c whose context lies in partition p.  A CTA takes SFQ_GC_RECS records of one
-// chunk (blockIdx.y), a warp one record at a time.
+// Key of a base: context (26 bits) | symbol << 26 | "is an N" << 28 | "quality is '!'" << 29 | which N byte << 30 (N, n, .).
+// gcnt[c * gp + p] += bases of chunk c whose context lies in partition p.  Order-free: a CTA takes SFQ_GC_RECS records
+// of one chunk (blockIdx.y), a warp one record at a time.  The keys lie in the chunk's step array, which k_gen_replay
+// only fills after k_gen_part has read them.
+#define SFQ_GK_N     (1u << 28)
+#define SFQ_GK_BADQ  (1u << 29)
 __global__ void __launch_bounds__(128)
-k_gen_count(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, const SfqChunkMeta *__restrict__ metas,
-            uint32_t *gcnt, uint32_t gp_bits, int level, uint32_t nchunks) {
-    extern __shared__ uint32_t hist[];                     // gp counters (gp <= SFQ_GP_SMEM_MAX), else straight to global
+k_gen_keys(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas, const uint32_t *__restrict__ rec_boff,
+           SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, int level, uint32_t nchunks) {
     const uint32_t c = blockIdx.y;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (c >= nchunks) return;
-    const SfqChunkMeta *meta = &metas[c];
+    SfqChunkMeta *meta = &metas[c];
     if (meta->status != SFQ_OK) return;
     const uint32_t nrec = meta->nrec;
     if (blockIdx.x * SFQ_GC_RECS >= nrec) return;
-    const uint32_t gp = 1u << gp_bits;
-    const bool in_smem = gp <= SFQ_GP_SMEM_MAX;
-    uint32_t *out = gcnt + (size_t)c * gp;
-    if (in_smem) { for (uint32_t k = threadIdx.x; k < gp; k += blockDim.x) hist[k] = 0; __syncthreads(); }
-    uint32_t *h = in_smem ? hist : out;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t gp_bits = e2.gp_bits;
+    uint32_t *cnt = e2.gcnt + ((size_t)c << gp_bits);
+    uint32_t *gkey = e2.gsteps + e2c[c].goff;
     const uint32_t solid = meta->solid, mask = sfq_gen_mask(level);
     const uint64_t line0 = meta->line0;
+    const uint32_t *boffs = rec_boff + line0 / 4;
     const uint32_t r_end = min(nrec, (blockIdx.x + 1u) * SFQ_GC_RECS);
     for (uint32_t r = blockIdx.x * SFQ_GC_RECS + warp; r < r_end; r += 4) {
         const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
+        const uint32_t bbase = boffs[r];
         uint32_t prev = 0x007616c7u;                                           // gens.cpp:139
         for (uint32_t w0 = 0; w0 < v.llen; w0 += 32) {
-            const bool active = w0 + lane < v.llen;
-            uint32_t n = sfq_gencode(active ? v.seq[w0 + lane] : (uint8_t)'A');
+            const uint32_t i = w0 + lane;
+            const bool active = i < v.llen;
+            const uint32_t g = active ? v.seq[i] : (uint32_t)'A';
+            const uint32_t q = active ? (i < v.qlen ? v.qual[i] : 40u) : (uint32_t)'I';        // gens.cpp:153
+            uint32_t n = sfq_gencode((uint8_t)g);
+            const unsigned errb = __ballot_sync(FULL, active && n > 4u);
+            if (errb) {                                                        // unexpected genome char (gens.cpp:125-126): the earliest one is reported
+                if (active && n > 4u) atomicMax(&meta->status_arg, ((0xffffffu - (bbase + i)) << 8) | g);    // (largest = earliest position)
+                if (lane == 0) atomicCAS(&meta->status, (uint32_t)SFQ_OK, (uint32_t)SFQ_E_BASE);
+            }
+            const bool bad_n = n == 4u;
             if (n > 3u) n = 0;
             const uint32_t ctx = sfq_gen_window_ctx(n, lane, prev, mask);
-            if (active) atomicAdd(h + sfq_gp_of(ctx, gp_bits), 1u);
+            if (active) {
+                gkey[bbase + i] = ctx | (n << 26) | (bad_n ? SFQ_GK_N : 0u) | (q == (uint32_t)'!' ? SFQ_GK_BADQ : 0u) |
+                                  ((g == (uint32_t)'n' ? 1u : g == (uint32_t)'.' ? 2u : 0u) << 30);
+                atomicAdd(cnt + sfq_gp_of(ctx, gp_bits), 1u);
+            }
         }
-    }
-    if (in_smem) {
-        __syncthreads();
-        for (uint32_t k = threadIdx.x; k < gp; k += blockDim.x) { const uint32_t v = hist[k]; if (v) atomicAdd(out + k, v); }
     }
 }
 
-// One warp per chunk, in stream order: exceptions, then (position | symbol << 24, context) appended to the list of
-// the context's partition.  gcnt holds the partition sizes on entry and each partition's END offset on exit (list p
-// starts at the end of list p-1 rounded up to 4 entries).
-template <int SFQ_GM_BATCH>
+// One warp per chunk walks the keys in stream order: exception lists (gens.cpp:91-114), then (position | symbol << 24,
+// context) appended to the list of the context's partition.  gcnt holds the partition sizes on entry and each
+// partition's END offset on exit (list p starts at the end of list p-1 rounded up to 4 entries).
 __global__ void __launch_bounds__(32)
-k_gen_scatter(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqChunkMeta *metas,
-              SfqArena *arenas, uint8_t *arena_buf, SfqWorkspace ws, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c,
-              int level, uint32_t nchunks) {
+k_gen_part(SfqChunkMeta *metas, SfqArena *arenas, uint8_t *arena_buf, SfqWorkspace ws, SfqEnc2Ws e2,
+           const SfqEnc2Chunk *__restrict__ e2c, uint32_t nchunks) {
     extern __shared__ uint4 sc_smem[];                     // gp staging rows of 4 entries (32 bytes), then gp cursors
     const uint32_t c = blockIdx.x;
     const uint32_t lane = threadIdx.x;
@@ -473,7 +484,7 @@ k_gen_scatter(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls,
     xnn.init(pwpool, SFQ_X_NN, arena_buf + ar->off[SFQ_S_GEN_NN], ar->cap[SFQ_S_GEN_NN]);
     const uint32_t gp_bits = e2.gp_bits, gp = 1u << gp_bits;
     uint32_t *gc = e2.gcnt + (size_t)c * gp;
-    const bool staged = gp <= SFQ_GP_SMEM_MAX;             // beyond that (chunks of > 3 M bases): cursors in global memory, entries written one by one
+    const bool staged = gp <= SFQ_GP_SMEM_MAX;             // beyond that (chunks of > 4 M bases): cursors in global memory, entries written one by one
     uint2 *stage = reinterpret_cast<uint2 *>(sc_smem);
     uint32_t *cur = staged ? reinterpret_cast<uint32_t *>(sc_smem + 2 * (size_t)gp) : gc;
     const unsigned FULL = 0xffffffffu;
@@ -489,91 +500,71 @@ k_gen_scatter(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls,
         for (uint32_t k = lo; k < hi; k++) { const uint32_t v = (gc[k] + 3u) & ~3u; cur[k] = run; run += v; }
         __syncwarp();
     }
-    const uint32_t mask = sfq_gen_mask(level);
-    const uint32_t solid = meta->solid, nrec = meta->nrec;
-    const uint64_t line0 = meta->line0;
+    const uint32_t *gkey = e2.gsteps + e2c[c].goff;
     uint2 *bins = reinterpret_cast<uint2 *>(e2.gbins) + sfq_gbins_off(e2c[c].goff, c, gp_bits);
-
-    uint32_t gbase = 0;                  // bases coded so far (g_genofs_count before this window)
+    const uint32_t nb = meta->nbases;
     uint64_t ns_index = 0, nn_index = 0;
     uint32_t n_byte = 0;
     uint32_t status = SFQ_OK, status_arg = 0;
-
-    for (uint32_t r = 0; r < nrec && status == SFQ_OK; r++) {
-        const SfqRecView v = sfq_rec_view(text, ls, line0, r, solid);
-        if (r + 2 < nrec && lane < 4) sfq_prefetch(text + ls[line0 + 4ull * (r + 2)] + 128u * lane);   // the record after next
-        uint32_t prev = 0x007616c7u;                                           // gens.cpp:139
-        for (uint32_t w0 = 0; w0 < v.llen && status == SFQ_OK; w0 += 32 * SFQ_GM_BATCH) {
-            uint32_t gg[SFQ_GM_BATCH], qq[SFQ_GM_BATCH];
+    constexpr int B = 8;
+    for (uint32_t p0 = 0; p0 < nb && status == SFQ_OK; p0 += 32 * B) {
+        uint32_t keys[B];
 #pragma unroll
-            for (int j = 0; j < SFQ_GM_BATCH; j++) {                            // the batch's text: all loads in flight together
-                const uint32_t i = w0 + 32u * j + lane;
-                const bool active = i < v.llen;
-                gg[j] = active ? v.seq[i] : (uint32_t)'A';
-                qq[j] = active ? (i < v.qlen ? v.qual[i] : 40u) : (uint32_t)'I';            // gens.cpp:153
-            }
+        for (int j = 0; j < B; j++) { const uint32_t pos = p0 + 32u * j + lane; keys[j] = pos < nb ? gkey[pos] : 0u; }
 #pragma unroll
-            for (int j = 0; j < SFQ_GM_BATCH; j++) {
-                const uint32_t wj = w0 + 32u * j;
-                if (wj < v.llen && status == SFQ_OK) {
-                    const bool active = wj + lane < v.llen;
-                    const uint32_t g = gg[j];
-                    uint32_t n = sfq_gencode((uint8_t)g);
-                    const bool bad_n = n == 4u;
-                    const unsigned errb = __ballot_sync(FULL, n > 4u);
-                    if (n > 3u) n = 0;
-                    const bool bad_q = qq[j] == (uint32_t)'!';
-                    unsigned excb = __ballot_sync(FULL, active && (bad_n || bad_q));
-                    if (errb) { status = SFQ_E_BASE; status_arg = __shfl_sync(FULL, g, __ffs(errb) - 1); }
-                    while (excb && status == SFQ_OK) {                         // exception lists, in base order (gens.cpp:91-114); rare
-                        const int b = __ffs(excb) - 1;
-                        excb &= excb - 1;
-                        const bool bn = __shfl_sync(FULL, (int)bad_n, b) != 0, bq = __shfl_sync(FULL, (int)bad_q, b) != 0;
-                        const uint32_t gb = __shfl_sync(FULL, g, b);
-                        const uint64_t genofs = (uint64_t)gbase + (uint32_t)b + 1u;
-                        if (!bn) { if (lane == 0) xnn.put(genofs - nn_index); nn_index = genofs; }
-                        else {
-                            if (!n_byte) n_byte = gb;
-                            if (gb != n_byte) { status = SFQ_E_NBYTE; status_arg = gb; break; }
-                            if (!bq) { if (lane == 0) xns.put(genofs - ns_index); ns_index = genofs; }
-                        }
+        for (int j = 0; j < B; j++) {
+            const uint32_t w0 = p0 + 32u * j, pos = w0 + lane;
+            if (w0 < nb && status == SFQ_OK) {
+                const bool active = pos < nb;
+                const uint32_t key = keys[j], ctx = key & 0x3ffffffu, n = (key >> 26) & 3u;
+                unsigned excb = __ballot_sync(FULL, active && (key & (SFQ_GK_N | SFQ_GK_BADQ)));
+                while (excb && status == SFQ_OK) {                             // exception lists, in base order (gens.cpp:91-114); rare
+                    const int b = __ffs(excb) - 1;
+                    excb &= excb - 1;
+                    const uint32_t kb = __shfl_sync(FULL, key, b);
+                    const bool bn = (kb & SFQ_GK_N) != 0, bq = (kb & SFQ_GK_BADQ) != 0;
+                    const uint32_t gb = (kb >> 30) == 1u ? (uint32_t)'n' : (kb >> 30) == 2u ? (uint32_t)'.' : (uint32_t)'N';
+                    const uint64_t genofs = (uint64_t)w0 + (uint32_t)b + 1u;
+                    if (!bn) { if (lane == 0) xnn.put(genofs - nn_index); nn_index = genofs; }
+                    else {
+                        if (!n_byte) n_byte = gb;
+                        if (gb != n_byte) { status = SFQ_E_NBYTE; status_arg = gb; break; }
+                        if (!bq) { if (lane == 0) xns.put(genofs - ns_index); ns_index = genofs; }
                     }
-                    const uint32_t ctx = sfq_gen_window_ctx(n, lane, prev, mask);
-                    if (status == SFQ_OK) {
-                        const unsigned am = __ballot_sync(FULL, active);
-                        const uint32_t p = sfq_gp_of(ctx, gp_bits);
-                        unsigned peers = sfq_match_bits(p, gp_bits, am);
-                        if (!active) peers = 1u << lane;
-                        const uint32_t rank = __popc(peers & lt), k = __popc(peers);
-                        uint32_t at0 = 0;
-                        if (active && rank == 0) { at0 = cur[p]; cur[p] = at0 + k; }
-                        at0 = __shfl_sync(FULL, at0, __ffs(peers) - 1);
-                        const uint32_t at = at0 + rank;
-                        const uint2 e = make_uint2((gbase + lane) | (n << 24), ctx);
-                        if (!staged) { if (active) bins[at] = e; }
-                        else {
-                            // the rows (4 entries = one sector) this window's group of partition p touches: entries of its first
-                            // row join what earlier windows staged; rows it fills alone go out directly (four lanes, one sector);
-                            // an unfinished last row is staged once the first one has left
-                            const uint32_t row = at >> 2, first = at0 >> 2, last = (at0 + k - 1u) >> 2;
-                            const bool last_done = ((at0 + k - 1u) & 3u) == 3u;
-                            const bool in_first = active && row == first;
-                            const bool direct = active && row != first && (row != last || last_done);
-                            const bool in_last = active && row != first && !direct;
-                            if (in_first) stage[4u * p + (at & 3u)] = e;
-                            if (direct) bins[at] = e;
-                            __syncwarp();
-                            if (in_first && (at & 3u) == 3u) {
-                                const uint4 *rowp = reinterpret_cast<const uint4 *>(stage + 4u * p);
-                                uint4 *dst = reinterpret_cast<uint4 *>(bins + (at - 3u));
-                                dst[0] = rowp[0]; dst[1] = rowp[1];
-                            }
-                            __syncwarp();
-                            if (in_last) stage[4u * p + (at & 3u)] = e;
-                        }
-                        gbase += min(32u, v.llen - wj);
+                }
+                if (status == SFQ_OK) {
+                    const unsigned am = __ballot_sync(FULL, active);
+                    const uint32_t p = sfq_gp_of(ctx, gp_bits);
+                    unsigned peers = sfq_match_bits(p, gp_bits, am);
+                    if (!active) peers = 1u << lane;
+                    const uint32_t rank = __popc(peers & lt), k = __popc(peers);
+                    uint32_t at0 = 0;
+                    if (active && rank == 0) { at0 = cur[p]; cur[p] = at0 + k; }
+                    at0 = __shfl_sync(FULL, at0, __ffs(peers) - 1);
+                    const uint32_t at = at0 + rank;
+                    const uint2 e = make_uint2(pos | (n << 24), ctx);
+                    if (!staged) { if (active) bins[at] = e; }
+                    else {
+                        // the rows (4 entries = one sector) this window's group of partition p touches: entries of its first
+                        // row join what earlier windows staged; rows it fills alone go out directly (four lanes, one sector);
+                        // an unfinished last row is staged once the first one has left
+                        const uint32_t row = at >> 2, first = at0 >> 2, last = (at0 + k - 1u) >> 2;
+                        const bool last_done = ((at0 + k - 1u) & 3u) == 3u;
+                        const bool in_first = active && row == first;
+                        const bool direct = active && row != first && (row != last || last_done);
+                        const bool in_last = active && row != first && !direct;
+                        if (in_first) stage[4u * p + (at & 3u)] = e;
+                        if (direct) bins[at] = e;
                         __syncwarp();
+                        if (in_first && (at & 3u) == 3u) {
+                            const uint4 *rowp = reinterpret_cast<const uint4 *>(stage + 4u * p);
+                            uint4 *dst = reinterpret_cast<uint4 *>(bins + (at - 3u));
+                            dst[0] = rowp[0]; dst[1] = rowp[1];
+                        }
+                        __syncwarp();
+                        if (in_last) stage[4u * p + (at & 3u)] = e;
                     }
+                    __syncwarp();
                 }
             }
         }

@@ -126,10 +126,10 @@ __global__ void k_chunk_bounds(const uint64_t *__restrict__ ls, uint64_t nrec_to
 }
 __global__ void k_chunk_plan(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls,
                              const uint64_t *__restrict__ r0, const uint64_t *__restrict__ r1,
-                             SfqChunkMeta *metas, uint32_t nchunks, uint32_t *rec_qoff) {
+                             SfqChunkMeta *metas, uint32_t nchunks, uint32_t *rec_qoff, uint32_t *rec_boff) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
-    sfq_plan_chunk(text, ls, r0[c], r1[c], &metas[c], rec_qoff + r0[c]);
+    sfq_plan_chunk(text, ls, r0[c], r1[c], &metas[c], rec_qoff + r0[c], rec_boff + r0[c]);
 }
 
 // One thread = one chunk-stream.  ROLE 0 = gen (+gen.Ns/Nn), 1 = qlt, 2 = rec (+rec.x, usr.*); the three

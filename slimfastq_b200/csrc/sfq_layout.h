@@ -33,10 +33,11 @@ static inline uint32_t sfq_gen_hbits(int level, uint64_t max_bases, uint32_t gro
     uint32_t b = sfq_ceil_log2(max_bases * 2 + 16) + grow;
     return b < 10 ? 10 : b > 27 ? 27 : b;
 }
-// Two-phase encoder: partitions of the base-context space per chunk, for at most ~768 bases per partition (k_gen_replay keeps
-// a partition's contexts in a 2048-slot table in shared memory); a table that still fills up reruns with twice as many.
+// Two-phase encoder: partitions of the base-context space per chunk, for at most 1024 bases per partition on average
+// (k_gen_replay keeps a partition's contexts in a 2048-slot table in shared memory); a table that still fills up reruns
+// with twice as many.
 static inline uint32_t sfq_gen_gp_bits(uint64_t max_bases, uint32_t grow) {
-    uint32_t b = sfq_ceil_log2((max_bases + 767) / 768) + grow;
+    uint32_t b = sfq_ceil_log2((max_bases + 1023) / 1024) + grow;
     return b > 14 ? 14 : b;
 }
 static inline uint64_t sfq_gtable_bytes(int level, uint32_t hbits) {
@@ -60,16 +61,18 @@ static inline uint64_t sfq_pwpool_bytes() { return (uint64_t)SFQ_PW_PER_CHUNK * 
 static inline void sfq_arena_layout(const SfqChunkMeta *m, uint32_t grow, uint64_t base, SfqArena *a, uint64_t *end) {
     const uint64_t g = 1ull << grow;
     uint64_t cap[SFQ_NSTREAMS];
-    cap[SFQ_S_REC] = (uint64_t)m->hdr_bytes * g + 16ull * m->nrec + 256;
-    cap[SFQ_S_GEN] = ((uint64_t)m->nbases * g) / 2 + 256;
-    cap[SFQ_S_QLT] = (uint64_t)m->nquals * g + 256;
-    cap[SFQ_S_GEN_NS] = ((uint64_t)m->nbases * g) / 8 + 256;
-    cap[SFQ_S_GEN_NN] = ((uint64_t)m->nbases * g) / 8 + 256;
-    cap[SFQ_S_REC_X] = (uint64_t)m->hdr_bytes * g + 16ull * m->nrec + 256;
-    cap[SFQ_S_USR_X] = 8ull * m->nrec * g + 256;
-    cap[SFQ_S_USR_XQ] = 8ull * m->nrec * g + 256;
-    cap[SFQ_S_USR_PFG] = 4ull * m->nrec * g + 256;
-    cap[SFQ_S_USR_PFQ] = 4ull * m->nrec * g + 256;
+    // first try: what real data needs with room to spare (2.25 bit per base, 6 bit per quality, half of the header bytes, one
+    // N exception per 64 bases, a length exception for every record); every retry doubles
+    cap[SFQ_S_REC] = ((uint64_t)m->hdr_bytes * g) / 2 + 4ull * m->nrec * g + 256;
+    cap[SFQ_S_GEN] = ((uint64_t)m->nbases * g * 9) / 32 + 256;
+    cap[SFQ_S_QLT] = ((uint64_t)m->nquals * g * 3) / 4 + 256;
+    cap[SFQ_S_GEN_NS] = ((uint64_t)m->nbases * g) / 64 + 256;
+    cap[SFQ_S_GEN_NN] = ((uint64_t)m->nbases * g) / 64 + 256;
+    cap[SFQ_S_REC_X] = ((uint64_t)m->hdr_bytes * g) / 4 + 4ull * m->nrec * g + 256;
+    cap[SFQ_S_USR_X] = 4ull * m->nrec * g + 256;
+    cap[SFQ_S_USR_XQ] = 4ull * m->nrec * g + 256;
+    cap[SFQ_S_USR_PFG] = 2ull * m->nrec * g + 256;
+    cap[SFQ_S_USR_PFQ] = 2ull * m->nrec * g + 256;
     // oversized records, character by character through an adaptive 256-symbol model: rarely more than a byte per character
     cap[SFQ_S_USR_LREC] = m->nbig ? ((uint64_t)m->big_hdr + 16ull * m->nbig) * g * 2 + 256 : 64;
     cap[SFQ_S_USR_LGEN] = m->nbig ? ((uint64_t)m->big_bases + 2ull * m->nbig) * g * 2 + 256 : 64;

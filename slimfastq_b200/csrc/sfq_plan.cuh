@@ -34,8 +34,9 @@ SFQ_HD bool sfq_is_big(uint64_t hdr_chars, uint64_t base_chars, uint64_t qual_ch
 }
 
 // Fills `m` for the chunk made of records [r0, r1).  nrec == 0 chunks are left empty (text_len 0).
-// `rec_qoff` (may be null): rec_qoff[r - r0] = index of record r's first coded quality within the chunk.
-SFQ_HDN void sfq_plan_chunk(const uint8_t *text, const uint64_t *ls, uint64_t r0, uint64_t r1, SfqChunkMeta *m, uint32_t *rec_qoff = nullptr) {
+// `rec_qoff` / `rec_boff` (may be null): [r - r0] = index of record r's first coded quality / base within the chunk.
+SFQ_HDN void sfq_plan_chunk(const uint8_t *text, const uint64_t *ls, uint64_t r0, uint64_t r1, SfqChunkMeta *m, uint32_t *rec_qoff = nullptr,
+                            uint32_t *rec_boff = nullptr) {
     m->line0 = 4 * r0;
     m->text_off = ls[4 * r0];
     m->text_len = ls[4 * r1] - ls[4 * r0];
@@ -86,6 +87,7 @@ SFQ_HDN void sfq_plan_chunk(const uint8_t *text, const uint64_t *ls, uint64_t r0
         const uint32_t recno = (uint32_t)(r - r0 + 1);
         if (hl == 0 || text[l[0]] != '@') { status = SFQ_E_AT; arg = recno; break; }
         if (rec_qoff) rec_qoff[r - r0] = (uint32_t)nq;
+        if (rec_boff) rec_boff[r - r0] = (uint32_t)nb;
         // (a SOLiD line always gives up its first character, usrs.cpp:324-329; an empty one is caught below)
         if (sfq_is_big(hl - 1, sl >= solid ? sl - solid : 0, ql >= solid ? ql - solid : 0)) {
             if (!sfq_is_big(hl - 1, sl >= solid ? sl - solid : 0, 0)) {

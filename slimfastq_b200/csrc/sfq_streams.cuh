@@ -540,40 +540,44 @@ SFQ_HD bool sfq_map_space(SfqSpaceMap &m, const uint8_t *p) {
         }
     }
 }
-// numberwang (recs.cpp:192-262)
+// What kind of number, if any, a header field is (the verdict of recs.cpp:192-262): one pass classifies the characters
+// after an optional single leading zero, then the value is accumulated in the base the classes call for.
+//   classes   0 = decimal digit, 1 = a-f, 2 = A-F, 3 = anything else
+//   decimal   every character a digit and the previous value of the field was not hexadecimal (pctype != 2); a value
+//             that wraps 64 bits on the way (value * 10 + digit < value) makes the field a string
+//   hex       at most 16 characters over all, one letter case only; tried when the previous value was hexadecimal or
+//             when the first non-digit is a hex letter
+// Two leading zeros cannot be reproduced by the decoder's "%lld" / "%llx": string.
+SFQ_HD uint32_t sfq_hex_class(uint8_t c) {
+    return (uint32_t)(c - '0') < 10u ? 0u : (uint32_t)(c - 'a') < 6u ? 1u : (uint32_t)(c - 'A') < 6u ? 2u : 3u;
+}
+SFQ_HD uint32_t sfq_hex_value(uint8_t c) { return (c & 0x40u) ? (c & 7u) + 9u : (uint32_t)(c - '0'); }
 SFQ_HD uint32_t sfq_numberwang(const uint8_t *p, uint32_t len, uint64_t &num, uint8_t pctype) {
-    uint32_t i = 0;
-    const bool has_z = p[0] == '0';
-    if (has_z && p[++i] == '0') return SFQ_ST_STR;
-    uint32_t caps = 0;
+    const bool lead0 = p[0] == '0';
+    if (lead0 && p[1] == '0') return SFQ_ST_STR;
+    const uint32_t from = lead0 ? 1u : 0u;
+    uint32_t seen = 0, run = 0;                        // classes met; length of the leading run of digits
+    for (uint32_t k = from; k < len; k++) {
+        const uint32_t cls = sfq_hex_class(p[k]);
+        if (!seen || seen == 1u) run += cls == 0u;     // still inside the leading digit run
+        seen |= 1u << cls;
+    }
     num = 0;
-    while (pctype != 2) {
-        if (i >= len) return has_z ? SFQ_ST_DGT_Z : SFQ_ST_DGT;
-        const uint8_t c = p[i];
-        if (sfq_is_dig(c)) {
-            const uint64_t t = (num << 3) + (num << 1) + c - '0';
-            i++;
-            if (t < num) return SFQ_ST_STR;
-            num = t;
-            continue;
+    if (pctype != 2) {
+        uint64_t v = 0;
+        for (uint32_t k = from; k < from + run; k++) {
+            const uint64_t t = v * 10u + (uint64_t)(p[k] - '0');
+            if (t < v) return SFQ_ST_STR;
+            v = t;
         }
-        if ((c | 0x20) < 'a' || (c | 0x20) > 'f') return SFQ_ST_STR;
-        caps = 1u + (c < 'a');
-        i = has_z;
-        num = 0;
-        break;
+        if (from + run >= len) { num = v; return lead0 ? SFQ_ST_DGT_Z : SFQ_ST_DGT; }
+        if (sfq_hex_class(p[from + run]) == 3u) return SFQ_ST_STR;
     }
-    if (len > 16) return SFQ_ST_STR;
-    for (; i < len; i++) {
-        const uint8_t c = p[i];
-        uint32_t nib;
-        if (sfq_is_dig(c)) nib = c - '0';
-        else if (c >= 'a' && c <= 'f') { if (caps == 2) return SFQ_ST_STR; caps = 1; nib = 10u + c - 'a'; }
-        else if (c >= 'A' && c <= 'F') { if (caps == 1) return SFQ_ST_STR; caps = 2; nib = 10u + c - 'A'; }
-        else return SFQ_ST_STR;
-        num = (num << 4) + nib;
-    }
-    return caps == 2 ? (has_z ? SFQ_ST_HGTC_Z : SFQ_ST_HGTC) : (has_z ? SFQ_ST_HGT_Z : SFQ_ST_HGT);
+    if (len > 16 || (seen & 8u) || (seen & 6u) == 6u) return SFQ_ST_STR;
+    uint64_t v = 0;
+    for (uint32_t k = from; k < len; k++) v = (v << 4) + sfq_hex_value(p[k]);
+    num = v;
+    return (seen & 4u) ? (lead0 ? SFQ_ST_HGTC_Z : SFQ_ST_HGTC) : (lead0 ? SFQ_ST_HGT_Z : SFQ_ST_HGT);
 }
 
 struct SfqFieldRangers {                              // RecBase::ranger_t, recs.hpp:42-46

@@ -80,7 +80,13 @@ static inline bool sfq_worm_write(const SfqBlobHeader &b, const uint8_t *rec_fir
     add("whoami", "slimfastq");
     add("version", std::to_string(SFQ_INTERNAL_VERSION));
     add("config.level", std::to_string(b.level));
-    add("orig.filename", orig_filename && *orig_filename ? orig_filename : "<< stdin >>");
+    {   // the reference reads an info line into 512 bytes and refuses values of 0x1ff+ characters (config.cpp:87-107,134-140):
+        // a longer path travels as its last component, cut if need be
+        std::string fn = orig_filename && *orig_filename ? orig_filename : "<< stdin >>";
+        if (fn.size() >= 0x1e0) { const size_t sl = fn.rfind('/'); if (sl != std::string::npos) fn = fn.substr(sl + 1); }
+        if (fn.size() >= 0x1e0) fn.resize(0x1df);
+        add("orig.filename", fn);
+    }
     add("orig.size", std::to_string((unsigned long long)b.text_len));
     if (b.solid) add("usr.solid", "1");
     if (b.nbig < b.nrec || b.llen) {               // (a file of oversized records only has neither key, usrs.cpp:190-198)
