@@ -24,7 +24,7 @@ class _Chunk(C.Structure):
     _fields_ = [
         ("level", C.c_int32), ("llen", C.c_int32), ("solid", C.c_int32), ("two_id", C.c_int32),
         ("n_byte", C.c_int32), ("extra_hi_qlt", C.c_uint32), ("num_records", C.c_uint64),
-        ("rec_first", C.c_char * 0x200), ("rec_first_len", C.c_uint32),
+        ("version", C.c_int32), ("rec_first", C.c_char * 0x200), ("rec_first_len", C.c_uint32),
         ("data", C.POINTER(C.c_uint8) * NSTREAMS), ("size", C.c_size_t * NSTREAMS),
     ]
 
@@ -40,6 +40,7 @@ class Encoded:
     num_records: int
     rec_first: bytes
     streams: dict[str, bytes] = field(default_factory=dict)
+    version: int = 6            # info key `version`; < 5 = pre-v5 header stream (recs.cpp:397-398)
 
     def info_tuple(self):
         return (self.level, self.llen, self.solid, self.two_id, self.n_byte, self.num_records, self.rec_first)
@@ -64,6 +65,8 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.sfq_oracle_encode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_Chunk), C.c_char_p]
         _lib.sfq_oracle_encode.restype = C.c_int
+        _lib.sfq_oracle_encode_pre5.argtypes = _lib.sfq_oracle_encode.argtypes
+        _lib.sfq_oracle_encode_pre5.restype = C.c_int
         _lib.sfq_oracle_decode.argtypes = [C.POINTER(_Chunk), C.POINTER(C.POINTER(C.c_uint8)),
                                            C.POINTER(C.c_size_t), C.c_char_p]
         _lib.sfq_oracle_decode.restype = C.c_int
@@ -72,17 +75,17 @@ def lib():
     return _lib
 
 
-def encode(fastq: bytes, level: int) -> Encoded:
+def encode(fastq: bytes, level: int, pre5: bool = False) -> Encoded:
     ck = _Chunk()
     err = C.create_string_buffer(256)
-    if lib().sfq_oracle_encode(fastq, len(fastq), level, C.byref(ck), err):
+    if (lib().sfq_oracle_encode_pre5 if pre5 else lib().sfq_oracle_encode)(fastq, len(fastq), level, C.byref(ck), err):
         raise OracleError(err.value.decode("latin1"))
     streams = {}
     for i, nm in enumerate(STREAM_NAMES):
         if ck.size[i]:
             streams[nm] = C.string_at(ck.data[i], ck.size[i])
     enc = Encoded(ck.level, ck.llen, ck.solid, ck.two_id, ck.n_byte, ck.num_records,
-                  C.string_at(ck.rec_first, ck.rec_first_len), streams)
+                  C.string_at(ck.rec_first, ck.rec_first_len), streams, ck.version)
     lib().sfq_oracle_free_chunk(C.byref(ck))
     return enc
 
@@ -91,6 +94,7 @@ def decode(enc: Encoded) -> bytes:
     ck = _Chunk()
     ck.level, ck.llen, ck.solid, ck.two_id = enc.level, enc.llen, enc.solid, enc.two_id
     ck.n_byte, ck.num_records = enc.n_byte, enc.num_records
+    ck.version = enc.version
     ck.rec_first = enc.rec_first
     ck.rec_first_len = len(enc.rec_first)
     keep = []

@@ -335,6 +335,7 @@ typedef struct {
     uint64_t cnumb[2][65];
     int imap, initialized;
     uint64_t index;            /* m_last.index */
+    int pre5;                  /* header stream of format versions < 5 (recs.cpp:397-398, 463-510) */
 } hmodel;
 enum { ST_DGT = 0, ST_DLT, ST_STR, ST_HGT, ST_HLT, ST_HGT_Z, ST_HLT_Z, ST_HGTC, ST_HLTC,
        ST_HGTC_Z, ST_HLTC_Z, ST_DGT_Z, ST_DLT_Z };
@@ -390,6 +391,38 @@ static int numberwang(const uint8_t *p, int len, uint64_t *num, uint8_t pctype) 
     }
     return caps == 2 ? (has_z ? ST_HGTC_Z : ST_HGTC) : (has_z ? ST_HGT_Z : ST_HGT);
 }
+static int is_number(const uint8_t *p, int len, long long *num) {                      /* recs.cpp:265-275 */
+    if (*p == '0') return 0;
+    *num = 0;
+    for (int i = 0; i < len; i++) {
+        if (!is_dig(p[i])) return 0;
+        *num = (long long)(((unsigned long long)*num << 3) + ((unsigned long long)*num << 1) + (unsigned long long)(p[i] - '0'));
+    }
+    return 1;
+}
+/* the fields of a changed header as load_pre5 expects them (test-side encoder, see sfq_oracle.h) */
+static void h_save_pre5_fields(hmodel *h, rc_enc *rc, const spacemap *S, const spacemap *Pm, uint64_t map,
+                               const uint8_t *buf, const uint8_t *prev) {
+    for (int i = 0; i < S->len; i++) {
+        if (!(map & (1ULL << (i & 63)))) continue;
+        const uint8_t *b = buf + S->off[i];
+        hranger *R = &h->ranger[i + 1];
+        long long pval = 0, cval = 0;
+        int numeric = is_number(prev + Pm->off[i], Pm->wln[i], &pval) && Pm->wln[i] < 18 && S->wln[i] > 0 && S->wln[i] < 18;
+        if (numeric) {                     /* what "%lld" prints must be the field itself: digits, no leading zero except "0" */
+            if (b[0] == '0') numeric = S->wln[i] == 1;
+            for (int j = 0; j < S->wln[i] && numeric; j++) { if (!is_dig(b[j])) numeric = 0; else cval = cval * 10 + (b[j] - '0'); }
+        }
+        if (!numeric) {
+            PW_PUT(&R->type, rc, (uint32_t)ST_STR);
+            pu_put(&R->num, rc, (uint64_t)S->wln[i]);
+            for (int j = 0; j < S->wln[i]; j++) PW_PUT(&R->str, rc, b[j]);
+            continue;
+        }
+        PW_PUT(&R->type, rc, (uint32_t)(cval >= pval ? ST_DGT : ST_DLT));
+        pu_put(&R->num, rc, (uint64_t)(cval >= pval ? cval - pval : pval - cval));
+    }
+}
 static void h_save(hmodel *h, rc_enc *rc, xsave *x_rec, uint64_t recno, const uint8_t *buf,
                    const uint8_t *end, const uint8_t *prev, sfq_or_chunk *out, errctx *e) {
     if (!h->initialized) {                                                             /* :279-286, 68-75 */
@@ -420,6 +453,7 @@ static void h_save(hmodel *h, rc_enc *rc, xsave *x_rec, uint64_t recno, const ui
         if (S->wln[i] != Pm->wln[i] || memcmp(buf + S->off[i], prev + Pm->off[i], (size_t)S->wln[i]))
             map |= 1ULL << (i & 63);                    /* x86 shift semantics of DO_SET at i==64 */
     pu_put(&h->ranger[0].num, rc, map);                                               /* :312 */
+    if (h->pre5) { h_save_pre5_fields(h, rc, S, Pm, map, buf, prev); return; }
     for (int i = 0; i < S->len; i++) {
         if (!(map & (1ULL << (i & 63)))) {
             h->ctype[im][i] = h->ctype[pm][i];
@@ -475,6 +509,30 @@ static size_t h_load(hmodel *h, rc_dec *rc, xload *x_rec, uint64_t recno, uint8_
     if (e->failed) return 0;
     uint64_t map = pu_get(&h->ranger[0].num, rc);
     uint8_t *b = buf;
+    if (h->pre5) {                                                                     /* load_pre5, :463-510 */
+        for (int i = 0; i < S->len; i++) {
+            if (map & (1ULL << (i & 63))) {
+                hranger *R = &h->ranger[i + 1];
+                int type = (int)PW_GET(&R->type, rc);
+                if (type == ST_DGT || type == ST_DLT) {
+                    long long pval = 0;
+                    if (!is_number(prev + S->off[i], S->wln[i], &pval)) { fail(e, "REC: pre-v5 numeric field after a non-number"); return 0; }   /* assert(expect_num) */
+                    long long gap = (long long)pu_get(&R->num, rc);
+                    long long val = type == ST_DGT ? (long long)((unsigned long long)pval + (unsigned long long)gap) : (long long)((unsigned long long)pval - (unsigned long long)gap);
+                    if (val == 0) *b++ = '0'; else b += fmt_u64(b, (uint64_t)val, 10, 0, 1);
+                } else if (type == ST_STR) {
+                    uint32_t len = (uint32_t)pu_get(&R->num, rc);
+                    for (uint32_t j = 0; j < len && (size_t)(b - buf) < 0x1f00; j++) *b++ = (uint8_t)PW_GET(&R->str, rc);
+                } else { fail(e, "REC: bad type value %d", type); return 0; }
+            } else {
+                memcpy(b, prev + S->off[i], (size_t)S->wln[i]);
+                b += S->wln[i];
+            }
+            *b++ = S->str[i];
+            if ((size_t)(b - buf) > 0x1f00) { fail(e, "decoded header too long"); return 0; }
+        }
+        return (size_t)(b - buf) - 1;
+    }
     for (int i = 0; i < S->len; i++) {
         if (!(map & (1ULL << (i & 63)))) {
             memcpy(b, prev + S->off[i], (size_t)S->wln[i]);
@@ -540,7 +598,10 @@ static long long scan_line(const uint8_t *buf, size_t n, size_t from, int limit)
     return -2;
 }
 
-int sfq_oracle_encode(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out, char *err) {
+static int encode_impl(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out, char *err, int pre5);
+int sfq_oracle_encode(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out, char *err) { return encode_impl(buf, n, level, out, err, 0); }
+int sfq_oracle_encode_pre5(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out, char *err) { return encode_impl(buf, n, level, out, err, 1); }
+static int encode_impl(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out, char *err, int pre5) {
     errctx e = { err, 0 };
     if (err) err[0] = 0;
     memset(out, 0, sizeof *out);
@@ -553,6 +614,8 @@ int sfq_oracle_encode(const uint8_t *buf, size_t n, int level, sfq_or_chunk *out
     memset(&rc_rec, 0, sizeof rc_rec); memset(&rc_gen, 0, sizeof rc_gen); memset(&rc_qlt, 0, sizeof rc_qlt);
     int okq = q_init(&Q, level), okg = g_init(&G, level), okh = h_init(&H);
     if (!xs || !okq || !okg || !okh) { fail(&e, "out of memory"); goto done; }
+    H.pre5 = pre5;
+    out->version = pre5 ? 4 : 6;
     enc_init(&rc_rec); enc_init(&rc_gen); enc_init(&rc_qlt);
     xsave *x_ns = &xs[0], *x_nn = &xs[1], *x_rec = &xs[2], *x_llen = &xs[3], *x_qlen = &xs[4],
           *x_sgen = &xs[5], *x_sqlt = &xs[6], *x_lrec = &xs[7], *x_lgen = &xs[8], *x_lqlt = &xs[9];
@@ -717,6 +780,7 @@ int sfq_oracle_decode(const sfq_or_chunk *in, uint8_t **outp, size_t *out_n, cha
             *m_qlt = (uint8_t *)malloc(MAX_GN_LLEN + 2);
     int okq = q_init(&Q, level), okg = g_init(&G, level), okh = h_init(&H);
     if (!xl || !m_rec || !m_gen || !m_qlt || !okq || !okg || !okh) { fail(&e, "out of memory"); goto done; }
+    H.pre5 = in->version < 5;                                                           /* (an absent key reads 0, config.cpp:373) */
     rc_dec rc_rec, rc_gen, rc_qlt;
     dec_init(&rc_rec, in->data[SFQ_OR_REC], in->size[SFQ_OR_REC]);
     dec_init(&rc_gen, in->data[SFQ_OR_GEN], in->size[SFQ_OR_GEN]);

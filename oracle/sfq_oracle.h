@@ -41,6 +41,7 @@ typedef struct sfq_or_chunk {
     int32_t  n_byte;         /* gen.N_byte, 0 when the key is absent ('N' implied)   */
     uint32_t extra_hi_qlt;   /* qlt.extra.hi (count of qualities >= 63)              */
     uint64_t num_records;    /* num_records                                          */
+    int32_t  version;        /* info key `version` (0 = absent); < 5 selects the pre-v5 header stream, recs.cpp:397-398 */
     char     rec_first[0x200];
     uint32_t rec_first_len;
     /* streams; size 0 and data NULL = the reference would not have created the stream */
@@ -54,6 +55,11 @@ const char *sfq_oracle_stream_name(int id);
  * (UsrSave::encode, usrs.cpp:392-407).  Returns 0, or non-zero with a croak-style message in
  * err[256].  Oversized records (usrs.hpp:34-36: id of 8 KiB or line of 64 KiB) go to usr.lrec / usr.lgen / usr.lqlt. */
 int sfq_oracle_encode(const uint8_t *fastq, size_t n, int level, sfq_or_chunk *out, char *err);
+/* Same, writing the header stream the way a pre-v5 slimfastq did (what RecLoad::load_pre5, recs.cpp:463-510, reads:
+ * decimal fields as DGT/DLT gaps against the previous header's TEXT, everything else as strings).  The reference
+ * ships no pre-v5 encoder; this one exists so that the legacy decode path can be tested, and it is pinned the other
+ * way round: the reference binary must decode what it writes (tests/test_legacy.py). */
+int sfq_oracle_encode_pre5(const uint8_t *fastq, size_t n, int level, sfq_or_chunk *out, char *err);
 
 /* Decode (UsrLoad::decode, usrs.cpp:539-574).  *out is malloc'ed. */
 int sfq_oracle_decode(const sfq_or_chunk *in, uint8_t **out, size_t *out_n, char *err);

@@ -1028,7 +1028,7 @@ int sfq_import_reference(const uint8_t *ref, size_t n, uint8_t *out, size_t out_
         b.two_id = num("usr.2id", 0) != 0;
         const long long nb = num("gen.N_byte", 'N');
         b.n_byte = (nb && nb != 'N') ? (uint8_t)nb : 0;
-        b.pad = SFQ_BLOB_IMPORTED;
+        b.pad = SFQ_BLOB_IMPORTED | (num("version", 0) < 5 ? SFQ_BLOB_PRE5 : 0u);         // recs.cpp:397-398: header stream of the older layout
         b.extra_hi = (uint32_t)num("qlt.extra.hi", 0);
         // oversized records: their count is not recorded either; the planes' upper bounds (orig.size) cover them
         b.nbig = 0; b.big_bases = b.big_quals = b.big_hdr = 0;

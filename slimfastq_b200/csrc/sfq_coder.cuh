@@ -455,26 +455,55 @@ struct SfqPower {
             }
         }
     }
+    // The sixteen group sums and the sixteen slots of one group, each as four independent 16-byte loads: the walk over
+    // them then runs in registers.  (Read one word at a time in a loop, every step of the walk waited for its own L2 round
+    // trip: ~30 of them per coded symbol, which is what the header coders spent their time on.)
+    SFQ_HD void load16(const uint32_t *p, uint32_t (&w)[16]) const {
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const SfqU4 v = sfq_ld16(p + 4 * q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+    }
     template <class RC> SFQ_HD void put(RC &rc, uint32_t sym) {    // power_ranger.hpp:93-106
-        const uint32_t i = (uint32_t)inv()[sym] ^ sym, g = i >> 4;
-        const uint32_t f = freq_of(m[i]), tot = m[336];
-        uint32_t sumf = 0;
-        for (uint32_t j = 0; j < g; j++) sumf += gsum()[j];
-        for (uint32_t k = 16 * g; k < i; k++) sumf += freq_of(m[k]);
+        const uint32_t i = (uint32_t)inv()[sym] ^ sym, g = i >> 4, k = i & 15u;
+        uint32_t gs[16], sl[16];
+        load16(gsum(), gs);
+        load16(m + 16u * g, sl);
+        const uint32_t tot = m[336];
+        uint32_t sumf = 0, f = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j++) {
+            sumf += j < g ? gs[j] : 0u;
+            sumf += j < k ? freq_of(sl[j]) : 0u;
+            f = j == k ? freq_of(sl[j]) : f;
+        }
         rc.encode(sumf + i, f + 1u, tot + 256u);
         update(i, f, sym, tot);
     }
     template <class RC> SFQ_HD uint32_t get(RC &rc) {              // power_ranger.hpp:108-130
         const uint32_t tot = m[336];
+        uint32_t gs[16];
+        load16(gsum(), gs);
         const uint32_t prob = rc.get_freq(tot + 256u);
         uint32_t cum = 0, g = 0;
-        for (; g < 15; g++) { const uint32_t t = gsum()[g] + 16u; if (cum + t <= prob) cum += t; else break; }
-        uint32_t i = 16 * g, f;
-        for (;; i++) {
-            f = freq_of(m[i]);
-            if (i < 16 * g + 15 && cum + f + 1u <= prob) cum += f + 1u; else break;   // the last slot also catches a corrupt stream
+        bool go = true;
+#pragma unroll
+        for (uint32_t j = 0; j < 15; j++) {                        // the last group also catches a corrupt stream
+            const uint32_t t = gs[j] + 16u;
+            go = go && cum + t <= prob;
+            cum += go ? t : 0u; g += go ? 1u : 0u;
         }
-        const uint32_t sym = sym_of(m[i], i);
+        uint32_t sl[16];
+        load16(m + 16u * g, sl);
+        uint32_t k = 0, f = freq_of(sl[0]), word = sl[0];
+        go = true;
+#pragma unroll
+        for (uint32_t j = 0; j < 15; j++) {                        // the last slot also catches a corrupt stream
+            const uint32_t fj = freq_of(sl[j]);
+            go = go && cum + fj + 1u <= prob;
+            cum += go ? fj + 1u : 0u; k += go ? 1u : 0u;
+            f = go ? freq_of(sl[j + 1]) : f; word = go ? sl[j + 1] : word;
+        }
+        const uint32_t i = 16u * g + k;
+        const uint32_t sym = sym_of(word, i);
         rc.decode(cum, f + 1u);
         update(i, f, sym, tot);
         return sym;

@@ -24,6 +24,10 @@
 // plane sizes - nbases / nquals / hdr_bytes / out_len are upper bounds (from orig.size), the decoder
 // establishes the real ones from the usr.* streams.
 #define SFQ_BLOB_IMPORTED 1u
+// Blob flag: the header stream (`rec`) is in the layout of format versions below 5 (the file's `version` info key is
+// below 5 or missing): decimal fields as gaps against the previous header's text, everything else as strings
+// (RecLoad::load_pre5, recs.cpp:397-398, 463-510).  Only ever set on import; this library writes version 6.
+#define SFQ_BLOB_PRE5 2u
 
 #pragma pack(push, 1)
 struct SfqFileHeader {

@@ -188,7 +188,7 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
         pwq = ws.pw + ((size_t)c * SFQ_PW_PER_CHUNK + SFQ_PW_QEX) * SFQ_PW_WORDS;
         qlen_tab = t.qlen + d.rec_base;
         rc.start(in + d.soff[SFQ_S_QLT], d.ssize[SFQ_S_QLT]);
-        oplane = quals + d.qual_plane;
+        oplane = quals + d.qual_plane + metas[c].big_quals;      // (oversized records' quality lines sit at the front of the chunk's plane)
     }
     tab += l8 * G::WPL;                                          // this lane's words of every entry
     // decoded qualities of a chunk are contiguous in the plane: eight bytes are gathered in two registers and

@@ -854,6 +854,7 @@ SFQ_HDN void sfq_rec_decode_chunk(const uint8_t *in, const uint32_t *ssize, cons
     uint32_t imap = 0;
     uint64_t x_index = x_rec.get();                                             // recs.cpp:104-105
     uint64_t pos = meta->nbig ? meta->big_hdr : 0;                              // oversized records' lines sit at the front of the plane
+    const bool pre5 = (meta->pad & 2u) != 0;                                    // SFQ_BLOB_PRE5
     const uint8_t *prev = nullptr;
     bool have_first = false;
     uint32_t status = SFQ_OK;
@@ -889,6 +890,32 @@ SFQ_HDN void sfq_rec_decode_chunk(const uint8_t *in, const uint32_t *ssize, cons
                 bool bad = false;
                 for (uint32_t i = 0; i < S.len; i++) {
                     if ((uint64_t)(b - buf) + S.wln[i] + 44ull > room) { bad = true; break; }
+                    if (pre5) {                                                 // RecLoad::load_pre5, recs.cpp:463-510
+                        if (map & (1ULL << (i & 63u))) {
+                            SfqFieldRangers R; R.bind(pwpool, i + 1);
+                            const uint32_t type = R.type.get(rc);
+                            if (type == SFQ_ST_DGT || type == SFQ_ST_DLT) {
+                                // the previous header's field, read as a number (is_number, recs.cpp:265-275: no leading zero)
+                                const uint8_t *pf = prev + S.off[i];
+                                uint64_t pval = 0;
+                                bool isnum = pf[0] != '0';
+                                for (uint32_t k = 0; k < S.wln[i] && isnum; k++) { if (sfq_is_dig(pf[k])) pval = pval * 10u + (uint64_t)(pf[k] - '0'); else isnum = false; }
+                                if (!isnum) { bad = true; break; }              // (the reference asserts)
+                                const uint64_t gap = R.num.get(rc);
+                                const uint64_t val = type == SFQ_ST_DGT ? pval + gap : pval - gap;
+                                if (val == 0) *b++ = '0'; else b += sfq_fmt_u64(b, val, 10u, false, true);
+                            } else if (type == SFQ_ST_STR) {
+                                const uint64_t len = R.num.get(rc);
+                                if ((uint64_t)(b - buf) + len + 2ull > room) { bad = true; break; }
+                                for (uint32_t j = 0; j < (uint32_t)len; j++) *b++ = (uint8_t)R.str.get(rc);
+                            } else { bad = true; break; }
+                        } else {
+                            const uint8_t *src = prev + S.off[i];
+                            for (uint32_t k = 0; k < S.wln[i]; k++) *b++ = src[k];
+                        }
+                        *b++ = S.str[i];
+                        continue;
+                    }
                     if (!(map & (1ULL << (i & 63u)))) {
                         const uint8_t *src = prev + S.off[i];
                         for (uint32_t k = 0; k < S.wln[i]; k++) *b++ = src[k];

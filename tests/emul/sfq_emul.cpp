@@ -176,7 +176,7 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **ou
         SfqChunkMeta m; memset(&m, 0, sizeof m);
         m.nrec = b.nrec; m.nbases = b.nbases; m.nquals = b.nquals; m.hdr_bytes = b.hdr_bytes; m.llen = b.llen;
         m.solid = b.solid; m.two_id = b.two_id; m.n_byte = b.n_byte; m.text_len = b.text_len; m.out_len = b.out_len;
-        m.nbig = b.nbig; m.big_bases = b.big_bases; m.big_quals = b.big_quals; m.big_hdr = b.big_hdr;
+        m.nbig = b.nbig; m.big_bases = b.big_bases; m.big_quals = b.big_quals; m.big_hdr = b.big_hdr; m.pad = b.pad;
         const int level = (int)b.level;
         uint64_t soff[SFQ_NSTREAMS]; uint32_t ssize[SFQ_NSTREAMS];
         uint64_t o = off + sizeof b + b.rec_first_len;

@@ -37,3 +37,18 @@ def summarize(data: bytes, blob: bytes) -> dict:
                 h.update(nm.encode() + b":" + md5(ch.streams[nm]).encode())
         h.update(repr(ch.info_tuple()).encode())
     return {"nchunks": len(ct.chunks), "stream_bytes": ct.stream_bytes, "digest": h.hexdigest()}
+
+
+def container_from_oracle(enc, orig_size: int, flags: int = 1) -> bytes:
+    """A single-chunk container around the streams of an oracle / reference `Encoded` (what sfq_import_reference builds
+    from a reference file): plane sizes are upper bounds (flag 1 = SFQ_BLOB_IMPORTED), flag 2 = SFQ_BLOB_PRE5."""
+    import struct
+
+    ss = [len(enc.streams.get(nm, b"")) for nm in K.STREAM_NAMES]
+    hdr = K.BLOB_HDR.pack(K.BLOB_MAGIC, enc.level, orig_size, orig_size + 16 * enc.num_records + 4096, enc.num_records,
+                          orig_size, orig_size, orig_size, enc.llen, enc.solid, enc.two_id, enc.n_byte if enc.n_byte != ord("N") else 0, flags,
+                          0, len(enc.rec_first), 0, 0, 0, 0, 0, 0, *ss)
+    body = hdr + enc.rec_first + b"".join(enc.streams.get(nm, b"") for nm in K.STREAM_NAMES)
+    index_off = K.FILE_HDR.size + len(body)
+    head = K.FILE_HDR.pack(K.STAMP, K.KIND, 6, enc.level, orig_size, 1, orig_size, index_off, orig_size + 16 * enc.num_records + 4096)
+    return head + body + struct.pack("<Q", K.FILE_HDR.size)
