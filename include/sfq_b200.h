@@ -111,6 +111,24 @@ int sfq_decompressed_size(const uint8_t *sfq, size_t n, uint64_t *out_n, int *le
 
 int sfq_get_stats(const sfq_ctx *ctx, sfq_stats *st);
 
+/* ---- per-plane test hooks ---------------------------------------------------------------------
+ * The three class pairs the reference drives per record - GenSave/GenLoad (gens.hpp:87-115), QltSave/QltLoad
+ * (qlts.hpp:79-116), RecSave/RecLoad (recs.hpp:87-107) with the UsrSave/UsrLoad framing streams - one plane at a time,
+ * so that a stream that differs from the reference's can be isolated from outside the library.
+ *   sfq_encode_<plane>_chunks   runs ONLY that plane's kernels over the FASTQ buffer; the container's chunks carry its
+ *                               streams (gen: gen gen.Ns gen.Nn | qlt: qlt | rec: rec rec.x usr.*) and sizes 0 elsewhere
+ *   sfq_decode_<plane>_chunks   runs ONLY that plane's decoder over a complete container and returns the plane as lines,
+ *                               one per record: base lines (exception lists applied; positions whose quality is '!' read
+ *                               as the coded base, the "'!' means N" rule needing the other plane, gens.cpp:200-213),
+ *                               quality lines, id lines
+ * Results are returned like sfq_compress / sfq_decompress return theirs. */
+int sfq_encode_gen_chunks(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes, const uint8_t **out, size_t *out_n);
+int sfq_encode_qlt_chunks(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes, const uint8_t **out, size_t *out_n);
+int sfq_encode_rec_chunks(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes, const uint8_t **out, size_t *out_n);
+int sfq_decode_gen_chunks(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **out, size_t *out_n);
+int sfq_decode_qlt_chunks(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **out, size_t *out_n);
+int sfq_decode_rec_chunks(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **out, size_t *out_n);
+
 /* ---- interchange with the reference's own file format -----------------------
  * The reference writes an 8 KiB-page WORM container (filer.cpp:41-303); one file = one set of streams,
  * i.e. exactly one chunk of this library's container.  These are host-side format conversions: no

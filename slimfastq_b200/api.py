@@ -45,6 +45,8 @@ EXPORTS = [
     "sfq_is_reference_file", "sfq_export_reference_bound", "sfq_export_reference",
     "sfq_import_reference_bound", "sfq_import_reference",
     "sfq_record_start_at_or_after", "sfq_last_record_start", "sfq_set_chunk_phase", "sfq_stream_cut",
+    "sfq_encode_gen_chunks", "sfq_encode_qlt_chunks", "sfq_encode_rec_chunks",
+    "sfq_decode_gen_chunks", "sfq_decode_qlt_chunks", "sfq_decode_rec_chunks",
 ]
 
 _lib = None
@@ -82,6 +84,9 @@ def load_library():
     L.sfq_record_start_at_or_after.argtypes = [vp, sz, sz]; L.sfq_record_start_at_or_after.restype = sz
     L.sfq_last_record_start.argtypes = [vp, sz]; L.sfq_last_record_start.restype = sz
     L.sfq_stream_cut.argtypes = [vp, sz, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]; L.sfq_stream_cut.restype = sz
+    for pl in ("gen", "qlt", "rec"):
+        f = getattr(L, f"sfq_encode_{pl}_chunks"); f.argtypes = L.sfq_compress.argtypes; f.restype = C.c_int
+        f = getattr(L, f"sfq_decode_{pl}_chunks"); f.argtypes = L.sfq_decompress.argtypes; f.restype = C.c_int
     _lib = L
     return L
 
@@ -160,6 +165,23 @@ class Codec:
     def decompress(self, sfq) -> bytes:
         addr, n = self.decompress_view(sfq)
         return C.string_at(addr, n)
+
+    # ---- per-plane test hooks (include/sfq_b200.h): one plane's coders only
+    def encode_plane(self, plane: str, fastq, level: int = 3, chunk_bytes: int = DEFAULT_CHUNK) -> bytes:
+        addr, n, keep = _host_ptr(fastq)
+        out = C.POINTER(C.c_uint8)()
+        on = C.c_size_t()
+        self._check(getattr(self._L, f"sfq_encode_{plane}_chunks")(self._h, addr, n, level, chunk_bytes, C.byref(out), C.byref(on)))
+        del keep
+        return C.string_at(out, on.value)
+
+    def decode_plane(self, plane: str, sfq) -> bytes:
+        addr, n, keep = _host_ptr(sfq)
+        out = C.POINTER(C.c_uint8)()
+        on = C.c_size_t()
+        self._check(getattr(self._L, f"sfq_decode_{plane}_chunks")(self._h, addr, n, C.byref(out), C.byref(on)))
+        del keep
+        return C.string_at(out, on.value)
 
     # ---- device-resident variants (torch CUDA uint8 tensors; caller synchronises its own stream first)
     def compress_device(self, d_fastq, d_out, level: int = 3, chunk_bytes: int = DEFAULT_CHUNK, nbytes: int | None = None) -> int:

@@ -97,6 +97,7 @@ struct sfq_ctx {
     int gdec32 = 0;                         // SFQ_GDEC=1: warp-converged base decoder (A/B; slower)
     uint32_t qlpc = 0;                      // SFQ_QLPC=4|8: lanes per chunk of the quality decoder (0 = by wave size)
     int gm_variant = 0;                     // SFQ_GM_VARIANT: register budget / batch of k_gen_model (A/B runs)
+    int plane_mask = 7;                     // per-plane test hooks: 1 = gen, 2 = qlt, 4 = rec paths run (7 = the product)
     bool q_scatter1 = false;                // SFQ_QSCATTER=1: one-pass quality scatter over 65 536 global cursors (the round-1 form)
     bool gm_table = false;                  // SFQ_GM_TABLE=1: base models in a global hash table (k_gen_model, the round-1 form) instead of partitioned replay
     int gen_ahead2 = -1;                    // SFQ_GEN_AHEAD2=0/1: base decoder's two-ahead line prefetch (default on)
@@ -415,7 +416,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     CK(cudaStreamWaitEvent(s, ctx->head_ev, 0));
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
-                if (two_phase && !gm_table) {
+                if (!(ctx->plane_mask & 1)) {}
+                else if (two_phase && !gm_table) {
                     const bool gp_smem = (1u << gp_bits) <= SFQ_GP_SMEM_MAX;
                     TRACED("k_gen_keys", s, (k_gen_keys<<<dim3((wave_max_nrec + SFQ_GC_RECS - 1) / SFQ_GC_RECS, nc), 128, 0, s>>>(d_text, d_ls, d_metas + c0, ctx->rec_boff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
                     TRACED("k_gen_part", s, (k_gen_part<<<nc, 32, gp_smem ? (size_t)36 << gp_bits : 0, s>>>(d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, nc))); LAUNCHED();
@@ -436,7 +438,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 if (!(two_phase && ctx->enc_order == 1)) CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
-                if (two_phase) {
+                if (!(ctx->plane_mask & 2)) {}
+                else if (two_phase) {
                     cudaStream_t q = side0;
                     if (ctx->enc_order != 1) {
                         TRACED("k_qlt_keys", q, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
@@ -455,9 +458,9 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
-                {
-                    const uint32_t rl = ctx->lanes ? ctx->lanes : ctx->enc_rec_lanes ? ctx->enc_rec_lanes : lanes;
-                    TRACED("k_encode<2>", side1, (k_encode<2><<<(nc + rl - 1) / rl, 32, 0, side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, rl))); LAUNCHED();
+                if (ctx->plane_mask & 4) {
+                    const uint32_t rl = ctx->lanes ? ctx->lanes : ctx->enc_rec_lanes ? ctx->enc_rec_lanes : std::min(lanes, 8u);
+                    TRACED("k_encode<2>", side1, (k_encode<2><<<(nc + rl - 1) / rl, 32, rl * sizeof(SfqRecScratch), side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, rl))); LAUNCHED();
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
@@ -653,7 +656,8 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 // the quality decoder is the longest chain of the three: it goes first (and on the high-priority
                 // stream) so that its warps are all resident from the start; gen and rec fill in around it
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
-                if (ctx->qdec_octets) {
+                if (!(ctx->plane_mask & 2)) {}
+                else if (ctx->qdec_octets) {
                     // lanes per chunk: 8 while the chains are latency-bound, 4 (twice the chunks per warp, a longer
                     // link) once a wave is large enough for issue slots to be what its warps compete for
                     const uint32_t lpc = ctx->qlpc ? ctx->qlpc : nc >= 4096u ? 4u : 8u;
@@ -667,13 +671,14 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
                 // base decoder: thread per chunk, `lanes` chunks per warp.  (SFQ_GDEC=1 runs the warp-converged form,
                 // 32 chunks per warp: correct, but its link waits for the slowest of 32 table reads - 45 % slower, kept for A/B.)
-                if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
+                if (!(ctx->plane_mask & 1)) {}
+                else if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
                 else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, (spread == 1 || spread == 3) ? ctx->spread_smem[0] : 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
                 LAUNCHED();
-                k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED();
+                if (ctx->plane_mask & 1) { k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED(); }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
-                k_decode<2><<<(nb + dw - 1) / dw, 32 * dw, spread == 1 ? ctx->spread_smem[2] : 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED();
+                if (ctx->plane_mask & 4) { k_decode<2><<<(nb + dw - 1) / dw, 32 * dw, spread == 1 ? ctx->spread_smem[2] : 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED(); }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
                 CK(cudaEventRecord(ctx->join_ev[1], side1));
@@ -687,9 +692,10 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         // output layout from the decoded lengths; equals the recorded out_len except where the reference
         // itself prints a header differently from how it read it
         uint64_t *d_cout = ctx->blob_off.as<uint64_t>();
-        k_out_sizes<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks); LAUNCHED();
+        const int plane = ctx->plane_mask == 7 ? 0 : ctx->plane_mask;           // a per-plane hook prints one plane as lines
+        k_out_sizes<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks, plane); LAUNCHED();
         k_scan_u64<<<1, 1024, 0, s>>>(d_cout, nchunks, ctx->scalars.as<uint64_t>()); LAUNCHED();
-        k_out_offsets<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks); LAUNCHED();
+        k_out_offsets<<<(nchunks + 31) / 32, 32, 0, s>>>(d_dcs, d_metas, t, d_cout, nchunks, plane); LAUNCHED();
         CK(cudaMemcpyAsync(h_total, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, s));
         std::vector<SfqChunkMeta> got(nchunks);
         CK(cudaMemcpyAsync(got.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
@@ -707,6 +713,11 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
     }
     no = *h_total;
     if (no > out_cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)no);
+    if (ctx->plane_mask != 7) {
+        const int plane = ctx->plane_mask;
+        k_plane_lines<<<(unsigned)((nrec * 32 + 255) / 256), 256, 0, s>>>(d_metas, t, ctx->rec_chunk.as<uint32_t>(),
+            plane == 1 ? ctx->bases.as<uint8_t>() : plane == 2 ? ctx->quals.as<uint8_t>() : ctx->hdrs.as<uint8_t>(), plane, d_out, nrec); LAUNCHED();
+    } else
     k_assemble<<<(unsigned)((nrec * 32 + 255) / 256), 256, 0, s>>>(d_dcs, d_metas, t, ctx->rec_chunk.as<uint32_t>(), ctx->bases.as<uint8_t>(),
                                                                    ctx->quals.as<uint8_t>(), ctx->hdrs.as<uint8_t>(), d_out, nrec); LAUNCHED();
     CK(cudaEventRecord(ctx->ev[EV_CODE_END], s));
@@ -797,7 +808,8 @@ int sfq_create(sfq_ctx **out, int device) {
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->head_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaFuncSetAttribute(k_gen_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SFQ_GR_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_gen_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(36u * SFQ_GP_SMEM_MAX)) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+        cudaFuncSetAttribute(k_gen_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(36u * SFQ_GP_SMEM_MAX)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_encode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * sizeof(SfqRecScratch))) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     {   // shared memory the decoders' CTAs reserve when they are spread (one of each kind per SM fits, two of a kind barely)
         int smem_sm = 0;
         cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
@@ -923,6 +935,21 @@ int sfq_decompress(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **o
         return 0;
     } catch (const std::bad_alloc &) { return ctx ? fail(ctx, SFQ_ERR_NOMEM, "out of host memory") : SFQ_ERR_NOMEM; }
 }
+
+// ------------------------------------------------------------------------------------------ per-plane test hooks
+static int plane_call(sfq_ctx *ctx, int plane, bool enc, const uint8_t *in, size_t n, int level, uint64_t chunk_bytes, const uint8_t **out, size_t *out_n) {
+    if (!ctx) return SFQ_ERR_ARG;
+    ctx->plane_mask = plane;
+    const int rc = enc ? sfq_compress(ctx, in, n, level, chunk_bytes, out, out_n) : sfq_decompress(ctx, in, n, out, out_n);
+    ctx->plane_mask = 7;
+    return rc;
+}
+int sfq_encode_gen_chunks(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes, const uint8_t **out, size_t *out_n) { return plane_call(ctx, 1, true, fastq, n, level, chunk_bytes, out, out_n); }
+int sfq_encode_qlt_chunks(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes, const uint8_t **out, size_t *out_n) { return plane_call(ctx, 2, true, fastq, n, level, chunk_bytes, out, out_n); }
+int sfq_encode_rec_chunks(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes, const uint8_t **out, size_t *out_n) { return plane_call(ctx, 4, true, fastq, n, level, chunk_bytes, out, out_n); }
+int sfq_decode_gen_chunks(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **out, size_t *out_n) { return plane_call(ctx, 1, false, sfq, n, 0, 0, out, out_n); }
+int sfq_decode_qlt_chunks(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **out, size_t *out_n) { return plane_call(ctx, 2, false, sfq, n, 0, 0, out, out_n); }
+int sfq_decode_rec_chunks(sfq_ctx *ctx, const uint8_t *sfq, size_t n, const uint8_t **out, size_t *out_n) { return plane_call(ctx, 4, false, sfq, n, 0, 0, out, out_n); }
 
 int sfq_decompress_device(sfq_ctx *ctx, const void *d_sfq, size_t n, void *d_out, size_t out_cap, size_t *out_n) {
     try {

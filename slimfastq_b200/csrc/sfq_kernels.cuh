@@ -156,7 +156,10 @@ k_encode(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqC
     if (m->status != SFQ_OK) return;
     uint32_t *pw = ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS;
     if (ROLE == 0) sfq_gen_encode_chunk(text, ls, m, level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw, arena_buf, &arenas[c]);
-    else sfq_rec_encode_chunk(text, ls, m, pw, arena_buf, &arenas[c]);
+    else {
+        extern __shared__ uint64_t rec_smem[];             // one SfqRecScratch per chunk-stream of the warp
+        sfq_rec_encode_chunk(text, ls, m, pw, arena_buf, &arenas[c], reinterpret_cast<SfqRecScratch *>(rec_smem) + threadIdx.x);
+    }
 }
 
 // `rec.first` (recs.cpp:68-75) = id line of the first record that went through the models; none if every record was oversized
@@ -326,7 +329,10 @@ k_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, Sfq
 
 // Output layout (UsrLoad::save line layout, usrs.cpp:512-529), from the decoded lengths: bytes per
 // chunk, exclusive prefix over all chunks of the container, then the offset of every record.
-__device__ __forceinline__ uint64_t sfq_rec_out_len(const SfqChunkMeta &m, const SfqRecTables &t, uint64_t k) {
+// `plane` 0 = the FASTQ text; 1 / 2 / 4 = one decoded plane as lines (per-plane test hooks): the record's base line,
+// quality line or id line (an oversized record's id + '+' line block) followed by a newline
+__device__ __forceinline__ uint64_t sfq_rec_out_len(const SfqChunkMeta &m, const SfqRecTables &t, uint64_t k, int plane = 0) {
+    if (plane) return 1ull + ((plane == 1 ? t.llen[k] : plane == 2 ? t.qlen[k] : t.hlen[k]) & ~SFQ_BIG_BIT);
     const uint32_t s = m.solid ? 1 : 0;
     // oversized: '@' id '\n' bases '\n' '+'line '\n' quals '\n', where hlen counts id + '\n' + '+'line
     if (t.hlen[k] & SFQ_BIG_BIT) return 4ull + (t.hlen[k] & ~SFQ_BIG_BIT) + (t.llen[k] & ~SFQ_BIG_BIT) + (t.qlen[k] & ~SFQ_BIG_BIT);
@@ -334,12 +340,12 @@ __device__ __forceinline__ uint64_t sfq_rec_out_len(const SfqChunkMeta &m, const
 }
 __global__ void __launch_bounds__(32)
 k_out_sizes(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ metas, SfqRecTables t,
-            uint64_t *chunk_out, uint32_t nchunks) {
+            uint64_t *chunk_out, uint32_t nchunks, int plane) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     uint64_t o = 0;
     if (metas[c].status == SFQ_OK)
-        for (uint32_t r = 0; r < metas[c].nrec; r++) o += sfq_rec_out_len(metas[c], t, dc[c].rec_base + r);
+        for (uint32_t r = 0; r < metas[c].nrec; r++) o += sfq_rec_out_len(metas[c], t, dc[c].rec_base + r, plane);
     chunk_out[c] = o;
 }
 __global__ void __launch_bounds__(1024)
@@ -362,14 +368,14 @@ k_scan_u64(uint64_t *v, uint32_t n, uint64_t *total) {        // in-place exclus
 }
 __global__ void __launch_bounds__(32)
 k_out_offsets(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ metas, SfqRecTables t,
-              const uint64_t *__restrict__ chunk_out_off, uint32_t nchunks) {
+              const uint64_t *__restrict__ chunk_out_off, uint32_t nchunks, int plane) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks || metas[c].status != SFQ_OK) return;
     uint64_t o = chunk_out_off[c];
     for (uint32_t r = 0; r < metas[c].nrec; r++) {
         const uint64_t k = dc[c].rec_base + r;
         t.ooff[k] = o;
-        o += sfq_rec_out_len(metas[c], t, k);
+        o += sfq_rec_out_len(metas[c], t, k, plane);
     }
 }
 
@@ -431,6 +437,21 @@ k_assemble(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ 
     if (m.solid) { if (lane == 0) o[0] = t.pfq[k]; o += 1; }
     for (uint32_t i = lane; i < qlen; i += 32) o[i] = q[i];
     if (lane == 0) o[qlen] = '\n';
+}
+
+// Per-plane test hooks: one warp per record copies the record's line of ONE decoded plane (bases with the exception
+// lists applied but without the "quality '!' means N" rule, which needs the other plane; qualities; id lines).
+__global__ void __launch_bounds__(256)
+k_plane_lines(const SfqChunkMeta *__restrict__ metas, SfqRecTables t, const uint32_t *__restrict__ rec_chunk,
+              const uint8_t *__restrict__ plane_buf, int plane, uint8_t *out, uint64_t nrec) {
+    const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (k >= nrec || metas[rec_chunk[k]].status != SFQ_OK) return;
+    const uint32_t len = (plane == 1 ? t.llen[k] : plane == 2 ? t.qlen[k] : t.hlen[k]) & ~SFQ_BIG_BIT;
+    const uint8_t *src = plane_buf + (plane == 1 ? t.boff[k] : plane == 2 ? t.qoff[k] : t.hoff[k]);
+    uint8_t *o = out + t.ooff[k];
+    for (uint32_t i = lane; i < len; i += 32) o[i] = plane == 1 ? (uint8_t)(src[i] & 0x7fu) : src[i];
+    if (lane == 0) o[len] = '\n';
 }
 
 // Blob headers of a device-resident container -> contiguous array (for the host to plan decode).

@@ -580,6 +580,24 @@ SFQ_HD uint32_t sfq_numberwang(const uint8_t *p, uint32_t len, uint64_t &num, ui
     return (seen & 4u) ? (lead0 ? SFQ_ST_HGTC_Z : SFQ_ST_HGTC) : (lead0 ? SFQ_ST_HGT_Z : SFQ_ST_HGT);
 }
 
+// Working state of one chunk's header coder.  On the device it lives in SHARED memory: as local arrays it sat in L1, and
+// L1 is what the coder kernels' neighbours on the SM take away (k_gen_replay and k_qlt_model carve 150-220 KB of shared
+// memory out of the 228 KB), so every byte of tokenising went to L2.  `hbuf` stages the current and the previous id line
+// (lines longer than the stage are read in place).
+#define SFQ_REC_STAGE 240u
+struct SfqRecScratch {
+    SfqSpaceMap smap[2];
+    uint64_t cnumb[2][65];
+    uint8_t ctype[2][65];
+    uint8_t hbuf[2][SFQ_REC_STAGE + 16];
+};
+// the id line `src` (hlen characters and the newline the tokeniser stops at) -> stage, or `src` itself if it does not fit
+SFQ_HD const uint8_t *sfq_rec_stage(uint8_t *stage, const uint8_t *src, uint32_t hlen) {
+    if (hlen + 1u > SFQ_REC_STAGE) return src;
+    for (uint32_t k = 0; k <= hlen; k++) stage[k] = src[k];
+    return stage;
+}
+
 struct SfqFieldRangers {                              // RecBase::ranger_t, recs.hpp:42-46
     SfqPower type, str;
     SfqPowerU num;
@@ -590,7 +608,7 @@ struct SfqFieldRangers {                              // RecBase::ranger_t, recs
 };
 
 SFQ_HDN void sfq_rec_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqChunkMeta *meta,
-                                  uint32_t *pwpool, uint8_t *arena, SfqArena *ar) {
+                                  uint32_t *pwpool, uint8_t *arena, SfqArena *ar, SfqRecScratch *scr) {
     SfqEnc rc;
     rc.start(arena + ar->off[SFQ_S_REC], ar->cap[SFQ_S_REC]);
     SfqXSave x_rec, x_llen, x_qlen, x_sgen, x_sqlt, x_lrec, x_lgen, x_lqlt;
@@ -603,11 +621,12 @@ SFQ_HDN void sfq_rec_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
     x_sgen.init(pwpool, SFQ_X_SGEN, arena + ar->off[SFQ_S_USR_PFG], ar->cap[SFQ_S_USR_PFG]);
     x_sqlt.init(pwpool, SFQ_X_SQLT, arena + ar->off[SFQ_S_USR_PFQ], ar->cap[SFQ_S_USR_PFQ]);
 
-    SfqSpaceMap smap[2];
-    uint8_t ctype[2][65];
-    uint64_t cnumb[2][65];
+    SfqSpaceMap (&smap)[2] = scr->smap;
+    uint8_t (&ctype)[2][65] = scr->ctype;
+    uint64_t (&cnumb)[2][65] = scr->cnumb;
     for (int a = 0; a < 2; a++) for (int b = 0; b < 65; b++) { ctype[a][b] = 0; cnumb[a][b] = 0; }
     smap[0].len = smap[1].len = 0;
+    uint32_t hflip = 0;                                // which stage holds the current id line
     uint32_t imap = 0;
     uint64_t x_index = 0;                              // RecBase::m_last.index
     const uint32_t solid = meta->solid;
@@ -651,7 +670,8 @@ SFQ_HDN void sfq_rec_encode_chunk(const uint8_t *text, const uint64_t *ls, SfqCh
         if (v.qlen != m_llen) { x_qlen.put(recno - i_qlen); x_qlen.put((uint16_t)v.qlen); i_qlen = recno; }
 
         // ---- header model (recs.cpp:277-372)
-        const uint8_t *buf = v.hdr;
+        hflip ^= 1u;
+        const uint8_t *buf = sfq_rec_stage(scr->hbuf[hflip], v.hdr, v.hlen);       // (`prev` keeps pointing at the other stage)
         if (!have_first) {
             // first header travels in clear as the `rec.first` info key (recs.cpp:68-75)
             if (v.hlen > 399) { status = SFQ_E_FIRSTHDR; break; }

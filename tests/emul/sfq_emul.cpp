@@ -132,7 +132,7 @@ extern "C" int sfq_emul_compress(const uint8_t *text_in, size_t n, int level, ui
                 emul_qlt_two_phase(text, ls.data(), &m, level, pw, arena.data(), &ar);
             } else
             sfq_qlt_encode_chunk(text, ls.data(), &m, level, qt, pw, arena.data(), &ar);
-            sfq_rec_encode_chunk(text, ls.data(), &m, pw, arena.data(), &ar);
+            { static SfqRecScratch scr; sfq_rec_encode_chunk(text, ls.data(), &m, pw, arena.data(), &ar, &scr); }
             free(gt); free(qt); free(pw);
             if ((m.status == SFQ_E_CAP || m.status == SFQ_E_TABLE) && grow < 6) continue;
             if (m.status) { *status_out = m.status; return 1; }

@@ -1,6 +1,6 @@
 # full GPU test-suite + 10 GB traces under a few knobs
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2e_pytest_gpu.log 2>&1; tail -8 gpurun_out/r2e_pytest_gpu.log
+timeout 1200 python -m pytest ${TESTS:-tests} -m gpu -x -q > gpurun_out/r2e_pytest_gpu.log 2>&1; tail -8 gpurun_out/r2e_pytest_gpu.log
 B="timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-extras"
 for knob in ${KNOBS:-A=1}; do
   env SFQ_TRACE=1 $knob $B --gb ${GB:-10} > gpurun_out/r2e_$knob.json 2> gpurun_out/r2e_$knob.err
