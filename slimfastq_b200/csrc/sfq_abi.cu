@@ -97,6 +97,7 @@ struct sfq_ctx {
     int gdec32 = 0;                         // SFQ_GDEC=1: warp-converged base decoder (A/B; slower)
     uint32_t qlpc = 0;                      // SFQ_QLPC=4|8: lanes per chunk of the quality decoder (0 = by wave size)
     int gm_variant = 0;                     // SFQ_GM_VARIANT: register budget / batch of k_gen_model (A/B runs)
+    bool enc_prio_gen = true;               // SFQ_ENC_PRIO=0: the high-priority stream goes to the quality path of a compress wave
     int plane_mask = 7;                     // per-plane test hooks: 1 = gen, 2 = qlt, 4 = rec paths run (7 = the product)
     bool q_scatter1 = false;                // SFQ_QSCATTER=1: one-pass quality scatter over 65 536 global cursors (the round-1 form)
     bool gm_table = false;                  // SFQ_GM_TABLE=1: base models in a global hash table (k_gen_model, the round-1 form) instead of partitioned replay
@@ -179,7 +180,7 @@ int status_to_error(sfq_ctx *ctx, const SfqChunkMeta &m, uint64_t chunk, uint64_
 uint32_t pick_resident(sfq_ctx *ctx, uint64_t nchunks, uint64_t per_chunk, uint64_t already_have, uint64_t fixed = 0) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    uint64_t budget = (uint64_t)((double)(free_b + already_have) * 0.85);
+    uint64_t budget = (uint64_t)((double)(free_b + already_have) * 0.92);
     budget = budget > fixed ? budget - fixed : 0;
     uint64_t r = budget / per_chunk;
     if (r < 1) r = 1;
@@ -395,7 +396,10 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             else { CK(cudaMemsetAsync(ctx->e2_cnt.p, 0, (uint64_t)nc * SFQ_Q_CNT * 4, s)); CK(cudaMemsetAsync(ctx->e2_ctr.p, 0, 64, s)); }
             CK(cudaMemsetAsync(ctx->pw.p, 0, nc * pbytes, s));
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
-            {   // fork: gen on the main stream, qlt and rec beside it; join before packing
+            {   // fork: three paths side by side, join before packing.  The base path is the longest of a wave since the quality path's
+                // scatter became cheap, so it gets the high-priority stream (its shared-memory-hungry CTAs are placed first);
+                // SFQ_ENC_PRIO=0 gives that stream to the quality path again, as in round 1
+                cudaStream_t sg = ctx->enc_prio_gen ? side0 : s, sq = ctx->enc_prio_gen ? s : side0;
                 const uint32_t lanes = pick_lanes(ctx, nc);
                 const unsigned nb = (nc + lanes - 1) / lanes;
                 const unsigned nwarp_blocks = (nc * 32u + 127u) / 128u;       // one warp per chunk, 4 warps per CTA
@@ -409,38 +413,38 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 if (two_phase && ctx->enc_order == 1) {
                     // the two short head kernels of the quality path get the machine before k_gen_model's long-running
                     // CTAs take its registers (they would otherwise trickle through what is left: 118 + 77 ms against 14 + 10)
-                    CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
-                    TRACED("k_qlt_keys", side0, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, side0>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
-                    TRACED("k_qlt_scan", side0, (k_qlt_scan<<<nc, 256, 0, side0>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
-                    CK(cudaEventRecord(ctx->head_ev, side0));
-                    CK(cudaStreamWaitEvent(s, ctx->head_ev, 0));
+                    CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], sq));
+                    TRACED("k_qlt_keys", sq, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, sq>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
+                    TRACED("k_qlt_scan", sq, (k_qlt_scan<<<nc, 256, 0, sq>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    CK(cudaEventRecord(ctx->head_ev, sq));
+                    CK(cudaStreamWaitEvent(sg, ctx->head_ev, 0));
                 }
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], sg));
                 if (!(ctx->plane_mask & 1)) {}
                 else if (two_phase && !gm_table) {
                     const bool gp_smem = (1u << gp_bits) <= SFQ_GP_SMEM_MAX;
-                    TRACED("k_gen_keys", s, (k_gen_keys<<<dim3((wave_max_nrec + SFQ_GC_RECS - 1) / SFQ_GC_RECS, nc), 128, 0, s>>>(d_text, d_ls, d_metas + c0, ctx->rec_boff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
-                    TRACED("k_gen_part", s, (k_gen_part<<<nc, 32, gp_smem ? (size_t)36 << gp_bits : 0, s>>>(d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, nc))); LAUNCHED();
-                    TRACED("k_gen_replay", s, (k_gen_replay<<<ctx->sm_count, 32 * SFQ_GR_WARPS, SFQ_GR_SMEM, s>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
-                    TRACED("k_rc_encode<0>", s, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
+                    TRACED("k_gen_keys", sg, (k_gen_keys<<<dim3((wave_max_nrec + SFQ_GC_RECS - 1) / SFQ_GC_RECS, nc), 128, 0, sg>>>(d_text, d_ls, d_metas + c0, ctx->rec_boff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
+                    TRACED("k_gen_part", sg, (k_gen_part<<<nc, 32, gp_smem ? (size_t)36 << gp_bits : 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, nc))); LAUNCHED();
+                    TRACED("k_gen_replay", sg, (k_gen_replay<<<ctx->sm_count, 32 * SFQ_GR_WARPS, SFQ_GR_SMEM, sg>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    TRACED("k_rc_encode<0>", sg, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else if (two_phase) {
-                    { TraceScope ts_(ctx, "k_gen_model", s);
+                    { TraceScope ts_(ctx, "k_gen_model", sg);
                     switch (ctx->gm_variant) {
-                    case 1: k_gen_model<4, 8><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
-                    case 2: k_gen_model<8, 8><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
-                    case 3: k_gen_model<8, 1><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
-                    default: k_gen_model<8, 6><<<nwarp_blocks, 128, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
+                    case 1: k_gen_model<4, 8><<<nwarp_blocks, 128, 0, sg>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
+                    case 2: k_gen_model<8, 8><<<nwarp_blocks, 128, 0, sg>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
+                    case 3: k_gen_model<8, 1><<<nwarp_blocks, 128, 0, sg>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
+                    default: k_gen_model<8, 6><<<nwarp_blocks, 128, 0, sg>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
                     } }
                     LAUNCHED();
-                    TRACED("k_rc_encode<0>", s, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, s>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
+                    TRACED("k_rc_encode<0>", sg, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else {
-                    k_encode<0><<<nb, 32, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
+                    k_encode<0><<<nb, 32, 0, sg>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
-                if (!(two_phase && ctx->enc_order == 1)) CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], sg));
+                if (!(two_phase && ctx->enc_order == 1)) CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], sq));
                 if (!(ctx->plane_mask & 2)) {}
                 else if (two_phase) {
-                    cudaStream_t q = side0;
+                    cudaStream_t q = sq;
                     if (ctx->enc_order != 1) {
                         TRACED("k_qlt_keys", q, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
                         TRACED("k_qlt_scan", q, (k_qlt_scan<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
@@ -454,9 +458,9 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
                     TRACED("k_rc_encode<1>", q, (k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else {
-                    k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, side0>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
+                    k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, sq>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
+                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], sq));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
                 if (ctx->plane_mask & 4) {
                     const uint32_t rl = ctx->lanes ? ctx->lanes : ctx->enc_rec_lanes ? ctx->enc_rec_lanes : std::min(lanes, 8u);
@@ -794,6 +798,7 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_GM_VARIANT")) ctx->gm_variant = atoi(e);
     if (const char *e = getenv("SFQ_GM_TABLE")) ctx->gm_table = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QSCATTER")) ctx->q_scatter1 = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_ENC_PRIO")) ctx->enc_prio_gen = atoi(e) != 0;
     if (const char *e = getenv("SFQ_GEN_AHEAD2")) ctx->gen_ahead2 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QDEC")) ctx->qdec_octets = atoi(e) != 0;
     if (const char *e = getenv("SFQ_SERIAL_ROLES")) ctx->serial_roles = atoi(e) != 0;
