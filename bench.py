@@ -385,7 +385,9 @@ class Bench:
             e_steps.append([round(s1["ms_total"], 1), round(s1["ms_code"], 1), round(s2["ms_total"], 1), round(s2["ms_gen"], 1), round(s2["ms_qlt"], 1), round(s2["ms_rec"], 1)])
             parts = {"c_total": s1["ms_total"], "c_h2d": s1["ms_h2d"], "c_code": s1["ms_code"], "c_d2h": s1["ms_d2h"], "c_waves": s1["waves"],
                      "d_total": s2["ms_total"], "d_h2d": s2["ms_h2d"], "d_code": s2["ms_code"], "d_d2h": s2["ms_d2h"], "d_waves": s2["waves"],
-                     "d_resident": s2["resident_chunks"]}
+                     "d_resident": s2["resident_chunks"],
+                     "c_scan_plan_clear_pack": s1["ms_scan"] + s1["ms_plan"] + s1["ms_clear"] + s1["ms_pack"],
+                     "d_plan_clear_pack": s2["ms_plan"] + s2["ms_clear"] + s2["ms_pack"]}
             launches += s1["kernel_launches"] + s2["kernel_launches"]
         self.barrier()
         res = {"ms": e_ms, "wall_s": time.perf_counter() - t0, "h2d": n + cn, "d2h": cn + n, "copy_ms": e_copy, "steps": e_steps,

@@ -92,11 +92,15 @@ struct sfq_ctx {
     int enc_order = 0;                      // SFQ_ENC_ORDER=1: quality path's keys+scan before k_gen_model
     uint32_t enc_rec_lanes = 0;             // SFQ_ENC_REC_LANES: chunk-streams per warp of the header encoder (0 = pick_lanes)
     cudaEvent_t head_ev = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;          // sfq_compress of a large host buffer: parts copied in / out beside the coding
+    cudaEvent_t part_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] text buffer filled, [2] part coded, [3] last copy out done
+    int parts = 0;                          // SFQ_PARTS: parts per sfq_compress call (0 = one per coder wave the input needs)
     bool trace = false;                     // SFQ_TRACE=1: per-kernel event timings of the coder waves on stderr
     std::vector<std::pair<const char *, std::pair<cudaEvent_t, cudaEvent_t>>> tr;
     int gdec32 = 0;                         // SFQ_GDEC=1: warp-converged base decoder (A/B; slower)
     uint32_t qlpc = 0;                      // SFQ_QLPC=4|8: lanes per chunk of the quality decoder (0 = by wave size)
     int gm_variant = 0;                     // SFQ_GM_VARIANT: register budget / batch of k_gen_model (A/B runs)
+    bool qspec = true;                      // SFQ_QSPEC=0: no prefetch of the model of the "same symbol again" context
     bool enc_prio_gen = true;               // SFQ_ENC_PRIO=0: the high-priority stream goes to the quality path of a compress wave
     int plane_mask = 7;                     // per-plane test hooks: 1 = gen, 2 = qlt, 4 = rec paths run (7 = the product)
     bool q_scatter1 = false;                // SFQ_QSCATTER=1: one-pass quality scatter over 65 536 global cursors (the round-1 form)
@@ -237,8 +241,16 @@ int ensure_wave_events(sfq_ctx *ctx, size_t waves) {
 }
 
 // ------------------------------------------------------------------------------------------ compress
+// A part of a file coded as the continuation of a container under construction (sfq_compress pipelines the parts of a large
+// host buffer: copy in, code, copy out): blobs go to d_out from `cursor` on, the index entries are collected by the caller,
+// no file header and no index are written.
+struct PartIo {
+    uint64_t cursor;                     // in: where this part's blobs start in d_out; out: where they end
+    std::vector<uint64_t> *index;        // blob offsets of all parts so far
+    uint64_t out_total;                  // bytes the parts so far decode to
+};
 int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level, uint64_t chunk_bytes,
-                       uint8_t *d_out, size_t out_cap, size_t *out_n) {
+                       uint8_t *d_out, size_t out_cap, size_t *out_n, PartIo *part = nullptr) {
     cudaStream_t s = ctx->stream;
     cudaStream_t side0 = ctx->serial_roles ? s : ctx->side[0], side1 = ctx->serial_roles ? s : ctx->side[1];
     sfq_stats &st = ctx->st;
@@ -382,7 +394,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             e2.gbins = ctx->e2_gbins.as<SfqU2>(); e2.gcnt = ctx->e2_gcnt.as<uint32_t>(); e2.gp_bits = gp_bits;
         }
         CK(cudaMemcpyAsync(d_arenas, arenas.data(), nchunks * sizeof(SfqArena), cudaMemcpyHostToDevice, s));
-        h_small[0] = 0; h_small[1] = sizeof(SfqFileHeader); h_small[2] = 0;
+        h_small[0] = 0; h_small[1] = part ? part->cursor : sizeof(SfqFileHeader); h_small[2] = 0;
         CK(cudaMemcpyAsync(d_scal, h_small, 24, cudaMemcpyHostToDevice, s));
         SfqWorkspace ws{};
         ws.gtab = ctx->gtab.as<uint8_t>(); ws.gtab_stride = gstride; ws.hbits = hbits;
@@ -508,6 +520,14 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
 
     // ---- file header + index ("host-side exchange of compressed-size offsets")
     const uint64_t index_off = end_cursor;
+    if (part) {
+        part->cursor = end_cursor;
+        part->index->insert(part->index->end(), blob_off.begin(), blob_off.end());
+        part->out_total += out_total;
+        CK(cudaEventRecord(ctx->ev[EV_CODE_END], s));
+        CK(cudaStreamSynchronize(s));
+        *out_n = end_cursor;
+    } else {
     if (index_off + nchunks * 8ull > out_cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)(index_off + nchunks * 8ull));
     SfqFileHeader fh;
     sfq_file_header_init(&fh, level, n, nchunks, chunk_bytes, index_off, out_total);
@@ -516,6 +536,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     CK(cudaEventRecord(ctx->ev[EV_CODE_END], s));
     CK(cudaStreamSynchronize(s));
     *out_n = index_off + nchunks * 8ull;
+    }
     st.stream_bytes = 0; st.gen_stream_bytes = 0; st.qlt_stream_bytes = 0;
     for (uint32_t c = 0; c < nchunks; c++) {
         for (int k = 0; k < SFQ_NSTREAMS; k++) st.stream_bytes += arenas[c].size[k];
@@ -666,8 +687,11 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                     // link) once a wave is large enough for issue slots to be what its warps compete for
                     const uint32_t lpc = ctx->qlpc ? ctx->qlpc : nc >= 4096u ? 4u : 8u;
                     const unsigned qw = (spread == 1 || spread == 2) ? SFQ_QD_MAXW : 2u;               // warps per CTA
-                    if (lpc == 4) k_qlt_decode<4><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, spread == 1 ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
-                    else k_qlt_decode<8><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, spread == 1 ? ctx->spread_smem[1] : 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    const unsigned qsm = spread == 1 ? ctx->spread_smem[1] : 0;
+                    if (lpc == 4 && ctx->qspec) k_qlt_decode<4, true><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, qsm, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    else if (lpc == 4) k_qlt_decode<4, false><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, qsm, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    else if (ctx->qspec) k_qlt_decode<8, true><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, qsm, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                    else k_qlt_decode<8, false><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, qsm, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
                     LAUNCHED();
                 }
                 else { k_decode<1><<<(nc + 2 * ctx->qgpw - 1) / (2 * ctx->qgpw), 64, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->qgpw); LAUNCHED(); }
@@ -761,6 +785,123 @@ int parse_host_container(sfq_ctx *ctx, const uint8_t *sfq, size_t n, SfqFileHead
     return 0;
 }
 
+// sfq_compress of a large host buffer, pipelined: the input is cut on the chunk grid into as many parts as it needs coder
+// waves anyway (the workspace of all its chunks does not fit the device at once), and while part p is coded, part p+1
+// travels to the device and the blobs of part p-1 travel back.  The parts' blobs laid out back to back with one index are
+// the one-call container byte for byte (sfq_set_chunk_phase).  Returns -1 when one part is all there is.
+int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64_t chunk_bytes, size_t cap,
+                      const uint8_t **out, size_t *out_n) {
+    const uint64_t B = !chunk_bytes ? 1ull << 20 : chunk_bytes < 4096 ? 4096 : chunk_bytes;
+    int P = ctx->parts;
+    if (P <= 0) {
+        // waves the whole input would take: ~15 bytes of workspace per input byte against what is free
+        // once the input and the container are resident
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const double have = (double)free_b + (double)ctx->text.cap + (double)ctx->out.cap + (double)ctx->scratch.cap + (double)ctx->pw.cap + (double)ctx->gtab.cap;
+        const double avail = 0.92 * (have - (double)n - (double)cap);
+        P = avail <= 0 ? 8 : (int)((15.0 * (double)n + avail - 1) / avail);
+        if (n < (256u << 20)) P = 1;
+    }
+    if (P > 16) P = 16;
+    const uint64_t nslots = (n + B - 1) / B;
+    if (P <= 1 || nslots < 2 * (uint64_t)P) return -1;
+    struct Part { size_t start, end; uint64_t phase; };
+    std::vector<Part> parts;
+    {
+        size_t prev = 0; uint64_t prev_phase = 0;
+        for (int p = 1; p <= P; p++) {
+            size_t cut = n; uint64_t ph = 0;
+            if (p < P) {
+                const uint64_t k = nslots * (uint64_t)p / (uint64_t)P;
+                cut = sfq_record_start_at_or_after(fastq, n, (size_t)(k * B));
+                ph = cut - k * B;
+            }
+            if (cut > prev) { parts.push_back({prev, cut, prev_phase}); prev = cut; prev_phase = ph; }
+        }
+    }
+    if (parts.size() < 2) return -1;
+    size_t max_part = 0;
+    for (auto &pt : parts) max_part = std::max(max_part, pt.end - pt.start);
+    const size_t tstride = (max_part + 16 + 255) & ~(size_t)255;
+    CK(ensure_big(ctx, ctx->text, 2 * tstride));
+    CK(ensure_big(ctx, ctx->out, cap));
+    cudaStream_t s = ctx->stream;
+    uint8_t *d_out = ctx->out.as<uint8_t>();
+    // the container is copied out part by part into the pinned result buffer; if that turns out too small (first call
+    // on a context) the pieces are skipped and everything is fetched once its size is known
+    if (ctx->h_out.cap < n / 6) CK(ctx->h_out.ensure(n / 4 + (1u << 20)));
+    bool piecewise = true;
+    sfq_stats acc{};
+    PartIo io{sizeof(SfqFileHeader), nullptr, 0};
+    std::vector<uint64_t> index;
+    io.index = &index;
+    CK(cudaEventRecord(ctx->ev[EV_START], s));
+    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev[EV_START], 0));
+    CK(cudaMemcpyAsync(ctx->text.p, fastq + parts[0].start, parts[0].end - parts[0].start, cudaMemcpyHostToDevice, ctx->copy_in));
+    CK(cudaEventRecord(ctx->part_ev[0], ctx->copy_in));
+    float ms_tail = 0;
+    for (size_t p = 0; p < parts.size(); p++) {
+        const size_t np = parts[p].end - parts[p].start;
+        uint8_t *d_text = ctx->text.as<uint8_t>() + (p & 1) * tstride;
+        if (p + 1 < parts.size()) {                       // the other text buffer is free: the part that used it has been coded
+            CK(cudaMemcpyAsync(ctx->text.as<uint8_t>() + ((p + 1) & 1) * tstride, fastq + parts[p + 1].start, parts[p + 1].end - parts[p + 1].start,
+                               cudaMemcpyHostToDevice, ctx->copy_in));
+            CK(cudaEventRecord(ctx->part_ev[(p + 1) & 1], ctx->copy_in));
+        }
+        CK(cudaStreamWaitEvent(s, ctx->part_ev[p & 1], 0));
+        CK(cudaEventRecord(ctx->ev[EV_H2D], s));
+        if (p == 0) { CK(cudaEventSynchronize(ctx->part_ev[0])); acc.ms_h2d = ev_ms(ctx->ev[EV_START], ctx->part_ev[0]); }   // the copy nobody could hide: the first part's
+        ctx->chunk_phase = parts[p].phase;
+        const uint64_t from = io.cursor;
+        size_t on = 0;
+        const int rc = compress_on_device(ctx, d_text, np, level, chunk_bytes, d_out, cap, &on, &io);
+        if (rc) { cudaStreamSynchronize(ctx->copy_in); cudaStreamSynchronize(ctx->copy_out); return rc; }    // (the caller's buffer may go away)
+        {   // per-call statistics: sums over the parts
+            const sfq_stats &st = ctx->st;
+            acc.nchunks += st.nchunks; acc.nrecords += st.nrecords; acc.nbases += st.nbases; acc.nquals += st.nquals;
+            acc.stream_bytes += st.stream_bytes; acc.gen_stream_bytes += st.gen_stream_bytes; acc.qlt_stream_bytes += st.qlt_stream_bytes;
+            acc.waves += st.waves; acc.resident_chunks = std::max(acc.resident_chunks, st.resident_chunks); acc.retries += st.retries;
+            acc.workspace_bytes = std::max(acc.workspace_bytes, st.workspace_bytes);
+            acc.ms_scan += st.ms_scan; acc.ms_plan += st.ms_plan; acc.ms_clear += st.ms_clear; acc.ms_code += st.ms_code; acc.ms_pack += st.ms_pack;
+            acc.ms_gen += st.ms_gen; acc.ms_qlt += st.ms_qlt; acc.ms_rec += st.ms_rec;
+            acc.kernel_launches = st.kernel_launches;        // (LAUNCHED() keeps counting through the parts)
+        }
+        if (piecewise && io.cursor + 8ull * index.size() + 4096 > ctx->h_out.cap) piecewise = false;
+        if (piecewise) {
+            CK(cudaEventRecord(ctx->part_ev[2], s));
+            CK(cudaStreamWaitEvent(ctx->copy_out, ctx->part_ev[2], 0));
+            CK(cudaMemcpyAsync(ctx->h_out.as<uint8_t>() + from, d_out + from, io.cursor - from, cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
+    }
+    const uint64_t index_off = io.cursor, total = index_off + 8ull * index.size();
+    if (total > cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)total);
+    SfqFileHeader fh;
+    sfq_file_header_init(&fh, level > 4 ? 4 : level < 1 ? 1 : level, n, index.size(), B, index_off, io.out_total);
+    if (piecewise) {
+        CK(cudaEventRecord(ctx->part_ev[3], ctx->copy_out));
+        CK(cudaStreamSynchronize(ctx->copy_out));
+        memcpy(ctx->h_out.p, &fh, sizeof fh);
+        memcpy(ctx->h_out.as<uint8_t>() + index_off, index.data(), 8ull * index.size());
+    } else {
+        CK(cudaMemcpyAsync(d_out, &fh, sizeof fh, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_out + index_off, index.data(), 8ull * index.size(), cudaMemcpyHostToDevice, s));
+        CK(ctx->h_out.ensure(total + total / 8));
+        CK(cudaMemcpyAsync(ctx->h_out.p, d_out, total, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(ctx->part_ev[3], s));
+        CK(cudaStreamSynchronize(s));
+    }
+    ms_tail = ev_ms(ctx->ev[EV_CODE_END], ctx->part_ev[3]);
+    acc.in_bytes = n; acc.out_bytes = total;
+    acc.ms_d2h = ms_tail > 0 ? ms_tail : 0;                       // the copy nobody could hide: the last part's blobs
+    acc.ms_total = ev_ms(ctx->ev[EV_START], ctx->part_ev[3]);
+    ctx->st = acc;
+    ctx->st.kernel_launches = acc.kernel_launches;
+    *out = ctx->h_out.as<uint8_t>();
+    *out_n = total;
+    return 0;
+}
+
 void begin_call(sfq_ctx *ctx) {
     cudaSetDevice(ctx->device);
     ctx->err.clear();
@@ -799,6 +940,8 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_GM_TABLE")) ctx->gm_table = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QSCATTER")) ctx->q_scatter1 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_ENC_PRIO")) ctx->enc_prio_gen = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_QSPEC")) ctx->qspec = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_PARTS")) ctx->parts = atoi(e);
     if (const char *e = getenv("SFQ_GEN_AHEAD2")) ctx->gen_ahead2 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QDEC")) ctx->qdec_octets = atoi(e) != 0;
     if (const char *e = getenv("SFQ_SERIAL_ROLES")) ctx->serial_roles = atoi(e) != 0;
@@ -812,6 +955,8 @@ int sfq_create(sfq_ctx **out, int device) {
             cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->head_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    for (auto &e : ctx->part_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaFuncSetAttribute(k_gen_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SFQ_GR_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_gen_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(36u * SFQ_GP_SMEM_MAX)) != cudaSuccess ||
         cudaFuncSetAttribute(k_encode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * sizeof(SfqRecScratch))) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
@@ -820,10 +965,13 @@ int sfq_create(sfq_ctx **out, int device) {
         cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
         const unsigned unit = smem_sm > 0 ? (unsigned)smem_sm / 11u : 20u << 10;      // ~20.7 KB on B200 (228 KB per SM): 4 + 3 + 3 units < one SM
         ctx->spread_smem[0] = 4 * unit - 8192; ctx->spread_smem[1] = 3 * unit; ctx->spread_smem[2] = 3 * unit - 1024;
+        if (const char *e = getenv("SFQ_GEN_RESERVE_KB")) { const int kb = atoi(e); if (kb >= 0 && kb <= 200) ctx->spread_smem[0] = (unsigned)kb << 10; }   // 112+: one base-decoder CTA per SM
         bool ok = cudaFuncSetAttribute(k_decode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[0]) == cudaSuccess &&
                   cudaFuncSetAttribute(k_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[2]) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_qlt_decode<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_qlt_decode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess;
+                  cudaFuncSetAttribute(k_qlt_decode<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_qlt_decode<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_qlt_decode<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_qlt_decode<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess;
         if (!ok) { cudaGetLastError(); ctx->spread_smem[0] = ctx->spread_smem[1] = ctx->spread_smem[2] = 0; }
     }
     *out = ctx;
@@ -840,6 +988,9 @@ void sfq_destroy(sfq_ctx *ctx) {
     for (int k = 0; k < 2; k++) { if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]); if (ctx->join_ev[k]) cudaEventDestroy(ctx->join_ev[k]); }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->head_ev) cudaEventDestroy(ctx->head_ev);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    for (auto &e : ctx->part_ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -879,6 +1030,10 @@ int sfq_compress(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, uint64
         begin_call(ctx);
         if (n == 0) return fail(ctx, SFQ_ERR_FASTQ, "no records were found");
         const size_t cap = sfq_compress_bound(n, chunk_bytes);
+        {
+            const int rc_parts = compress_in_parts(ctx, fastq, n, level, chunk_bytes, cap, out, out_n);
+            if (rc_parts != -1) return rc_parts;             // -1: one part only, the plain path below
+        }
         CK(ensure_big(ctx, ctx->text, n + 16));
         CK(ensure_big(ctx, ctx->out, cap));
         CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));

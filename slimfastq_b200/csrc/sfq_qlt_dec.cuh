@@ -158,7 +158,7 @@ __device__ __forceinline__ void sfq_qd_fetch(uint4 (&v)[SfqQdGeo<LPC>::NV], cons
 }
 
 #define SFQ_QD_MAXW 8                   // most warps per CTA (the launch picks 2 or 8)
-template <int LPC>
+template <int LPC, bool SPEC>
 __global__ void __launch_bounds__(32 * SFQ_QD_MAXW)
 k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas, SfqWorkspace ws,
              SfqRecTables t, uint8_t *quals, uint32_t nchunks) {
@@ -250,6 +250,16 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
             }
         }
         const bool act = live;
+        if (SPEC) {
+            // The next context is only known once this symbol is: its model is requested below, after the search, and its
+            // DRAM latency sits on the chain.  A quality most often repeats its predecessor, and for that case the next
+            // context is known NOW (qlts.hpp:52-74 with b = p1: same symbol twice, no drop): ask L2 for that entry's
+            // line before the search starts.  A wrong guess costs a line of bandwidth and nothing else.
+            const uint32_t guess = level >= 3u ? ((p1 | (p1 << 6) | (1u << 12) | ((dl >> 3 < 7u ? dl >> 3 : 7u) << 13)) & 0xffffu)
+                                               : ((p1 | (last << 6)) & lmask);
+            const uint32_t hg = dense ? guess : __umulhi(guess * 2654435761u, nent);
+            if (act) sfq_prefetch(tab + (size_t)hg * 64u);
+        }
 
         // ---------------------------------------------------------------- Log64Ranger::get (log64_ranger.hpp:114-138)
         const uint32_t tot = m.hdr & 0x3fffffu, count = m.hdr >> 24;

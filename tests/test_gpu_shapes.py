@@ -54,6 +54,23 @@ def test_benchmark_kernel_shapes_bit_exact(oracle, env):
         c.close()
 
 
+def test_pipelined_parts_give_the_one_call_container(codec):
+    """sfq_compress of a large host buffer codes it in parts cut on the chunk grid (copies beside the coding); forced here
+    on a small one: the container must be the plain call's, byte for byte."""
+    data = synth.illumina(9000)
+    c = codec_with({"SFQ_PARTS": "3"})
+    try:
+        for level in (3, 1):
+            blob = c.compress(data, level, 1 << 17)
+            assert c.stats()["waves"] >= 3
+            assert blob == codec.compress(data, level, 1 << 17)
+            assert c.decompress(blob) == data
+        ont = synth.ont(80)
+        assert c.compress(ont, 3, 1 << 18) == codec.compress(ont, 3, 1 << 18)
+    finally:
+        c.close()
+
+
 def test_chunks_equal_the_reference_binary_itself(codec, oracle):
     """Not the restatement: the unmodified reference run on each chunk as a standalone file."""
     if not oracle.have_ref():
