@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
+#include <chrono>
 #include <new>
 #include <string>
 #include <utility>
@@ -100,7 +102,8 @@ struct sfq_ctx {
     int gdec32 = 0;                         // SFQ_GDEC=1: warp-converged base decoder (A/B; slower)
     uint32_t qlpc = 0;                      // SFQ_QLPC=4|8: lanes per chunk of the quality decoder (0 = by wave size)
     int gm_variant = 0;                     // SFQ_GM_VARIANT: register budget / batch of k_gen_model (A/B runs)
-    bool qspec = true;                      // SFQ_QSPEC=0: no prefetch of the model of the "same symbol again" context
+    bool dec_gen_first = false;             // SFQ_DEC_ORDER=1: base decoder launched first, on the high-priority stream (A/B: consistently packed, 2x slower)
+    bool qspec = false;                     // SFQ_QSPEC=1: the quality decoder prefetches the model of the "same symbol again" context (A/B: 4 % faster alone, 2 % slower beside the other decoders)
     bool enc_prio_gen = true;               // SFQ_ENC_PRIO=0: the high-priority stream goes to the quality path of a compress wave
     int plane_mask = 7;                     // per-plane test hooks: 1 = gen, 2 = qlt, 4 = rec paths run (7 = the product)
     bool q_scatter1 = false;                // SFQ_QSCATTER=1: one-pass quality scatter over 65 536 global cursors (the round-1 form)
@@ -207,6 +210,8 @@ uint32_t pick_lanes(const sfq_ctx *ctx, uint32_t nc) { return ctx->lanes ? ctx->
 SfqWorkspace ws_at(const SfqWorkspace &ws, uint32_t) { return ws; }
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+// SFQ_TRACE: host wall-clock marks (where the host thread waits or works while the device could be idle)
+void host_mark(const sfq_ctx *ctx, const char *what);
 
 // SFQ_TRACE: bracket a launch with events on its stream; trace_dump() prints and frees them after the sync.
 struct TraceScope {
@@ -248,6 +253,10 @@ struct PartIo {
     uint64_t cursor;                     // in: where this part's blobs start in d_out; out: where they end
     std::vector<uint64_t> *index;        // blob offsets of all parts so far
     uint64_t out_total;                  // bytes the parts so far decode to
+    // Called once the part's coder waves are enqueued: the next part's text is sent off only now.  Sent earlier, the 5 GB
+    // transfer would sit in the host-to-device copy engine ahead of this part's own small set-up copies (arena layout,
+    // chunk tables: pageable, hence synchronous), and the waves would start ~90 ms late behind it (measured).
+    std::function<int()> on_enqueued;
 };
 int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level, uint64_t chunk_bytes,
                        uint8_t *d_out, size_t out_cap, size_t *out_n, PartIo *part = nullptr) {
@@ -277,6 +286,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     uint8_t last_byte = 0;
     CK(cudaMemcpyAsync(&h_small[1], d_text + n - 1, 1, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    host_mark(ctx, "compress: newline count known");
     const uint64_t nlines = h_small[0];
     last_byte = *reinterpret_cast<uint8_t *>(&h_small[1]);
     if (last_byte != '\n' || nlines % 4 || nlines == 0)
@@ -310,6 +320,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
     CK(cudaMemcpyAsync(metas.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[EV_PLAN], s));
     CK(cudaStreamSynchronize(s));
+    host_mark(ctx, "compress: chunk plan known");
     uint64_t max_bases = 0, out_total = 0;
     st.nchunks = nchunks; st.nrecords = nrec_total; st.nbases = st.nquals = 0;
     for (uint32_t c = 0; c < nchunks; c++) {
@@ -490,11 +501,14 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                                       d_out, out_cap, reinterpret_cast<uint32_t *>(d_scal + 2)); LAUNCHED();
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 3], s));
         }
+        if (part && part->on_enqueued && grow == 0) { const int rc_ = part->on_enqueued(); if (rc_) return rc_; }
+        host_mark(ctx, "compress: waves enqueued");
         CK(cudaMemcpyAsync(metas.data(), d_metas, nchunks * sizeof(SfqChunkMeta), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(arenas.data(), d_arenas, nchunks * sizeof(SfqArena), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(blob_off.data(), d_blob_off, nchunks * 8ull, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h_small, d_scal, 24, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        host_mark(ctx, "compress: waves done");
         CK(cudaGetLastError());
         trace_dump(ctx, "compress");
         bool again = false;
@@ -597,14 +611,12 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
 
     CK(ctx->metas.ensure(nchunks * sizeof(SfqChunkMeta)));
     CK(ctx->dchunks.ensure(nchunks * sizeof(SfqDecChunk)));
-    CK(ctx->rec_chunk.ensure(nrec * 4));
-    std::vector<uint32_t> rec_chunk(nrec);
-    for (uint32_t c = 0; c < nchunks; c++) std::fill(rec_chunk.begin() + dcs[c].rec_base, rec_chunk.begin() + dcs[c].rec_base + metas[c].nrec, c);
+    CK(ctx->rec_chunk.ensure(nrec * 4 + 64));
     SfqChunkMeta *d_metas = ctx->metas.as<SfqChunkMeta>();
     SfqDecChunk *d_dcs = ctx->dchunks.as<SfqDecChunk>();
     CK(cudaMemcpyAsync(d_metas, metas.data(), nchunks * sizeof(SfqChunkMeta), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_dcs, dcs.data(), nchunks * sizeof(SfqDecChunk), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->rec_chunk.p, rec_chunk.data(), nrec * 4, cudaMemcpyHostToDevice, s));
+    k_fill_rec_chunk<<<nchunks, 128, 0, s>>>(d_dcs, d_metas, ctx->rec_chunk.as<uint32_t>()); LAUNCHED();      // record -> chunk, for the assemble kernel
     // planes and per-record tables: carved from the scratch arena together with the quality tables (below)
     const size_t fixed_sz[] = {nb + 16, nq + 16, nh + 16, nrec * 4, nrec * 4, nrec * 4, nrec, nrec, nrec * 8, nrec * 8, nrec * 8, nrec * 8};
     DevBuf *fixed_buf[] = {&ctx->bases, &ctx->quals, &ctx->hdrs, &ctx->t_llen, &ctx->t_qlen, &ctx->t_hlen, &ctx->t_pfg, &ctx->t_pfq,
@@ -678,33 +690,46 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 CK(cudaEventRecord(ctx->fork_ev, s));
                 CK(cudaStreamWaitEvent(side0, ctx->fork_ev, 0));
                 CK(cudaStreamWaitEvent(side1, ctx->fork_ev, 0));
-                // the quality decoder is the longest chain of the three: it goes first (and on the high-priority
-                // stream) so that its warps are all resident from the start; gen and rec fill in around it
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], side0));
-                if (!(ctx->plane_mask & 2)) {}
-                else if (ctx->qdec_octets) {
-                    // lanes per chunk: 8 while the chains are latency-bound, 4 (twice the chunks per warp, a longer
-                    // link) once a wave is large enough for issue slots to be what its warps compete for
-                    const uint32_t lpc = ctx->qlpc ? ctx->qlpc : nc >= 4096u ? 4u : 8u;
-                    const unsigned qw = (spread == 1 || spread == 2) ? SFQ_QD_MAXW : 2u;               // warps per CTA
-                    const unsigned qsm = spread == 1 ? ctx->spread_smem[1] : 0;
-                    if (lpc == 4 && ctx->qspec) k_qlt_decode<4, true><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, qsm, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
-                    else if (lpc == 4) k_qlt_decode<4, false><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, qsm, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
-                    else if (ctx->qspec) k_qlt_decode<8, true><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, qsm, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
-                    else k_qlt_decode<8, false><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, qsm, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                // Launch order and priorities: the quality decoder (the longest chain) goes first, on the high-priority stream; the
+                // base decoder's ~150 fat CTAs arrive on a machine already holding 600 quality CTAs and are spread one per SM
+                // most of the time (about one call in eight they are packed two to an SM and that call's base decoder runs up to
+                // 2x slower; the shared-memory reservation above bounds it there).  The other order (SFQ_DEC_ORDER=1: base decoder
+                // first, on the empty machine) was measured: the block scheduler then packs them EVERY time (1 378 ms against
+                // 681 ms per call, 10 of 10 steps) - it fills an SM to its limit before it moves on.
+                cudaStream_t sgd = ctx->dec_gen_first ? side0 : s, sqd = ctx->dec_gen_first ? s : side0;
+                auto launch_qlt = [&]() -> int {
+                    CK(cudaEventRecord(ctx->wave_ev[WEV * w + 6], sqd));
+                    if (!(ctx->plane_mask & 2)) {}
+                    else if (ctx->qdec_octets) {
+                        // lanes per chunk: 8 while the chains are latency-bound, 4 (twice the chunks per warp, a longer
+                        // link) once a wave is large enough for issue slots to be what its warps compete for
+                        const uint32_t lpc = ctx->qlpc ? ctx->qlpc : nc >= 4096u ? 4u : 8u;
+                        const unsigned qw = (spread == 1 || spread == 2) ? SFQ_QD_MAXW : 2u;               // warps per CTA
+                        const unsigned qsm = spread == 1 ? ctx->spread_smem[1] : 0;
+                        if (lpc == 4 && ctx->qspec) k_qlt_decode<4, true><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, qsm, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                        else if (lpc == 4) k_qlt_decode<4, false><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, qsm, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                        else if (ctx->qspec) k_qlt_decode<8, true><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, qsm, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                        else k_qlt_decode<8, false><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, qsm, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                        LAUNCHED();
+                    }
+                    else { k_decode<1><<<(nc + 2 * ctx->qgpw - 1) / (2 * ctx->qgpw), 64, 0, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->qgpw); LAUNCHED(); }
+                    CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], sqd));
+                    return 0;
+                };
+                auto launch_gen = [&]() -> int {
+                    CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], sgd));
+                    // base decoder: thread per chunk, `lanes` chunks per warp.  (SFQ_GDEC=1 runs the warp-converged form,
+                    // 32 chunks per warp: correct, but its link waits for the slowest of 32 table reads - 45 % slower, kept for A/B.)
+                    if (!(ctx->plane_mask & 1)) {}
+                    else if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, sgd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
+                    else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, (spread == 1 || spread == 3) ? ctx->spread_smem[0] : 0, sgd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
                     LAUNCHED();
-                }
-                else { k_decode<1><<<(nc + 2 * ctx->qgpw - 1) / (2 * ctx->qgpw), 64, 0, side0>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, ctx->qgpw); LAUNCHED(); }
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], side0));
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], s));
-                // base decoder: thread per chunk, `lanes` chunks per warp.  (SFQ_GDEC=1 runs the warp-converged form,
-                // 32 chunks per warp: correct, but its link waits for the slowest of 32 table reads - 45 % slower, kept for A/B.)
-                if (!(ctx->plane_mask & 1)) {}
-                else if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
-                else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, (spread == 1 || spread == 3) ? ctx->spread_smem[0] : 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
-                LAUNCHED();
-                if (ctx->plane_mask & 1) { k_gen_exceptions<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED(); }
-                CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], s));
+                    if (ctx->plane_mask & 1) { k_gen_exceptions<<<(nc + 31) / 32, 32, 0, sgd>>>(d_in, d_dcs + c0, d_metas + c0, ws, pb, nc); LAUNCHED(); }
+                    CK(cudaEventRecord(ctx->wave_ev[WEV * w + 5], sgd));
+                    return 0;
+                };
+                if (ctx->dec_gen_first) { if (launch_gen() || launch_qlt()) return SFQ_ERR_CUDA; }
+                else { if (launch_qlt() || launch_gen()) return SFQ_ERR_CUDA; }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
                 if (ctx->plane_mask & 4) { k_decode<2><<<(nb + dw - 1) / dw, 32 * dw, spread == 1 ? ctx->spread_smem[2] : 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED(); }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
@@ -833,7 +858,7 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
     if (ctx->h_out.cap < n / 6) CK(ctx->h_out.ensure(n / 4 + (1u << 20)));
     bool piecewise = true;
     sfq_stats acc{};
-    PartIo io{sizeof(SfqFileHeader), nullptr, 0};
+    PartIo io{sizeof(SfqFileHeader), nullptr, 0, nullptr};
     std::vector<uint64_t> index;
     io.index = &index;
     CK(cudaEventRecord(ctx->ev[EV_START], s));
@@ -844,13 +869,18 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
     for (size_t p = 0; p < parts.size(); p++) {
         const size_t np = parts[p].end - parts[p].start;
         uint8_t *d_text = ctx->text.as<uint8_t>() + (p & 1) * tstride;
+        io.on_enqueued = nullptr;
         if (p + 1 < parts.size()) {                       // the other text buffer is free: the part that used it has been coded
-            CK(cudaMemcpyAsync(ctx->text.as<uint8_t>() + ((p + 1) & 1) * tstride, fastq + parts[p + 1].start, parts[p + 1].end - parts[p + 1].start,
-                               cudaMemcpyHostToDevice, ctx->copy_in));
-            CK(cudaEventRecord(ctx->part_ev[(p + 1) & 1], ctx->copy_in));
+            io.on_enqueued = [ctx, fastq, &parts, p, tstride]() -> int {
+                CK(cudaMemcpyAsync(ctx->text.as<uint8_t>() + ((p + 1) & 1) * tstride, fastq + parts[p + 1].start, parts[p + 1].end - parts[p + 1].start,
+                                   cudaMemcpyHostToDevice, ctx->copy_in));
+                CK(cudaEventRecord(ctx->part_ev[(p + 1) & 1], ctx->copy_in));
+                return 0;
+            };
         }
         CK(cudaStreamWaitEvent(s, ctx->part_ev[p & 1], 0));
         CK(cudaEventRecord(ctx->ev[EV_H2D], s));
+        host_mark(ctx, "parts: next part");
         if (p == 0) { CK(cudaEventSynchronize(ctx->part_ev[0])); acc.ms_h2d = ev_ms(ctx->ev[EV_START], ctx->part_ev[0]); }   // the copy nobody could hide: the first part's
         ctx->chunk_phase = parts[p].phase;
         const uint64_t from = io.cursor;
@@ -891,6 +921,7 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
         CK(cudaEventRecord(ctx->part_ev[3], s));
         CK(cudaStreamSynchronize(s));
     }
+    host_mark(ctx, "parts: all copied out");
     ms_tail = ev_ms(ctx->ev[EV_CODE_END], ctx->part_ev[3]);
     acc.in_bytes = n; acc.out_bytes = total;
     acc.ms_d2h = ms_tail > 0 ? ms_tail : 0;                       // the copy nobody could hide: the last part's blobs
@@ -900,6 +931,13 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
     *out = ctx->h_out.as<uint8_t>();
     *out_n = total;
     return 0;
+}
+
+void host_mark(const sfq_ctx *ctx, const char *what) {
+    if (!ctx->trace) return;
+    static std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[sfq host] %10.3f ms  %s\n", ms, what);
 }
 
 void begin_call(sfq_ctx *ctx) {
@@ -942,6 +980,7 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_ENC_PRIO")) ctx->enc_prio_gen = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QSPEC")) ctx->qspec = atoi(e) != 0;
     if (const char *e = getenv("SFQ_PARTS")) ctx->parts = atoi(e);
+    if (const char *e = getenv("SFQ_DEC_ORDER")) ctx->dec_gen_first = atoi(e) != 0;
     if (const char *e = getenv("SFQ_GEN_AHEAD2")) ctx->gen_ahead2 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QDEC")) ctx->qdec_octets = atoi(e) != 0;
     if (const char *e = getenv("SFQ_SERIAL_ROLES")) ctx->serial_roles = atoi(e) != 0;

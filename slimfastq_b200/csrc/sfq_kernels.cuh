@@ -252,6 +252,14 @@ struct SfqRecTables {
 #include "sfq_qlt_dec.cuh"
 #include "sfq_gen_dec.cuh"
 
+// rec_chunk[k] = chunk of record k (one CTA per chunk)
+__global__ void __launch_bounds__(128)
+k_fill_rec_chunk(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ metas, uint32_t *rec_chunk) {
+    const uint32_t c = blockIdx.x;
+    uint32_t *p = rec_chunk + dc[c].rec_base;
+    for (uint32_t r = threadIdx.x; r < metas[c].nrec; r += blockDim.x) p[r] = c;
+}
+
 __global__ void __launch_bounds__(32)
 k_decode_usr(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas,
              SfqWorkspace ws, SfqRecTables t, uint8_t *bases, uint8_t *quals, uint8_t *hdrs, uint32_t nchunks) {
