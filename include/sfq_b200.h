@@ -41,7 +41,8 @@ enum {
     SFQ_ERR_CUDA = 1,        /* no device / CUDA runtime failure                               */
     SFQ_ERR_ARG = 2,         /* bad argument                                                   */
     SFQ_ERR_FASTQ = 3,       /* input is not FASTQ the reference would accept (croak text)      */
-    SFQ_ERR_UNSUPPORTED = 4, /* oversized records (usrs.hpp:34-36) are not coded by this build  */
+    SFQ_ERR_UNSUPPORTED = 4, /* input the reference itself cannot represent (first header > 399, */
+                             /* empty first base line) or a chunk of 4 GiB+ per plane             */
     SFQ_ERR_FORMAT = 5,      /* not a b200 chunked .sfq container / corrupt container           */
     SFQ_ERR_NOMEM = 6,       /* host or device memory                                          */
     SFQ_ERR_SPACE = 7        /* caller-provided output buffer too small                        */
@@ -78,6 +79,10 @@ const char *sfq_version(void);          /* "2.04/6 b200" - user version / intern
 
 /* Upper bound on resident chunks per coder wave (0 = as many as device memory allows). */
 int sfq_set_max_resident(sfq_ctx *ctx, uint32_t chunks);
+
+/* Give back the device and pinned memory the context keeps between calls (grow-only workspace sized for the largest
+ * call so far - up to ~90 % of the device after a 10 GB call).  Results returned by earlier calls become invalid. */
+int sfq_trim(sfq_ctx *ctx);
 
 /* The chunk grid of a PART of a file (a segment of a pipe, the shard of one GPU).  Chunk c of a whole file
  * holds the records that start in [c*chunk_bytes, (c+1)*chunk_bytes); "chunks are partitioned by index

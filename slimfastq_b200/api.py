@@ -46,7 +46,7 @@ EXPORTS = [
     "sfq_import_reference_bound", "sfq_import_reference",
     "sfq_record_start_at_or_after", "sfq_last_record_start", "sfq_set_chunk_phase", "sfq_stream_cut",
     "sfq_encode_gen_chunks", "sfq_encode_qlt_chunks", "sfq_encode_rec_chunks",
-    "sfq_decode_gen_chunks", "sfq_decode_qlt_chunks", "sfq_decode_rec_chunks",
+    "sfq_decode_gen_chunks", "sfq_decode_qlt_chunks", "sfq_decode_rec_chunks", "sfq_trim",
 ]
 
 _lib = None
@@ -66,6 +66,7 @@ def load_library():
     L.sfq_last_error.argtypes = [vp]; L.sfq_last_error.restype = C.c_char_p
     L.sfq_version.argtypes = []; L.sfq_version.restype = C.c_char_p
     L.sfq_set_max_resident.argtypes = [vp, C.c_uint32]; L.sfq_set_max_resident.restype = C.c_int
+    L.sfq_trim.argtypes = [vp]; L.sfq_trim.restype = C.c_int
     L.sfq_set_chunk_phase.argtypes = [vp, C.c_uint64]; L.sfq_set_chunk_phase.restype = C.c_int
     L.sfq_host_alloc.argtypes = [sz]; L.sfq_host_alloc.restype = vp
     L.sfq_host_free.argtypes = [vp]; L.sfq_host_free.restype = None
@@ -125,6 +126,10 @@ class Codec:
             self._h = None
 
     __del__ = close
+
+    def trim(self):
+        """Release the device / pinned memory the context caches between calls (views returned earlier become invalid)."""
+        self._check(self._L.sfq_trim(self._h))
 
     def _check(self, rc: int):
         if rc:

@@ -94,8 +94,16 @@ struct sfq_ctx {
     int enc_order = 0;                      // SFQ_ENC_ORDER=1: quality path's keys+scan before k_gen_model
     uint32_t enc_rec_lanes = 0;             // SFQ_ENC_REC_LANES: chunk-streams per warp of the header encoder (0 = pick_lanes)
     cudaEvent_t head_ev = nullptr;
+    cudaEvent_t gbins_ev = nullptr;         // k_gen_replay has read the partition lists: their memory may become the quality steps
+    int enc_sched = 0;                      // SFQ_ENC_SCHED: when the header encoder / base coder chain of a wave may start (see compress_on_device)
+    cudaEvent_t qp2_ev = nullptr, qtp_ev = nullptr;   // quality path: second-level partition done / model replay done
+    bool marks = false;                     // SFQ_MARKS=1: host-side time marks of a call on stderr (without the per-kernel events of SFQ_TRACE)
+    bool alias_steps = true;                // SFQ_ALIAS=0: partition lists (gbins) and quality steps (qsteps) in separate memory, as before
     cudaStream_t copy_in = nullptr, copy_out = nullptr;          // sfq_compress of a large host buffer: parts copied in / out beside the coding
     cudaEvent_t part_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] text buffer filled, [2] part coded, [3] last copy out done
+    uint32_t dec_lanes = 0;                 // SFQ_DEC_LANES: chunk-streams per warp of the thread-per-chunk decoders (0 = pick_lanes / dec_fit)
+    bool dec_fit = false;                   // SFQ_DEC_FIT=1: widen the warps of a large wave so that its CTAs number at most one per SM (A/B: 17 lanes per warp cost the base decoder 3 %, and no outlier either way in 6 steps)
+    double head_frac = 0.15;                // SFQ_HEAD_FRAC: size of the head part of a pipelined sfq_compress, as a fraction of a coder wave
     int parts = 0;                          // SFQ_PARTS: parts per sfq_compress call (0 = one per coder wave the input needs)
     bool trace = false;                     // SFQ_TRACE=1: per-kernel event timings of the coder waves on stderr
     std::vector<std::pair<const char *, std::pair<cudaEvent_t, cudaEvent_t>>> tr;
@@ -135,7 +143,8 @@ void release_workspace(sfq_ctx *ctx) {
                        &ctx->e2_gsteps, &ctx->e2_qkey, &ctx->e2_qb, &ctx->e2_sorted, &ctx->e2_qsteps, &ctx->e2_cnt,
                        &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs, &ctx->e2_gbins, &ctx->e2_gcnt};
     for (DevBuf *d : views) d->release();
-    ctx->scratch.release(); ctx->gtab.release(); ctx->pw.release();
+    ctx->gtab.release(); ctx->pw.release();
+    ctx->scratch.release();
 }
 // Large caller-facing buffers win over the cached coder workspace: on OOM drop it and retry.
 cudaError_t ensure_big(sfq_ctx *ctx, DevBuf &b, size_t bytes) {
@@ -359,12 +368,14 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         auto esc_cap = [grow](uint64_t nq) { return std::min<uint64_t>(nq, (nq >> 4) << grow) + 64; };
         auto seg_cap = [](uint64_t nq) { return std::min<uint64_t>(SFQ_Q_NCTX, nq) + 1; };
         // two-phase encoder: no quality-model table in global memory, but the coding steps of every symbol
-        const uint64_t e2_per_chunk = 4 * max_nb + (gm_table ? 0 : 8 * max_nb + (36ull << gp_bits)) + 15 * max_nq + SFQ_Q_CNT * 4ull + 16 * seg_cap(max_nq) + 12 * esc_cap(max_nq) + 256;
+        // The base path's partition lists (8 B per base, dead once k_gen_replay has run) and the quality path's coding steps
+        // (8 B per quality, first written by k_qlt_part1) share one range of the arena: the quality path waits for gbins_ev
+        // before it touches it.  That is a quarter of a chunk's workspace, and what lets the 10 GB workload code in ONE wave.
+        const bool alias = two_phase && !gm_table && ctx->alias_steps;
+        const uint64_t e2_per_chunk = 4 * max_nb + (gm_table ? 0 : (alias ? 8 * (std::max(max_nb, max_nq) - max_nq) : 8 * max_nb) + (36ull << gp_bits)) + 15 * max_nq + SFQ_Q_CNT * 4ull + 16 * seg_cap(max_nq) + 12 * esc_cap(max_nq) + 256;
         const uint64_t per_chunk = gstride + pbytes + max_arena + 4096 + (two_phase ? e2_per_chunk : qbytes);
-        const uint64_t have_now = ctx->gtab.cap + ctx->pw.cap + ctx->scratch.cap;
+        const uint64_t have_now = ctx->scratch.cap;
         const uint32_t R = pick_resident(ctx, nchunks, per_chunk, have_now);
-        if (gm_table) CK(ctx->gtab.ensure(R * gstride)); else ctx->gtab.release();
-        CK(ctx->pw.ensure(R * pbytes));
         const uint32_t nwaves = (nchunks + R - 1) / R;
         if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
         st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * per_chunk;
@@ -383,17 +394,27 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
         }
         SfqEnc2Ws e2{};
         {   // everything wave-sized comes out of the shared scratch arena
-            const size_t sz[] = {wave_arena_max + 64, wave_nb * 4 + 256, wave_nq * 2 + 64, wave_nq + 64, wave_nq * 4 + 64, wave_nq * 8 + 256,
+            size_t sz[] = {wave_arena_max + 64, wave_nb * 4 + 256, wave_nq * 2 + 64, wave_nq + 64, wave_nq * 4 + 64, wave_nq * 8 + 256,
                                  (size_t)R * SFQ_Q_CNT * 4, wave_ne * 4 + 64, wave_ne * 8 + 64, wave_seg * sizeof(SfqSeg),
-                                 gm_table ? 0 : (wave_nb + ((size_t)R * 4 << gp_bits)) * 8 + 256, gm_table ? 0 : ((size_t)R * 4 << gp_bits) + 64, (size_t)R * qbytes};
+                                 gm_table ? 0 : (wave_nb + ((size_t)R * 4 << gp_bits)) * 8 + 256, gm_table ? 0 : ((size_t)R * 4 << gp_bits) + 64, (size_t)R * qbytes,
+                                 gm_table ? (size_t)R * gstride : 0, (size_t)R * pbytes};
+            if (alias) { sz[5] = std::max(sz[5], sz[10]); sz[10] = 0; }
             DevBuf *bufs[] = {&ctx->arena_buf, &ctx->e2_gsteps, &ctx->e2_qkey, &ctx->e2_qb, &ctx->e2_sorted, &ctx->e2_qsteps,
-                              &ctx->e2_cnt, &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs, &ctx->e2_gbins, &ctx->e2_gcnt, &ctx->qtab};
-            const int first = 0, last = two_phase ? 12 : 13;
+                              &ctx->e2_cnt, &ctx->e2_esorted, &ctx->e2_esteps, &ctx->e2_segs, &ctx->e2_gbins, &ctx->e2_gcnt, &ctx->qtab,
+                              &ctx->gtab, &ctx->pw};
+            // (the base-model table of the single-pass coder and the 256-symbol models come out of the same arena, so that
+            // compress and decompress calls on one context reuse one allocation)
+            auto used = [&](int k) { return k >= 13 || (two_phase ? k < 12 : (k == 0 || k == 12)); };
             size_t total = 0;
-            for (int k = first; k < last; k++) if (two_phase || k == 0 || k == 12) total += (sz[k] + 255) & ~(size_t)255;
-            CK(ctx->scratch.ensure(total));
+            for (int k = 0; k < 15; k++) if (used(k)) total += (sz[k] + 255) & ~(size_t)255;
+            {
+                cudaError_t e = ctx->scratch.ensure(total);
+                if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); release_workspace(ctx); e = ctx->scratch.ensure(total); }
+                CK(e);
+            }
             size_t off = 0;
-            for (int k = first; k < last; k++) if (two_phase || k == 0 || k == 12) bufs[k]->carve(ctx->scratch, sz[k], &off);
+            for (int k = 0; k < 15; k++) if (used(k)) bufs[k]->carve(ctx->scratch, sz[k], &off);
+            if (alias) { size_t o = static_cast<uint8_t *>(ctx->e2_qsteps.p) - static_cast<uint8_t *>(ctx->scratch.p); ctx->e2_gbins.carve(ctx->scratch, sz[5], &o); }
         }
         if (two_phase) {
             CK(ctx->e2_ctr.ensure(64)); CK(ctx->e2_chunks.ensure(nchunks * sizeof(SfqEnc2Chunk)));
@@ -404,6 +425,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             e2.seg_cap = wave_seg; e2.ctr = ctx->e2_ctr.as<uint32_t>();
             e2.gbins = ctx->e2_gbins.as<SfqU2>(); e2.gcnt = ctx->e2_gcnt.as<uint32_t>(); e2.gp_bits = gp_bits;
         }
+        host_mark(ctx, "compress: workspace carved");
         CK(cudaMemcpyAsync(d_arenas, arenas.data(), nchunks * sizeof(SfqArena), cudaMemcpyHostToDevice, s));
         h_small[0] = 0; h_small[1] = part ? part->cursor : sizeof(SfqFileHeader); h_small[2] = 0;
         CK(cudaMemcpyAsync(d_scal, h_small, 24, cudaMemcpyHostToDevice, s));
@@ -449,6 +471,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     TRACED("k_gen_keys", sg, (k_gen_keys<<<dim3((wave_max_nrec + SFQ_GC_RECS - 1) / SFQ_GC_RECS, nc), 128, 0, sg>>>(d_text, d_ls, d_metas + c0, ctx->rec_boff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
                     TRACED("k_gen_part", sg, (k_gen_part<<<nc, 32, gp_smem ? (size_t)36 << gp_bits : 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, nc))); LAUNCHED();
                     TRACED("k_gen_replay", sg, (k_gen_replay<<<ctx->sm_count, 32 * SFQ_GR_WARPS, SFQ_GR_SMEM, sg>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
+                    CK(cudaEventRecord(ctx->gbins_ev, sg));
                     TRACED("k_rc_encode<0>", sg, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else if (two_phase) {
                     { TraceScope ts_(ctx, "k_gen_model", sg);
@@ -472,18 +495,31 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                         TRACED("k_qlt_keys", q, (k_qlt_keys<<<dim3((wave_max_nrec + SFQ_QK_RECS - 1) / SFQ_QK_RECS, nc), 128, 0, q>>>(d_text, d_ls, d_metas + c0, ctx->rec_qoff.as<uint32_t>(), e2, d_e2c, level, nc))); LAUNCHED();
                         TRACED("k_qlt_scan", q, (k_qlt_scan<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
                     }
+                    if (alias && (ctx->plane_mask & 1)) CK(cudaStreamWaitEvent(q, ctx->gbins_ev, 0));
                     if (ctx->q_scatter1) { TRACED("k_qlt_scatter", q, (k_qlt_scatter<<<nwarp_blocks, 128, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED(); }
                     else {
                         TRACED("k_qlt_part1", q, (k_qlt_part1<<<nc, 32, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
                         TRACED("k_qlt_part2", q, (k_qlt_part2<<<ctx->sm_count * 6, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
                     }
+                    CK(cudaEventRecord(ctx->qp2_ev, q));
                     TRACED("k_qlt_model", q, (k_qlt_model<<<ctx->sm_count * 4, SFQ_QM_THREADS, 0, q>>>(d_metas + c0, ws_at(ws, c0), e2, d_e2c, c0))); LAUNCHED();
+                    CK(cudaEventRecord(ctx->qtp_ev, q));
                     k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
                     TRACED("k_rc_encode<1>", q, (k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else {
                     k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, sq>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 7], sq));
+                if (two_phase && !gm_table && ctx->plane_mask == 7) {
+                    // The header encoder is one long chain per chunk whose CTAs hold ~2 KB of shared memory per chunk for the whole wave;
+                    // beside it the short throughput kernels of the other two paths run 3-5x slower than alone.  SFQ_ENC_SCHED holds it back:
+                    //   1  until the quality models are replayed     2  until both paths' partition passes are done
+                    //   4  until the base models are replayed
+                    const int sch = ctx->enc_sched;
+                    if (sch == 1) CK(cudaStreamWaitEvent(side1, ctx->qtp_ev, 0));
+                    if (sch == 2) { CK(cudaStreamWaitEvent(side1, ctx->gbins_ev, 0)); CK(cudaStreamWaitEvent(side1, ctx->qp2_ev, 0)); }
+                    if (sch == 4) CK(cudaStreamWaitEvent(side1, ctx->gbins_ev, 0));
+                }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
                 if (ctx->plane_mask & 4) {
                     const uint32_t rl = ctx->lanes ? ctx->lanes : ctx->enc_rec_lanes ? ctx->enc_rec_lanes : std::min(lanes, 8u);
@@ -500,6 +536,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
             k_pack<<<nc, 256, 0, s>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, ctx->arena_buf.as<uint8_t>(), d_blob_off + c0, level,
                                       d_out, out_cap, reinterpret_cast<uint32_t *>(d_scal + 2)); LAUNCHED();
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 3], s));
+            host_mark(ctx, "compress: wave enqueued");
         }
         if (part && part->on_enqueued && grow == 0) { const int rc_ = part->on_enqueued(); if (rc_) return rc_; }
         host_mark(ctx, "compress: waves enqueued");
@@ -644,19 +681,21 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         const uint32_t cbits = qent;
         const uint64_t gstride = std::max(sfq_gbuckets_bytes(max_level, hbits), sfq_gbuckets_bytes(1, 1));
         const uint64_t qbytes = (uint64_t)std::max(qent, 4096u) * SFQ_L64_WORDS * 4, pbytes = sfq_pwpool_bytes();
-        const uint32_t R = pick_resident(ctx, nchunks, gstride + qbytes + pbytes + 4096, ctx->gtab.cap + ctx->pw.cap + ctx->scratch.cap, fixed_total);
+        const uint32_t R = pick_resident(ctx, nchunks, gstride + qbytes + pbytes + 4096, ctx->scratch.cap, fixed_total);
         {
-            cudaError_t e = ctx->scratch.ensure(fixed_total + (size_t)R * qbytes + 256);
-            if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); release_workspace(ctx); e = ctx->scratch.ensure(fixed_total + (size_t)R * qbytes + 256); }
+            const size_t need = fixed_total + (size_t)R * (qbytes + gstride + pbytes) + 1024;
+            cudaError_t e = ctx->scratch.ensure(need);
+            if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); release_workspace(ctx); e = ctx->scratch.ensure(need); }
             CK(e);
             size_t off = 0;
             for (int k = 0; k < 12; k++) fixed_buf[k]->carve(ctx->scratch, fixed_sz[k], &off);
             ctx->qtab.carve(ctx->scratch, (size_t)R * qbytes, &off);
+            ctx->gtab.carve(ctx->scratch, (size_t)R * gstride, &off);
+            ctx->pw.carve(ctx->scratch, (size_t)R * pbytes, &off);
             t.llen = ctx->t_llen.as<uint32_t>(); t.qlen = ctx->t_qlen.as<uint32_t>(); t.hlen = ctx->t_hlen.as<uint32_t>();
             t.pfg = ctx->t_pfg.as<uint8_t>(); t.pfq = ctx->t_pfq.as<uint8_t>();
             t.boff = ctx->t_boff.as<uint64_t>(); t.qoff = ctx->t_qoff.as<uint64_t>(); t.hoff = ctx->t_hoff.as<uint64_t>(); t.ooff = ctx->t_ooff.as<uint64_t>();
         }
-        CK(ctx->gtab.ensure(R * gstride)); CK(ctx->pw.ensure(R * pbytes));
         nwaves = (nchunks + R - 1) / R;
         if (ensure_wave_events(ctx, nwaves)) return SFQ_ERR_CUDA;
         st.waves = nwaves; st.resident_chunks = R; st.workspace_bytes = (uint64_t)R * (gstride + qbytes + pbytes);
@@ -673,7 +712,13 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
             CK(cudaEventRecord(ctx->wave_ev[WEV * w + 1], s));
             k_decode_usr<<<(nc + 31) / 32, 32, 0, s>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, ctx->bases.as<uint8_t>(), ctx->quals.as<uint8_t>(), ctx->hdrs.as<uint8_t>(), nc); LAUNCHED();
             {
-                const uint32_t lanes = pick_lanes(ctx, nc);
+                uint32_t lanes = pick_lanes(ctx, nc);
+                if (ctx->dec_lanes) lanes = ctx->dec_lanes;
+                else if (ctx->dec_fit && nc >= 4096u && !ctx->lanes) {
+                    // At most one 4-warp CTA of a thread-per-chunk decoder per SM: 9 481 chunks at 16 per warp are 149 CTAs on
+                    // 148 SMs, so one SM always carries two base-decoder CTAs and the launch lasts as long as that SM needs
+                    while (lanes < 32u && ((nc + lanes - 1) / lanes + SFQ_DEC_MAXW - 1) / SFQ_DEC_MAXW > (uint32_t)ctx->sm_count) lanes++;
+                }
                 const unsigned nb = (nc + lanes - 1) / lanes;
                 // Launched next to the other two kernels, the base decoder's CTAs are now and then packed onto few SMs by
                 // the block scheduler: that call's base decoder runs 3.7x slower while the other two run faster (about one
@@ -818,17 +863,28 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
                       const uint8_t **out, size_t *out_n) {
     const uint64_t B = !chunk_bytes ? 1ull << 20 : chunk_bytes < 4096 ? 4096 : chunk_bytes;
     int P = ctx->parts;
+    // Fractions of the grid slots at which the parts end.  A part costs a fixed time (its chains are latency-bound however
+    // few chunks it holds) plus a time per chunk, so the fewest parts win: as many as the input needs coder waves anyway
+    // (W; ~12 bytes of workspace per input byte) plus ONE short head part - 15 % of a wave - whose
+    // copy-in is the only one nobody can hide and whose coding covers the copy-in of the first full part.
+    std::vector<double> ends;
     if (P <= 0) {
-        // waves the whole input would take: ~15 bytes of workspace per input byte against what is free
-        // once the input and the container are resident
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        const double have = (double)free_b + (double)ctx->text.cap + (double)ctx->out.cap + (double)ctx->scratch.cap + (double)ctx->pw.cap + (double)ctx->gtab.cap;
-        const double avail = 0.92 * (have - (double)n - (double)cap);
-        P = avail <= 0 ? 8 : (int)((15.0 * (double)n + avail - 1) / avail);
-        if (n < (256u << 20)) P = 1;
+        const double have = (double)free_b + (double)ctx->text.cap + (double)ctx->out.cap + (double)ctx->scratch.cap;
+        const double avail = 0.92 * (have - 1.2 * (double)n - (double)cap);      // (next to the two text buffers)
+        int W = avail <= 0 ? 8 : (int)((12.0 * (double)n + avail - 1) / avail);
+        if (W < 1) W = 1;
+        if (W > 15) W = 15;
+        if (n < (256u << 20)) return -1;
+        const double head = ctx->head_frac / W;
+        ends.push_back(head);
+        for (int w = 1; w <= W; w++) ends.push_back(head + (1.0 - head) * w / W);
+        P = W + 1;
+    } else {
+        if (P > 16) P = 16;
+        for (int p = 1; p <= P; p++) ends.push_back((double)p / P);
     }
-    if (P > 16) P = 16;
     const uint64_t nslots = (n + B - 1) / B;
     if (P <= 1 || nslots < 2 * (uint64_t)P) return -1;
     struct Part { size_t start, end; uint64_t phase; };
@@ -838,7 +894,7 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
         for (int p = 1; p <= P; p++) {
             size_t cut = n; uint64_t ph = 0;
             if (p < P) {
-                const uint64_t k = nslots * (uint64_t)p / (uint64_t)P;
+                const uint64_t k = std::min<uint64_t>(nslots, std::max<uint64_t>(1, (uint64_t)((double)nslots * ends[p - 1] + 0.5)));
                 cut = sfq_record_start_at_or_after(fastq, n, (size_t)(k * B));
                 ph = cut - k * B;
             }
@@ -846,10 +902,11 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
         }
     }
     if (parts.size() < 2) return -1;
-    size_t max_part = 0;
-    for (auto &pt : parts) max_part = std::max(max_part, pt.end - pt.start);
-    const size_t tstride = (max_part + 16 + 255) & ~(size_t)255;
-    CK(ensure_big(ctx, ctx->text, 2 * tstride));
+    // two text buffers: even parts in the first, odd parts behind it (each sized for its own largest part)
+    size_t max_part[2] = {0, 0};
+    for (size_t p = 0; p < parts.size(); p++) max_part[p & 1] = std::max(max_part[p & 1], parts[p].end - parts[p].start);
+    const size_t tstride = (max_part[0] + 16 + 255) & ~(size_t)255;
+    CK(ensure_big(ctx, ctx->text, tstride + max_part[1] + 16));
     CK(ensure_big(ctx, ctx->out, cap));
     cudaStream_t s = ctx->stream;
     uint8_t *d_out = ctx->out.as<uint8_t>();
@@ -934,7 +991,7 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
 }
 
 void host_mark(const sfq_ctx *ctx, const char *what) {
-    if (!ctx->trace) return;
+    if (!ctx->trace && !ctx->marks) return;
     static std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     fprintf(stderr, "[sfq host] %10.3f ms  %s\n", ms, what);
@@ -979,7 +1036,13 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_QSCATTER")) ctx->q_scatter1 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_ENC_PRIO")) ctx->enc_prio_gen = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QSPEC")) ctx->qspec = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_ENC_SCHED")) ctx->enc_sched = atoi(e);
+    if (const char *e = getenv("SFQ_MARKS")) ctx->marks = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_ALIAS")) ctx->alias_steps = atoi(e) != 0;
     if (const char *e = getenv("SFQ_PARTS")) ctx->parts = atoi(e);
+    if (const char *e = getenv("SFQ_DEC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) ctx->dec_lanes = (uint32_t)v; }
+    if (const char *e = getenv("SFQ_DEC_FIT")) ctx->dec_fit = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_HEAD_FRAC")) { const double v = atof(e); if (v > 0.0 && v < 1.0) ctx->head_frac = v; }
     if (const char *e = getenv("SFQ_DEC_ORDER")) ctx->dec_gen_first = atoi(e) != 0;
     if (const char *e = getenv("SFQ_GEN_AHEAD2")) ctx->gen_ahead2 = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QDEC")) ctx->qdec_octets = atoi(e) != 0;
@@ -994,6 +1057,9 @@ int sfq_create(sfq_ctx **out, int device) {
             cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->head_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->gbins_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->qp2_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->qtp_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     for (auto &e : ctx->part_ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return SFQ_ERR_CUDA; }
     if (cudaFuncSetAttribute(k_gen_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SFQ_GR_SMEM) != cudaSuccess ||
@@ -1027,6 +1093,9 @@ void sfq_destroy(sfq_ctx *ctx) {
     for (int k = 0; k < 2; k++) { if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]); if (ctx->join_ev[k]) cudaEventDestroy(ctx->join_ev[k]); }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->head_ev) cudaEventDestroy(ctx->head_ev);
+    if (ctx->gbins_ev) cudaEventDestroy(ctx->gbins_ev);
+    if (ctx->qp2_ev) cudaEventDestroy(ctx->qp2_ev);
+    if (ctx->qtp_ev) cudaEventDestroy(ctx->qtp_ev);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     for (auto &e : ctx->part_ev) if (e) cudaEventDestroy(e);
@@ -1035,6 +1104,13 @@ void sfq_destroy(sfq_ctx *ctx) {
 }
 
 const char *sfq_last_error(const sfq_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context (is a CUDA device present?)"; }
+int sfq_trim(sfq_ctx *ctx) {
+    if (!ctx) return SFQ_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return SFQ_ERR_CUDA;
+    ctx->release_all();                     // (pointers returned by earlier calls die with the buffers)
+    return 0;
+}
 int sfq_set_max_resident(sfq_ctx *ctx, uint32_t chunks) { if (!ctx) return SFQ_ERR_ARG; ctx->max_resident = chunks; return 0; }
 int sfq_set_chunk_phase(sfq_ctx *ctx, uint64_t phase) { if (!ctx) return SFQ_ERR_ARG; ctx->chunk_phase = phase; return 0; }
 int sfq_get_stats(const sfq_ctx *ctx, sfq_stats *st) { if (!ctx || !st) return SFQ_ERR_ARG; *st = ctx->st; return 0; }
