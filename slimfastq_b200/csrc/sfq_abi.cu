@@ -95,6 +95,9 @@ struct sfq_ctx {
     uint32_t enc_rec_lanes = 0;             // SFQ_ENC_REC_LANES: chunk-streams per warp of the header encoder (0 = pick_lanes)
     cudaEvent_t head_ev = nullptr;
     cudaEvent_t gbins_ev = nullptr;         // k_gen_replay has read the partition lists: their memory may become the quality steps
+    bool qch = false;                       // SFQ_QCH=1: the 4-lane quality decoder with the compact-header entry (7 sectors read, 2 dirtied per quality instead of 8 / 5;
+                                            // A/B at 10 GB: DRAM traffic of the kernel -30 %, but five more loads and three selects per link: 943 ms against 915)
+    int dec_sched = 0;                      // SFQ_DEC_SCHED=1: header decoder after the base decoder instead of beside it
     int enc_sched = 0;                      // SFQ_ENC_SCHED: when the header encoder / base coder chain of a wave may start (see compress_on_device)
     cudaEvent_t qp2_ev = nullptr, qtp_ev = nullptr;   // quality path: second-level partition done / model replay done
     bool marks = false;                     // SFQ_MARKS=1: host-side time marks of a call on stderr (without the per-kernel events of SFQ_TRACE)
@@ -752,6 +755,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                         const unsigned qw = (spread == 1 || spread == 2) ? SFQ_QD_MAXW : 2u;               // warps per CTA
                         const unsigned qsm = spread == 1 ? ctx->spread_smem[1] : 0;
                         if (lpc == 4 && ctx->qspec) k_qlt_decode<4, true><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, qsm, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
+                        else if (lpc == 4 && ctx->qch) k_qlt_decode<4, false, true><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, qsm, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
                         else if (lpc == 4) k_qlt_decode<4, false><<<(nc + 8 * qw - 1) / (8 * qw), 32 * qw, qsm, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
                         else if (ctx->qspec) k_qlt_decode<8, true><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, qsm, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
                         else k_qlt_decode<8, false><<<(nc + 4 * qw - 1) / (4 * qw), 32 * qw, qsm, sqd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pq, nc);
@@ -775,6 +779,8 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                 };
                 if (ctx->dec_gen_first) { if (launch_gen() || launch_qlt()) return SFQ_ERR_CUDA; }
                 else { if (launch_qlt() || launch_gen()) return SFQ_ERR_CUDA; }
+                // SFQ_DEC_SCHED=1: the header decoder (154 ms alone, 480 ms beside the other two) starts when the base decoder is done
+                if (ctx->dec_sched == 1 && ctx->plane_mask == 7) CK(cudaStreamWaitEvent(side1, ctx->wave_ev[WEV * w + 5], 0));
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
                 if (ctx->plane_mask & 4) { k_decode<2><<<(nb + dw - 1) / dw, 32 * dw, spread == 1 ? ctx->spread_smem[2] : 0, side1>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes); LAUNCHED(); }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
@@ -1037,6 +1043,8 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_ENC_PRIO")) ctx->enc_prio_gen = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QSPEC")) ctx->qspec = atoi(e) != 0;
     if (const char *e = getenv("SFQ_ENC_SCHED")) ctx->enc_sched = atoi(e);
+    if (const char *e = getenv("SFQ_DEC_SCHED")) ctx->dec_sched = atoi(e);
+    if (const char *e = getenv("SFQ_QCH")) ctx->qch = atoi(e) != 0;
     if (const char *e = getenv("SFQ_MARKS")) ctx->marks = atoi(e) != 0;
     if (const char *e = getenv("SFQ_ALIAS")) ctx->alias_steps = atoi(e) != 0;
     if (const char *e = getenv("SFQ_PARTS")) ctx->parts = atoi(e);
@@ -1074,6 +1082,7 @@ int sfq_create(sfq_ctx **out, int device) {
         bool ok = cudaFuncSetAttribute(k_decode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[0]) == cudaSuccess &&
                   cudaFuncSetAttribute(k_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[2]) == cudaSuccess &&
                   cudaFuncSetAttribute(k_qlt_decode<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_qlt_decode<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
                   cudaFuncSetAttribute(k_qlt_decode<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
                   cudaFuncSetAttribute(k_qlt_decode<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
                   cudaFuncSetAttribute(k_qlt_decode<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess;

@@ -157,8 +157,16 @@ __device__ __forceinline__ void sfq_qd_fetch(uint4 (&v)[SfqQdGeo<LPC>::NV], cons
     for (int q = 0; q < SfqQdGeo<LPC>::NV; q++) v[q] = __ldcg(reinterpret_cast<const uint4 *>(e + 4 * q));
 }
 
+// CH ("compact header", LPC 4 only): everything a visit changes besides one lane's frequencies lives in ONE 32-byte sector
+// of the entry instead of in every lane's own words -
+//   words 0..7    hdr (total | count << 24), prefix of lanes 1, 2, 3, key, 3 unused
+//   words 8..39   freq pairs, lane L at 8 + 8L           words 40..55  symbol bytes, lane L at 40 + 4L
+// - so a visit reads 7 sectors and dirties 2 (the header's and the coded slot's lane) where the lane-owned layout reads 8 and
+// dirties 5.  Measured (profiles/README.md, r2v): the kernel's DRAM traffic falls by 30 %, its link grows by 9 % (eight load
+// instructions instead of four, the lane's prefix picked by selects) and at the benched residency it ends up 3 % slower -
+// bit-exact, kept for A/B (SFQ_QCH=1), not the default.
 #define SFQ_QD_MAXW 8                   // most warps per CTA (the launch picks 2 or 8)
-template <int LPC, bool SPEC>
+template <int LPC, bool SPEC, bool CH = false>
 __global__ void __launch_bounds__(32 * SFQ_QD_MAXW)
 k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc, SfqChunkMeta *metas, SfqWorkspace ws,
              SfqRecTables t, uint8_t *quals, uint32_t nchunks) {
@@ -190,7 +198,8 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
         rc.start(in + d.soff[SFQ_S_QLT], d.ssize[SFQ_S_QLT]);
         oplane = quals + d.qual_plane + metas[c].big_quals;      // (oversized records' quality lines sit at the front of the chunk's plane)
     }
-    tab += l8 * G::WPL;                                          // this lane's words of every entry
+    static_assert(!CH || (LPC == 4 && !SPEC), "compact-header layout: 4 lanes per chunk, no speculative prefetch");
+    if (!CH) tab += l8 * G::WPL;                                 // this lane's words of every entry
     // decoded qualities of a chunk are contiguous in the plane: eight bytes are gathered in two registers and
     // stored as one aligned word; `opos` counts from the aligned address at or below the chunk's first byte
     uint8_t *const obase = (uint8_t *)((uintptr_t)oplane & ~(uintptr_t)7);
@@ -219,15 +228,52 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
     bool full = false;
     SfqQdModelT<LPC> m;
     m.zero();
-    uint4 nv[G::NV];                                                      // the next model, as loaded
+    uint4 nv[G::NV];                                                      // the next model, as loaded (CH: header, two freq vectors, symbols)
+    uint32_t nkey = 0;                                                    // CH: its key word
 #pragma unroll
     for (int q = 0; q < G::NV; q++) nv[q] = make_uint4(0, 0, 0, 0);
-    if (live) sfq_qd_fetch<LPC>(nv, tab);
+    uint32_t ex1 = 0, ex2 = 0, ex3 = 0, key = 0;                          // CH: the prefixes of lanes 1..3 and the entry's key, in every lane
+    bool claimed = false;                                                 // CH: the entry was taken by this visit (its key goes out with the header)
+    // CH: fetch / unpack of an entry
+#define SFQ_QD_FETCH(e_)                                                                                   \
+    {                                                                                                      \
+        const uint32_t *e__ = (e_);                                                                        \
+        if (CH) {                                                                                          \
+            /* (scalar loads: a 128-bit load pins its four words to an aligned register quad, and the register       \
+               allocator then copies the first word out of the quad right behind the load - a first touch that waits   \
+               out the whole DRAM latency before the model update meant to cover it) */                                \
+            nv[0].x = __ldcg(e__); nv[0].y = __ldcg(e__ + 1); nv[0].z = __ldcg(e__ + 2); nv[0].w = __ldcg(e__ + 3);    \
+            nkey = __ldcg(e__ + 4);                                                                        \
+            nv[1] = __ldcg(reinterpret_cast<const uint4 *>(e__ + 8 + 8 * l8));                             \
+            nv[2] = __ldcg(reinterpret_cast<const uint4 *>(e__ + 12 + 8 * l8));                            \
+            nv[3] = __ldcg(reinterpret_cast<const uint4 *>(e__ + 40 + 4 * l8));                            \
+        } else sfq_qd_fetch<LPC>(nv, e__);                                                                 \
+    }
+#define SFQ_QD_UNPACK()                                                                                    \
+    {                                                                                                      \
+        if (CH) {                                                                                          \
+            const uint32_t fw_[8] = {nv[1].x, nv[1].y, nv[1].z, nv[1].w, nv[2].x, nv[2].y, nv[2].z, nv[2].w}; \
+            _Pragma("unroll")                                                                              \
+            for (int k_ = 0; k_ < 8; k_++) { m.f[(2 * k_) % SPL] = fw_[k_] & 0xffffu; m.f[(2 * k_ + 1) % SPL] = fw_[k_] >> 16; } \
+            m.sy[0] = nv[3].x; m.sy[G::SW > 1 ? 1 : 0] = nv[3].y; m.sy[G::SW > 2 ? 2 : 0] = nv[3].z; m.sy[G::SW > 3 ? 3 : 0] = nv[3].w; \
+            m.hdr = nv[0].x; ex1 = nv[0].y; ex2 = nv[0].z; ex3 = nv[0].w; key = nkey;                      \
+            m.excl = l8 == 1u ? ex1 : l8 == 2u ? ex2 : l8 == 3u ? ex3 : 0u;                                \
+            claimed = false;                                                                               \
+        } else m.unpack(nv);                                                                               \
+    }
+    if (live) SFQ_QD_FETCH(tab)
     bool fresh = live;                                                    // nv holds a model not yet unpacked
     bool chk = live && !dense;
 
     while (__any_sync(FULL, live)) {
-        if (fresh) m.unpack(nv);
+        if (CH) {
+            // `fresh` as the compiler cannot see through it: the unpack below is partly plain copies of the loaded words, and
+            // with the condition known to be the one the fetch ran under, those copies are resolved right behind the loads
+            // at the bottom of the previous step - the first touch of the loaded registers, which then waits out the whole
+            // DRAM latency before the model update that was meant to cover it (measured: long-scoreboard stalls x2.2)
+            const bool fr = __shfl_sync(FULL, (uint32_t)fresh, lane) != 0u;
+            if (fr) SFQ_QD_UNPACK()
+        } else if (fresh) SFQ_QD_UNPACK()
         // ---------------------------------------------------------------- the entry of `ctx` (hash probe)
         // An entry is in use once its total is non-zero (every update adds to it, and every lane holds the
         // total); lane 0 keeps the 16-bit key in its otherwise unused prefix word.
@@ -235,16 +281,16 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
             uint32_t probes = 0;
             for (;;) {
                 const bool occ = (m.hdr & 0x3fffffu) != 0u;
-                const unsigned vb = __ballot_sync(FULL, chk && occ && l8 == 0 && m.excl != ctx);
-                const bool bad = (vb >> osh) & 1u;
+                const unsigned vb = __ballot_sync(FULL, chk && occ && (CH ? key != ctx : (l8 == 0 && m.excl != ctx)));
+                const bool bad = CH ? (chk && occ && key != ctx) : (bool)((vb >> osh) & 1u);
                 if (chk && !occ) {                                        // first visit of this context in the chunk
                     if (used + 1u >= nent) { full = true; live = false; }
-                    else { used++; if (l8 == 0) m.excl = ctx; }
+                    else { used++; if (CH) { key = ctx; claimed = true; } else if (l8 == 0) m.excl = ctx; }
                     chk = false;
                 } else if (chk && bad) {                                  // somebody else's entry: walk on
                     h = h + 1u == nent ? 0u : h + 1u;
                     if (++probes > nent) { full = true; live = false; chk = false; }
-                    else { sfq_qd_fetch<LPC>(nv, tab + (size_t)h * 64u); m.unpack(nv); }
+                    else { SFQ_QD_FETCH(tab + (size_t)h * 64u) SFQ_QD_UNPACK() }
                 } else chk = false;
                 if (!vb) break;
             }
@@ -367,7 +413,7 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
         if (fresh) {
             hn = dense ? nctx : __umulhi(nctx * 2654435761u, nent);
             if (!dense && hn == h) hn = h + 1u == nent ? 0u : h + 1u;       // entry h is ours (key = ctx): skip it unseen, its store is still pending
-            sfq_qd_fetch<LPC>(nv, tab + (size_t)hn * 64u);
+            SFQ_QD_FETCH(tab + (size_t)hn * 64u)
         }
 
         // ---------------------------------------------------------------- update_freq (log64_ranger.hpp:69-87)
@@ -385,6 +431,10 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
 #pragma unroll
             for (int d = 1; d < LPC; d <<= 1) { tmp = __shfl_up_sync(FULL, inc, d, LPC); if (l8 >= (uint32_t)d) inc += tmp; }
             const uint32_t total = __shfl_sync(FULL, inc, LPC - 1, LPC);
+            if (CH) {                                                        // every lane keeps all three prefixes
+                const uint32_t p1_ = __shfl_sync(FULL, inc - ls, 1, LPC), p2_ = __shfl_sync(FULL, inc - ls, 2, LPC), p3_ = __shfl_sync(FULL, inc - ls, 3, LPC);
+                if (dohalve) { ex1 = p1_; ex2 = p2_; ex3 = p3_; }
+            }
             if (dohalve) {
                 if (l8) m.excl = inc - ls;
                 tot2 = total;
@@ -398,6 +448,7 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
             fn += 6u;
             tot2 += 6u;
             if (l8 > hl) m.excl += 6u;
+            if (CH) { ex1 += hl < 1u ? 6u : 0u; ex2 += hl < 2u ? 6u : 0u; ex3 += hl < 3u ? 6u : 0u; }
         }
         if (mine) m.set_freq(hk, fn);
         uint32_t cnt2 = count;
@@ -419,6 +470,10 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
                 const uint32_t symprev = bprev ^ (slot - 1u);
                 const uint32_t byte_lo = (ssym ^ (slot - 1u)) & 0xffu;        // slot-1 now holds this symbol ...
                 const uint32_t byte_hi = (symprev ^ slot) & 0xffu;            // ... and slot the neighbour's
+                if (CH && hk == 0u) {                                         // the slot moved into the lane before: that lane's prefix is unchanged, lane hl's grows
+                    const uint32_t d_ = fn - fprev;
+                    ex1 += hl == 1u ? d_ : 0u; ex2 += hl == 2u ? d_ : 0u; ex3 += hl == 3u ? d_ : 0u;
+                }
                 if (l8 == hl) {
                     if (hk == 0u) {
                         m.f[0] = fprev;
@@ -440,13 +495,31 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
         if (act) {
             m.hdr = tot2 | (cnt2 << 24);
             uint32_t *e = tab + (size_t)h * 64u;
-            if (wide || mine) m.store_freqs(e);
-            if (syms_dirty) m.store_syms(e);
-            m.store_hdr(e);
+            if (CH) {
+                if (wide || mine) {
+                    uint32_t *fe = e + 8 + 8 * l8;
+                    *reinterpret_cast<uint4 *>(fe) = make_uint4(m.f[0] | (m.f[1] << 16), m.f[2] | (m.f[3] << 16), m.f[4] | (m.f[5] << 16), m.f[6] | (m.f[7] << 16));
+                    *reinterpret_cast<uint4 *>(fe + 4) = make_uint4(m.f[8 % SPL] | (m.f[9 % SPL] << 16), m.f[10 % SPL] | (m.f[11 % SPL] << 16),
+                                                                    m.f[12 % SPL] | (m.f[13 % SPL] << 16), m.f[14 % SPL] | (m.f[15 % SPL] << 16));
+                }
+                if (syms_dirty) *reinterpret_cast<uint4 *>(e + 40 + 4 * l8) = make_uint4(m.sy[0], m.sy[G::SW > 1 ? 1 : 0], m.sy[G::SW > 2 ? 2 : 0], m.sy[G::SW > 3 ? 3 : 0]);
+                if (l8 == 0) {
+                    *reinterpret_cast<uint4 *>(e) = make_uint4(m.hdr, ex1, ex2, ex3);
+                    if (claimed) e[4] = key;
+                }
+                claimed = false;
+            } else {
+                if (wide || mine) m.store_freqs(e);
+                if (syms_dirty) m.store_syms(e);
+                m.store_hdr(e);
+            }
         }
+        if (CH) __syncwarp();            // the header sector is written by lane 0 and read by all four lanes: order the warp's stores before its later loads
         if (fresh) { h = hn; ctx = nctx; chk = !dense; }
     }
 #undef SFQ_QD_OPEN
+#undef SFQ_QD_FETCH
+#undef SFQ_QD_UNPACK
 #undef SFQ_QD_BC32
 #undef SFQ_QD_BC64
     if (valid && l8 == 0) {
