@@ -107,7 +107,7 @@ struct sfq_ctx {
     uint32_t dec_lanes = 0;                 // SFQ_DEC_LANES: chunk-streams per warp of the thread-per-chunk decoders (0 = pick_lanes / dec_fit)
     bool dec_fit = false;                   // SFQ_DEC_FIT=1: widen the warps of a large wave so that its CTAs number at most one per SM (A/B: 17 lanes per warp cost the base decoder 3 %, and no outlier either way in 6 steps)
     double head_frac = 0.15;                // SFQ_HEAD_FRAC: size of the head part of a pipelined sfq_compress, as a fraction of a coder wave
-    int parts = 0;                          // SFQ_PARTS: parts per sfq_compress call (0 = one per coder wave the input needs)
+    int parts = 0;                          // SFQ_PARTS: parts per sfq_compress call (0 = a head part + one per coder wave the input needs, from 256 MB; -1 = that for any size)
     bool trace = false;                     // SFQ_TRACE=1: per-kernel event timings of the coder waves on stderr
     std::vector<std::pair<const char *, std::pair<cudaEvent_t, cudaEvent_t>>> tr;
     int gdec32 = 0;                         // SFQ_GDEC=1: warp-converged base decoder (A/B; slower)
@@ -882,7 +882,7 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
         int W = avail <= 0 ? 8 : (int)((12.0 * (double)n + avail - 1) / avail);
         if (W < 1) W = 1;
         if (W > 15) W = 15;
-        if (n < (256u << 20)) return -1;
+        if (n < (256u << 20) && P == 0) return -1;                 // (SFQ_PARTS=-1: the automatic split whatever the size - tests)
         const double head = ctx->head_frac / W;
         ends.push_back(head);
         for (int w = 1; w <= W; w++) ends.push_back(head + (1.0 - head) * w / W);
@@ -891,23 +891,27 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
         if (P > 16) P = 16;
         for (int p = 1; p <= P; p++) ends.push_back((double)p / P);
     }
-    const uint64_t nslots = (n + B - 1) / B;
+    // the caller's own buffer may itself be a part of a file (sfq_set_chunk_phase): its grid lines lie at k*B - phase0
+    const uint64_t phase0 = ctx->chunk_phase;
+    const uint64_t nslots = sfq_slot_count(n, B, phase0);
     if (P <= 1 || nslots < 2 * (uint64_t)P) return -1;
     struct Part { size_t start, end; uint64_t phase; };
     std::vector<Part> parts;
     {
-        size_t prev = 0; uint64_t prev_phase = 0;
+        size_t prev = 0; uint64_t prev_phase = phase0;
         for (int p = 1; p <= P; p++) {
             size_t cut = n; uint64_t ph = 0;
             if (p < P) {
                 const uint64_t k = std::min<uint64_t>(nslots, std::max<uint64_t>(1, (uint64_t)((double)nslots * ends[p - 1] + 0.5)));
-                cut = sfq_record_start_at_or_after(fastq, n, (size_t)(k * B));
-                ph = cut - k * B;
+                const uint64_t line = sfq_slot_target(k, B, phase0);
+                cut = line >= n ? n : sfq_record_start_at_or_after(fastq, n, (size_t)line);
+                ph = cut - line;
             }
             if (cut > prev) { parts.push_back({prev, cut, prev_phase}); prev = cut; prev_phase = ph; }
         }
     }
     if (parts.size() < 2) return -1;
+    ctx->chunk_phase = 0;                                      // consumed: every part below sets its own
     // two text buffers: even parts in the first, odd parts behind it (each sized for its own largest part)
     size_t max_part[2] = {0, 0};
     for (size_t p = 0; p < parts.size(); p++) max_part[p & 1] = std::max(max_part[p & 1], parts[p].end - parts[p].start);

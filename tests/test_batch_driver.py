@@ -74,3 +74,22 @@ def test_workers_keep_one_context_and_never_overwrite_on_decompress(tmp_path):
     for k, v in data.items():
         if k != "s0.fq":
             assert (back / k).read_bytes() == v
+
+
+@pytest.mark.gpu
+def test_batch_over_two_gpus(tmp_path):
+    """-g 0,1: one worker (one context) per device, files from one shared queue."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    src, mid, back = tmp_path / "FQ", tmp_path / "SFQ", tmp_path / "BACK"
+    src.mkdir()
+    data = {f"s{i}.fq": synth.illumina(1500, seed=300 + i) for i in range(6)}
+    for k, v in data.items():
+        (src / k).write_bytes(v)
+    r = run("-v", "-g", "0,1", "-c", "2", "-t", str(mid), str(src))
+    assert r.returncode == 0
+    assert run("-d", "-g", "0,1", "-c", "2", "-t", str(back), "-f", ".fq", str(mid)).returncode == 0
+    for k, v in data.items():
+        assert (back / k).read_bytes() == v

@@ -69,6 +69,26 @@ def test_pipelined_parts_give_the_one_call_container(codec):
         assert c.compress(ont, 3, 1 << 18) == codec.compress(ont, 3, 1 << 18)
     finally:
         c.close()
+    # a buffer that is itself a shard of a file (sfq_set_chunk_phase) cut into parts: the shards' containers must still merge
+    # into the one-call container (the parts' grid lines lie at k*B - phase)
+    from slimfastq_b200 import api
+    c = codec_with({"SFQ_PARTS": "2"})
+    try:
+        B = 1 << 17
+        shards = api.split_on_grid(data, 2, B)
+        assert len(shards) == 2 and shards[1][2] != 0
+        blobs = [c.compress(data[a:b], 3, B, phase=ph) for a, b, ph in shards]
+        assert api.merge_containers(blobs) == codec.compress(data, 3, B)
+    finally:
+        c.close()
+    # the automatic split: a short head part (its copy-in is the exposed one) + one part per coder wave
+    c = codec_with({"SFQ_PARTS": "-1", "SFQ_HEAD_FRAC": "0.3"})
+    try:
+        blob = c.compress(data, 3, 1 << 17)
+        assert c.stats()["waves"] == 2
+        assert blob == codec.compress(data, 3, 1 << 17) and c.decompress(blob) == data
+    finally:
+        c.close()
 
 
 def test_chunks_equal_the_reference_binary_itself(codec, oracle):
