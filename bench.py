@@ -234,7 +234,8 @@ def reference_timed(block: bytes, level: int, chunk: int, cores: int, steps: int
         left = max(5.0, budget_s - (time.perf_counter() - t_begin) - 5.0)
         per_pass = left / npass                                      # seconds a pass may take: enforced, not hoped for
         want = (sample_mb << 20) if sample_mb else int(rate * per_pass * 0.8)
-        want = max(len(cal), min(want, 2 << 30))
+        want = max(len(cal), min(want, 512 << 20))     # (2 GiB passes showed 2x pass-to-pass swings on the 16-core box - 300 GB of table
+                                                       # zeroing per pass in the kernel's page allocator - where ~400 MiB passes stay within 1 %)
         sample, lens = sample_of(want)
         # batches of ~4 s of work: a pass stops at the first batch boundary past its deadline (a pass of the reference is
         # now and then several times slower than its neighbours - page zeroing of its 77 MB of tables per process, tmpfs
@@ -565,7 +566,7 @@ def main():
         traffic, traffic_src = None, None
         try:
             tp = json.load(open(TRAFFIC_PROFILE))
-            kk = tp["kernels"].get(kname)
+            kk = next((v for k, v in tp["kernels"].items() if k.startswith("k_qlt_decode<%d" % lpc)), None)   # (ncu prints every template argument)
             same = tp["config"]["chunk_bytes"] == args.chunk and tp["config"]["level"] == args.level and abs(tp["config"]["nchunks"] - sc["nchunks"]) <= 0.02 * sc["nchunks"]
             if kk and same:
                 traffic = int(kk["dram_bytes_read"] + kk["dram_bytes_write"])
@@ -716,8 +717,10 @@ def run_extras(args, B: Bench, K, block: bytes, d_text, line: dict, sc: dict, sd
                "compress_GBps": round(m["n"] * 2 / (a["t_c"] / 1e3) / 1e9, 4), "decompress_GBps": round(m["n"] * 2 / (a["t_d"] / 1e3) / 1e9, 4),
                "ratio": round(m["n"] / m["csz"], 4), "stream_ratio": round(m["n"] / m["sc"]["stream_bytes"], 4), "waves": [m["sc"]["waves"], m["sd"]["waves"]]}
         if not args.no_e2e:
-            e, err = B.e2e_steps(dt, m["csz"], level, args.chunk, 2, 1)
+            e, err = B.e2e_steps(dt, m["csz"], level, args.chunk, 2, 2)
             leg["e2e"] = round(2 * m["n"] * 2 / e["wall_s"] / 1e9, 4) if e else None
+            if e:
+                leg["e2e_per_step_ms[c_total,c_code,d_total,d_gen,d_qlt,d_rec]"] = e["steps"]
             if err:
                 leg["e2e_error"] = err
         legs[name] = leg

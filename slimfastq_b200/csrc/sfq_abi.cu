@@ -106,7 +106,7 @@ struct sfq_ctx {
     cudaEvent_t part_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] text buffer filled, [2] part coded, [3] last copy out done
     uint32_t dec_lanes = 0;                 // SFQ_DEC_LANES: chunk-streams per warp of the thread-per-chunk decoders (0 = pick_lanes / dec_fit)
     bool dec_fit = false;                   // SFQ_DEC_FIT=1: widen the warps of a large wave so that its CTAs number at most one per SM (A/B: 17 lanes per warp cost the base decoder 3 %, and no outlier either way in 6 steps)
-    double head_frac = 0.15;                // SFQ_HEAD_FRAC: size of the head part of a pipelined sfq_compress, as a fraction of a coder wave
+    double head_frac = 0.08;                // SFQ_HEAD_FRAC: size of the head part of a pipelined sfq_compress, as a fraction of a coder wave (swept 0.05 .. 0.25 at 10 GB: 815 / 821 / 827 / 841 ms per call)
     int parts = 0;                          // SFQ_PARTS: parts per sfq_compress call (0 = a head part + one per coder wave the input needs, from 256 MB; -1 = that for any size)
     bool trace = false;                     // SFQ_TRACE=1: per-kernel event timings of the coder waves on stderr
     std::vector<std::pair<const char *, std::pair<cudaEvent_t, cudaEvent_t>>> tr;
@@ -871,7 +871,7 @@ int compress_in_parts(sfq_ctx *ctx, const uint8_t *fastq, size_t n, int level, u
     int P = ctx->parts;
     // Fractions of the grid slots at which the parts end.  A part costs a fixed time (its chains are latency-bound however
     // few chunks it holds) plus a time per chunk, so the fewest parts win: as many as the input needs coder waves anyway
-    // (W; ~12 bytes of workspace per input byte) plus ONE short head part - 15 % of a wave - whose
+    // (W; ~12 bytes of workspace per input byte) plus ONE short head part - 8 % of a wave - whose
     // copy-in is the only one nobody can hide and whose coding covers the copy-in of the first full part.
     std::vector<double> ends;
     if (P <= 0) {
