@@ -492,6 +492,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # pinned staging buffers on the GPU's own NUMA node (first touch): N ranks then do not all copy through node 0
+    from slimfastq_b200.api import bind_to_device_node
+    numa_node, all_cpus = bind_to_device_node(local)
     codec = S.Codec(local)
     B = Bench(torch, dist, codec, local, world)
     if args.single_file:
@@ -592,7 +595,8 @@ def main():
                                     % ("ONT-style long-read" if args.workload == "ont" else "Markov-quality Illumina", len(block) // 10**6, tiles, max(1, round(len(block) / args.chunk))),
             "config": {"workload": workload_label(args.workload, args.bins8, args.gb),
                        "level": args.level, "chunk_bytes": args.chunk, "bytes_per_gpu": n, "l2": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" % (n / 1e9),
-                       "step": "compress + decompress", "sharding": "chunks by rank, no data-path collective"},
+                       "step": "compress + decompress", "sharding": "chunks by rank, no data-path collective",
+                       "host_numa_node": numa_node},
             "compress_GBps": round(tot_bytes * K_ / (t_c_max / 1e3) / 1e9, 4),
             "decompress_GBps": round(tot_bytes * K_ / (t_d_max / 1e3) / 1e9, 4),
             "ratio": round(tot_bytes / tot_csz, 4), "stream_ratio": round(n / sc["stream_bytes"], 4),
@@ -634,6 +638,8 @@ def main():
     # ---------------- extras (N = 1 only; all outside the timed headline region)
     if extras:
         try:
+            if all_cpus:
+                os.sched_setaffinity(0, all_cpus)          # the CPU legs below use every core the process was given
             run_extras(args, B, K, block, d_text, line, sc, sd, acc, cores)
         except Exception as ex:                          # the headline numbers stand on their own
             line["extras_error"] = "%s: %s" % (type(ex).__name__, str(ex)[:300])

@@ -80,6 +80,11 @@ const char *sfq_version(void);          /* "2.04/6 b200" - user version / intern
 /* Upper bound on resident chunks per coder wave (0 = as many as device memory allows). */
 int sfq_set_max_resident(sfq_ctx *ctx, uint32_t chunks);
 
+/* NUMA node of the host the CUDA device hangs off (sysfs numa_node of its PCI function), -1 if unknown.  Pinned staging
+ * buffers are placed by first touch: a caller that binds its thread to that node's cores before it allocates them keeps
+ * the host<->device copies off the inter-socket link (slimfastq_b200.api.bind_to_device_node does exactly that). */
+int sfq_device_numa_node(int device);
+
 /* Give back the device and pinned memory the context keeps between calls (grow-only workspace sized for the largest
  * call so far - up to ~90 % of the device after a 10 GB call).  Results returned by earlier calls become invalid. */
 int sfq_trim(sfq_ctx *ctx);

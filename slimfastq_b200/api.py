@@ -47,6 +47,7 @@ EXPORTS = [
     "sfq_record_start_at_or_after", "sfq_last_record_start", "sfq_set_chunk_phase", "sfq_stream_cut",
     "sfq_encode_gen_chunks", "sfq_encode_qlt_chunks", "sfq_encode_rec_chunks",
     "sfq_decode_gen_chunks", "sfq_decode_qlt_chunks", "sfq_decode_rec_chunks", "sfq_trim",
+    "sfq_device_numa_node",
 ]
 
 _lib = None
@@ -67,6 +68,7 @@ def load_library():
     L.sfq_version.argtypes = []; L.sfq_version.restype = C.c_char_p
     L.sfq_set_max_resident.argtypes = [vp, C.c_uint32]; L.sfq_set_max_resident.restype = C.c_int
     L.sfq_trim.argtypes = [vp]; L.sfq_trim.restype = C.c_int
+    L.sfq_device_numa_node.argtypes = [C.c_int]; L.sfq_device_numa_node.restype = C.c_int
     L.sfq_set_chunk_phase.argtypes = [vp, C.c_uint64]; L.sfq_set_chunk_phase.restype = C.c_int
     L.sfq_host_alloc.argtypes = [sz]; L.sfq_host_alloc.restype = vp
     L.sfq_host_free.argtypes = [vp]; L.sfq_host_free.restype = None
@@ -105,6 +107,37 @@ def _host_ptr(buf):
 
     a = np.ascontiguousarray(buf)
     return a.ctypes.data, a.nbytes, a
+
+
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_device_node(device: int):
+    """Bind the calling process to the cores of the NUMA node the GPU hangs off, so that pinned buffers allocated from now
+    on are placed there (first touch) and host<->device copies stay off the inter-socket link.  Returns
+    (node, previous affinity set) or (None, None) when the node is unknown or has no core this process may use; restore with
+    os.sched_setaffinity(0, previous) before starting CPU work that should use every core."""
+    try:
+        node = load_library().sfq_device_numa_node(device)
+        if node < 0:
+            return None, None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        prev = os.sched_getaffinity(0)
+        want = cpus & prev
+        if not want or want == prev:
+            return (node, prev) if want else (None, None)
+        os.sched_setaffinity(0, want)
+        return node, prev
+    except (OSError, ValueError, AttributeError):
+        return None, None
 
 
 class Codec:

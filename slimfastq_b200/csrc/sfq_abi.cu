@@ -97,6 +97,8 @@ struct sfq_ctx {
     cudaEvent_t gbins_ev = nullptr;         // k_gen_replay has read the partition lists: their memory may become the quality steps
     bool qch = false;                       // SFQ_QCH=1: the 4-lane quality decoder with the compact-header entry (7 sectors read, 2 dirtied per quality instead of 8 / 5;
                                             // A/B at 10 GB: DRAM traffic of the kernel -30 %, but five more loads and three selects per link: 943 ms against 915)
+    bool rec_global = false;                // SFQ_REC_GLOBAL=1 (see the header coder's launch)
+    DevBuf rec_scr;
     int dec_sched = 0;                      // SFQ_DEC_SCHED=1: header decoder after the base decoder instead of beside it
     int enc_sched = 0;                      // SFQ_ENC_SCHED: when the header encoder / base coder chain of a wave may start (see compress_on_device)
     cudaEvent_t qp2_ev = nullptr, qtp_ev = nullptr;   // quality path: second-level partition done / model replay done
@@ -130,7 +132,7 @@ struct sfq_ctx {
         DevBuf *all[] = {&text, &out, &tiles, &tile_prefix, &lines, &scalars, &rec_begin, &r0, &r1, &metas,
                          &arenas, &arena_buf, &blob_off, &gtab, &qtab, &pw, &dchunks, &bhdrs, &bases, &quals,
                          &hdrs, &rec_chunk, &t_llen, &t_qlen, &t_hlen, &t_pfg, &t_pfq, &t_boff, &t_qoff,
-                         &t_hoff, &t_ooff, &e2_gsteps, &e2_qkey, &e2_qb, &e2_sorted, &e2_qsteps, &e2_cnt, &e2_esorted,
+                         &t_hoff, &t_ooff, &rec_scr, &e2_gsteps, &e2_qkey, &e2_qb, &e2_sorted, &e2_qsteps, &e2_cnt, &e2_esorted,
                          &e2_esteps, &e2_segs, &e2_ctr, &e2_chunks, &rec_qoff, &e2_gbins, &e2_gcnt, &rec_boff};
         for (DevBuf *b : all) b->release();
         scratch.release();
@@ -526,7 +528,12 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 8], side1));
                 if (ctx->plane_mask & 4) {
                     const uint32_t rl = ctx->lanes ? ctx->lanes : ctx->enc_rec_lanes ? ctx->enc_rec_lanes : std::min(lanes, 8u);
-                    TRACED("k_encode<2>", side1, (k_encode<2><<<(nc + rl - 1) / rl, 32, rl * sizeof(SfqRecScratch), side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, rl))); LAUNCHED();
+                    SfqWorkspace wr = ws;
+                    if (ctx->rec_global) {                                   // SFQ_REC_GLOBAL=1: the header coder's scratch in global memory (A/B: no shared memory held for the whole wave)
+                        CK(ctx->rec_scr.ensure((size_t)nc * sizeof(SfqRecScratch)));
+                        wr.rec_scratch = ctx->rec_scr.as<uint8_t>();
+                    }
+                    TRACED("k_encode<2>", side1, (k_encode<2><<<(nc + rl - 1) / rl, 32, ctx->rec_global ? 0 : rl * sizeof(SfqRecScratch), side1>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, wr, level, nc, rl))); LAUNCHED();
                 }
                 CK(cudaEventRecord(ctx->wave_ev[WEV * w + 9], side1));
                 CK(cudaEventRecord(ctx->join_ev[0], side0));
@@ -822,7 +829,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         k_plane_lines<<<(unsigned)((nrec * 32 + 255) / 256), 256, 0, s>>>(d_metas, t, ctx->rec_chunk.as<uint32_t>(),
             plane == 1 ? ctx->bases.as<uint8_t>() : plane == 2 ? ctx->quals.as<uint8_t>() : ctx->hdrs.as<uint8_t>(), plane, d_out, nrec); LAUNCHED();
     } else
-    k_assemble<<<(unsigned)((nrec * 32 + 255) / 256), 256, 0, s>>>(d_dcs, d_metas, t, ctx->rec_chunk.as<uint32_t>(), ctx->bases.as<uint8_t>(),
+    k_assemble<<<(unsigned)(((nrec + SFQ_ASM_RECS - 1) / SFQ_ASM_RECS * 32 + 255) / 256), 256, 0, s>>>(d_dcs, d_metas, t, ctx->rec_chunk.as<uint32_t>(), ctx->bases.as<uint8_t>(),
                                                                    ctx->quals.as<uint8_t>(), ctx->hdrs.as<uint8_t>(), d_out, nrec); LAUNCHED();
     CK(cudaEventRecord(ctx->ev[EV_CODE_END], s));
     CK(cudaStreamSynchronize(s));
@@ -1048,6 +1055,7 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_QSPEC")) ctx->qspec = atoi(e) != 0;
     if (const char *e = getenv("SFQ_ENC_SCHED")) ctx->enc_sched = atoi(e);
     if (const char *e = getenv("SFQ_DEC_SCHED")) ctx->dec_sched = atoi(e);
+    if (const char *e = getenv("SFQ_REC_GLOBAL")) ctx->rec_global = atoi(e) != 0;
     if (const char *e = getenv("SFQ_QCH")) ctx->qch = atoi(e) != 0;
     if (const char *e = getenv("SFQ_MARKS")) ctx->marks = atoi(e) != 0;
     if (const char *e = getenv("SFQ_ALIAS")) ctx->alias_steps = atoi(e) != 0;
@@ -1117,6 +1125,19 @@ void sfq_destroy(sfq_ctx *ctx) {
 }
 
 const char *sfq_last_error(const sfq_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context (is a CUDA device present?)"; }
+int sfq_device_numa_node(int device) {
+    char id[32] = {0};
+    if (cudaDeviceGetPCIBusId(id, sizeof id, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *p = id; *p; p++) if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');
+    char path[96];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", id);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
 int sfq_trim(sfq_ctx *ctx) {
     if (!ctx) return SFQ_ERR_ARG;
     cudaSetDevice(ctx->device);

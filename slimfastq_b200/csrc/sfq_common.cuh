@@ -122,5 +122,6 @@ struct SfqWorkspace {
     uint32_t *qtab;  uint64_t qtab_words;   uint32_t cbits;     // quality-context tables (hashed); cbits = ENTRIES of one table
     uint32_t *pw;                                                // 256-symbol model pools
     uint32_t gen_ahead2;                                         // base decoder: prefetch the table line two bases ahead
+    uint8_t  *rec_scratch;                                       // header encoder: per-chunk scratch in global memory (null: shared memory)
 };
 

@@ -158,7 +158,8 @@ k_encode(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, SfqC
     if (ROLE == 0) sfq_gen_encode_chunk(text, ls, m, level, ws.gtab + (size_t)c * ws.gtab_stride, ws.hbits, pw, arena_buf, &arenas[c]);
     else {
         extern __shared__ uint64_t rec_smem[];             // one SfqRecScratch per chunk-stream of the warp
-        sfq_rec_encode_chunk(text, ls, m, pw, arena_buf, &arenas[c], reinterpret_cast<SfqRecScratch *>(rec_smem) + threadIdx.x);
+        SfqRecScratch *scr = ws.rec_scratch ? reinterpret_cast<SfqRecScratch *>(ws.rec_scratch) + c : reinterpret_cast<SfqRecScratch *>(rec_smem) + threadIdx.x;
+        sfq_rec_encode_chunk(text, ls, m, pw, arena_buf, &arenas[c], scr);
     }
 }
 
@@ -389,13 +390,11 @@ k_out_offsets(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict
 
 // One warp per record: planes -> FASTQ text, applying the "quality '!' means N" rule of
 // GenLoad::normalize_gen (gens.cpp:200-213) with the flags left by sfq_gen_decode_chunk.
-__global__ void __launch_bounds__(256)
-k_assemble(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ metas, SfqRecTables t,
+// (SFQ_ASM_RECS consecutive records per warp: a warp that lives for one 340-byte record spends its life being launched)
+#define SFQ_ASM_RECS 8u
+__device__ __forceinline__ void sfq_assemble_record(const SfqChunkMeta *__restrict__ metas, const SfqRecTables &t,
            const uint32_t *__restrict__ rec_chunk, const uint8_t *__restrict__ bases,
-           const uint8_t *__restrict__ quals, const uint8_t *__restrict__ hdrs, uint8_t *out, uint64_t nrec) {
-    const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    if (k >= nrec) return;
+           const uint8_t *__restrict__ quals, const uint8_t *__restrict__ hdrs, uint8_t *out, uint64_t k, uint32_t lane) {
     const SfqChunkMeta &m = metas[rec_chunk[k]];
     if (m.status != SFQ_OK) return;
     const uint32_t hlen = t.hlen[k], llen = t.llen[k], qlen = t.qlen[k];
@@ -445,6 +444,16 @@ k_assemble(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ 
     if (m.solid) { if (lane == 0) o[0] = t.pfq[k]; o += 1; }
     for (uint32_t i = lane; i < qlen; i += 32) o[i] = q[i];
     if (lane == 0) o[qlen] = '\n';
+}
+__global__ void __launch_bounds__(256)
+k_assemble(const SfqDecChunk *__restrict__ dc, const SfqChunkMeta *__restrict__ metas, SfqRecTables t,
+           const uint32_t *__restrict__ rec_chunk, const uint8_t *__restrict__ bases,
+           const uint8_t *__restrict__ quals, const uint8_t *__restrict__ hdrs, uint8_t *out, uint64_t nrec) {
+    (void)dc;
+    const uint64_t k0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * SFQ_ASM_RECS;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t k = k0; k < k0 + SFQ_ASM_RECS && k < nrec; k++)
+        sfq_assemble_record(metas, t, rec_chunk, bases, quals, hdrs, out, k, lane);
 }
 
 // Per-plane test hooks: one warp per record copies the record's line of ONE decoded plane (bases with the exception

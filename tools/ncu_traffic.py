@@ -31,7 +31,9 @@ def main():
         key = m.group(1).replace("(int)", "").replace("(bool)", "") if m else name
         d = per.setdefault((key, lid), {})
         try:
-            d[metric] = float(value.replace(",", ""))
+            v = float(value.replace(",", ""))
+            if v == v:                       # (a launch ncu was cut off in reports nan)
+                d[metric] = v
         except ValueError:
             pass
     best = {}
