@@ -97,6 +97,9 @@ struct sfq_ctx {
     cudaEvent_t gbins_ev = nullptr;         // k_gen_replay has read the partition lists: their memory may become the quality steps
     bool qch = false;                       // SFQ_QCH=1: the 4-lane quality decoder with the compact-header entry (7 sectors read, 2 dirtied per quality instead of 8 / 5;
                                             // A/B at 10 GB: DRAM traffic of the kernel -30 %, but five more loads and three selects per link: 943 ms against 915)
+    uint32_t rc_warps = 1;                  // SFQ_RC_WARPS=1..4: warps per CTA of the base coder chain sharing one reciprocal table (A/B r2af: 4 frees 24 KB of
+                                            // shared memory per SM and changes nothing: 576 against 571 ms per wave)
+    bool rc_q4 = true;                      // SFQ_RC_Q4=0: the quality coder chain with one lane per chunk-stream (k_rc_encode<1>) instead of four
     bool rec_global = false;                // SFQ_REC_GLOBAL=1 (see the header coder's launch)
     DevBuf rec_scr;
     int dec_sched = 0;                      // SFQ_DEC_SCHED=1: header decoder after the base decoder instead of beside it
@@ -477,7 +480,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     TRACED("k_gen_part", sg, (k_gen_part<<<nc, 32, gp_smem ? (size_t)36 << gp_bits : 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, nc))); LAUNCHED();
                     TRACED("k_gen_replay", sg, (k_gen_replay<<<ctx->sm_count, 32 * SFQ_GR_WARPS, SFQ_GR_SMEM, sg>>>(d_metas + c0, e2, d_e2c, nc))); LAUNCHED();
                     CK(cudaEventRecord(ctx->gbins_ev, sg));
-                    TRACED("k_rc_encode<0>", sg, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
+                    TRACED("k_rc_encode<0>", sg, (k_rc_encode<0><<<((nc + ctx->rc_lanes - 1) / ctx->rc_lanes + ctx->rc_warps - 1) / ctx->rc_warps, 32 * ctx->rc_warps, 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else if (two_phase) {
                     { TraceScope ts_(ctx, "k_gen_model", sg);
                     switch (ctx->gm_variant) {
@@ -487,7 +490,7 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     default: k_gen_model<8, 6><<<nwarp_blocks, 128, 0, sg>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, e2, d_e2c, level, nc); break;
                     } }
                     LAUNCHED();
-                    TRACED("k_rc_encode<0>", sg, (k_rc_encode<0><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
+                    TRACED("k_rc_encode<0>", sg, (k_rc_encode<0><<<((nc + ctx->rc_lanes - 1) / ctx->rc_lanes + ctx->rc_warps - 1) / ctx->rc_warps, 32 * ctx->rc_warps, 0, sg>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
                 } else {
                     k_encode<0><<<nb, 32, 0, sg>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
@@ -510,7 +513,8 @@ int compress_on_device(sfq_ctx *ctx, const uint8_t *d_text, size_t n, int level,
                     TRACED("k_qlt_model", q, (k_qlt_model<<<ctx->sm_count * 4, SFQ_QM_THREADS, 0, q>>>(d_metas + c0, ws_at(ws, c0), e2, d_e2c, c0))); LAUNCHED();
                     CK(cudaEventRecord(ctx->qtp_ev, q));
                     k_qlt_mark_escapes<<<nc, 256, 0, q>>>(d_metas + c0, e2, d_e2c, nc); LAUNCHED();
-                    TRACED("k_rc_encode<1>", q, (k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED();
+                    if (ctx->rc_q4) { TRACED("k_rc_encode_q4", q, (k_rc_encode_q4<<<(nc + 7) / 8, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc))); LAUNCHED(); }
+                    else { TRACED("k_rc_encode<1>", q, (k_rc_encode<1><<<(nc + ctx->rc_lanes - 1) / ctx->rc_lanes, 32, 0, q>>>(d_metas + c0, d_arenas + c0, abuf, e2, d_e2c, nc, ctx->rc_lanes))); LAUNCHED(); }
                 } else {
                     k_encode<1><<<(nc * SFQ_QG + 31) / 32, 32, 0, sq>>>(d_text, d_ls, d_metas + c0, d_arenas + c0, abuf, ws, level, nc, lanes); LAUNCHED();
                 }
@@ -1056,6 +1060,8 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_ENC_SCHED")) ctx->enc_sched = atoi(e);
     if (const char *e = getenv("SFQ_DEC_SCHED")) ctx->dec_sched = atoi(e);
     if (const char *e = getenv("SFQ_REC_GLOBAL")) ctx->rec_global = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_RC_Q4")) ctx->rc_q4 = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_RC_WARPS")) { int v = atoi(e); if (v >= 1 && v <= SFQ_RC_MAXW) ctx->rc_warps = (uint32_t)v; }
     if (const char *e = getenv("SFQ_QCH")) ctx->qch = atoi(e) != 0;
     if (const char *e = getenv("SFQ_MARKS")) ctx->marks = atoi(e) != 0;
     if (const char *e = getenv("SFQ_ALIAS")) ctx->alias_steps = atoi(e) != 0;

@@ -1075,17 +1075,74 @@ __device__ __forceinline__ uint32_t sfq_recip32(uint32_t d) {                   
     const uint32_t q = 0xffffffffu / d;
     return q + ((0xffffffffu - q * d) == d - 1u ? 1u : 0u);
 }
-template <int KIND>
+// The quality chain with four lanes per chunk-stream (eight streams per warp).  What is NOT part of the chain - fetching a
+// step, taking it apart, floor(2^32 / totFreq) (a real division: two thirds of the instructions of the one-lane form) - is done
+// for four consecutive steps at once, one per lane; the chain itself then takes each step's fields out of its lane with four
+// shuffles.  All four lanes run the coder (same state, same bytes: no divergence inside a group), only lane 0 stores.
 __global__ void __launch_bounds__(32)
+k_rc_encode_q4(SfqChunkMeta *metas, SfqArena *arenas, uint8_t *arena_buf, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c, uint32_t nchunks) {
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t g = threadIdx.x >> 2, sub = threadIdx.x & 3u;
+    const uint32_t c = blockIdx.x * 8u + g;
+    const bool on = c < nchunks && metas[c].status == SFQ_OK;
+    SfqEnc rc;
+    rc.reset();
+    uint32_t n = 0;
+    const uint64_t *steps = e2.qsteps, *es = e2.esteps;
+    if (on) {
+        rc.start(arena_buf + arenas[c].off[SFQ_S_QLT], arenas[c].cap[SFQ_S_QLT]);
+        n = metas[c].nquals;
+        steps = e2.qsteps + e2c[c].qoff;
+        es = e2.esteps + e2c[c].eoff;
+    }
+    rc.out.mute = !on || sub != 0u;
+    uint32_t nmax = n;
+    nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 4)); nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 8)); nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 16));
+    uint64_t cur = steps[sub], nxt = steps[4u + sub];            // (the arrays are padded: reading up to 8 steps past a stream's end is safe)
+    for (uint32_t i = 0; i < nmax; i += 4u) {
+        const uint64_t s = cur;
+        cur = nxt;
+        nxt = i < n ? steps[i + 8u + sub] : 0ull;                  // (a short stream beside long ones must not read on behind its own padding)
+        uint32_t tot = (uint32_t)(s >> 39) & 0x3fffffu;
+        if (tot < 64u) tot = 64u;                                 // tot >= 64 in every real step; the clamp only guards the read-ahead padding
+        const uint32_t inv = sfq_recip32(tot);
+        const uint32_t cum = (uint32_t)s & 0x3fffffu;
+        const uint32_t fe = ((uint32_t)(s >> 22) & 0x1ffffu) | ((uint32_t)(s >> 61) << 31);      // freq | escape-follows << 31
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; k++) {
+            const uint32_t ck = __shfl_sync(FULL, cum, k, 4), fk = __shfl_sync(FULL, fe, k, 4);
+            const uint32_t tk = __shfl_sync(FULL, tot, k, 4), ik = __shfl_sync(FULL, inv, k, 4);
+            if (i + k < n) {
+                rc.encode_scaled(ck, fk & 0x1ffffu, sfq_div_by(rc.range, tk, ik));
+                if (fk >> 31) {                                   // qlts.cpp:120-125
+                    const uint64_t x = *es++;
+                    rc.encode((uint32_t)x & 0xffffffu, (uint32_t)(x >> 24) & 0xffffu, (uint32_t)(x >> 40));
+                }
+            }
+        }
+    }
+    if (on && sub == 0u) {
+        rc.finish();
+        arenas[c].size[SFQ_S_QLT] = rc.out.n;
+        if (rc.out.overflow()) atomicCAS(&metas[c].status, (uint32_t)SFQ_OK, (uint32_t)SFQ_E_CAP);
+    }
+}
+
+// (Up to SFQ_RC_MAXW warps per CTA may share the base chain's 4 KB reciprocal table - SFQ_RC_WARPS; measured: no effect on the
+// kernels running beside it, so the launch keeps one-warp CTAs.)
+#define SFQ_RC_MAXW 4
+template <int KIND>
+__global__ void __launch_bounds__(32 * SFQ_RC_MAXW)
 k_rc_encode(SfqChunkMeta *metas, SfqArena *arenas, uint8_t *arena_buf, SfqEnc2Ws e2, const SfqEnc2Chunk *__restrict__ e2c,
             uint32_t nchunks, uint32_t lanes) {
-    __shared__ uint32_t lut[1024];
+    __shared__ uint32_t lut[KIND == 0 ? 1024 : 1];
     if (KIND == 0) {
-        for (uint32_t t = threadIdx.x; t < 1024; t += 32) lut[t] = t < 2 ? 0xffffffffu : sfq_recip32(t);
-        __syncwarp();
+        for (uint32_t t = threadIdx.x; t < 1024; t += blockDim.x) lut[t] = t < 2 ? 0xffffffffu : sfq_recip32(t);
+        __syncthreads();
     }
-    const uint32_t c = blockIdx.x * lanes + threadIdx.x;
-    if (threadIdx.x >= lanes || c >= nchunks) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes + lane;
+    if (lane >= lanes || c >= nchunks) return;
     SfqChunkMeta *m = &metas[c];
     if (m->status != SFQ_OK) return;
     SfqArena *ar = &arenas[c];
