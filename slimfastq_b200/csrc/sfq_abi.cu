@@ -100,6 +100,8 @@ struct sfq_ctx {
     uint32_t rc_warps = 1;                  // SFQ_RC_WARPS=1..4: warps per CTA of the base coder chain sharing one reciprocal table (A/B r2af: 4 frees 24 KB of
                                             // shared memory per SM and changes nothing: 576 against 571 ms per wave)
     bool rc_q4 = true;                      // SFQ_RC_Q4=0: the quality coder chain with one lane per chunk-stream (k_rc_encode<1>) instead of four
+    uint32_t dec_hold_us = 0;               // SFQ_DEC_HOLD_US: device-side delay in front of the base decoder of a large wave (A/B r2ah: with 100 us the base
+                                            // decoder's CTAs are packed two to an SM in 60 of 60 calls - the even spread needs the kernels to arrive TOGETHER)
     bool rec_global = false;                // SFQ_REC_GLOBAL=1 (see the header coder's launch)
     DevBuf rec_scr;
     int dec_sched = 0;                      // SFQ_DEC_SCHED=1: header decoder after the base decoder instead of beside it
@@ -780,6 +782,8 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
                     CK(cudaEventRecord(ctx->wave_ev[WEV * w + 4], sgd));
                     // base decoder: thread per chunk, `lanes` chunks per warp.  (SFQ_GDEC=1 runs the warp-converged form,
                     // 32 chunks per warp: correct, but its link waits for the slowest of 32 table reads - 45 % slower, kept for A/B.)
+                    // (A/B only, off by default: see k_hold_ns)
+                    if (!ctx->dec_gen_first && ctx->dec_hold_us && nc >= 4096u && ctx->plane_mask == 7) { k_hold_ns<<<1, 1, 0, sgd>>>((uint64_t)ctx->dec_hold_us * 1000ull); LAUNCHED(); }
                     if (!(ctx->plane_mask & 1)) {}
                     else if (ctx->gdec32 > 0) k_gen_decode32<<<(nc + 31) / 32, 32, 0, sgd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, nc);
                     else k_decode<0><<<(nb + dw - 1) / dw, 32 * dw, (spread == 1 || spread == 3) ? ctx->spread_smem[0] : 0, sgd>>>(d_in, d_dcs + c0, d_metas + c0, ws, t, pb, pq, ph, nc, lanes);
@@ -1061,6 +1065,7 @@ int sfq_create(sfq_ctx **out, int device) {
     if (const char *e = getenv("SFQ_DEC_SCHED")) ctx->dec_sched = atoi(e);
     if (const char *e = getenv("SFQ_REC_GLOBAL")) ctx->rec_global = atoi(e) != 0;
     if (const char *e = getenv("SFQ_RC_Q4")) ctx->rc_q4 = atoi(e) != 0;
+    if (const char *e = getenv("SFQ_DEC_HOLD_US")) { int v = atoi(e); if (v >= 0 && v <= 100000) ctx->dec_hold_us = (uint32_t)v; }
     if (const char *e = getenv("SFQ_RC_WARPS")) { int v = atoi(e); if (v >= 1 && v <= SFQ_RC_MAXW) ctx->rc_warps = (uint32_t)v; }
     if (const char *e = getenv("SFQ_QCH")) ctx->qch = atoi(e) != 0;
     if (const char *e = getenv("SFQ_MARKS")) ctx->marks = atoi(e) != 0;

@@ -295,6 +295,17 @@ k_gen_exceptions(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__
     sfq_gen_apply_exceptions(in, d.ssize, d.soff, &metas[c], ws.pw + (size_t)c * SFQ_PW_PER_CHUNK * SFQ_PW_WORDS, bases + d.base_plane + metas[c].big_bases);
 }
 
+// Holds a stream back for `ns` nanoseconds of device time (one thread).  An experiment on the packed-CTA outlier of the decode
+// wave (about one call in thirty the base decoder's CTAs sit two to an SM on half the SMs and that kernel runs 2.1x slower,
+// 1 423 against 671 ms): launched alone on an empty machine the block scheduler packs them every time (round 2, r2m), and held back
+// until the other two decoders are in place it ALSO packs them every time (r2ah: 60 of 60 calls) - the even spread of the
+// default launch comes from the three grids being distributed at the same moment.  Kept for A/B (SFQ_DEC_HOLD_US), off by default.
+__global__ void k_hold_ns(uint64_t ns) {
+    uint64_t t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+
 #define SFQ_DEC_MAXW 4                 // warps per CTA of the thread-per-chunk decoders (1..4; more per CTA = fewer, fatter CTAs)
 template <int ROLE>
 __global__ void __launch_bounds__(ROLE == 1 ? 64 : 32 * SFQ_DEC_MAXW)
