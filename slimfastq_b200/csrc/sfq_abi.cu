@@ -1110,6 +1110,13 @@ int sfq_create(sfq_ctx **out, int device) {
                   cudaFuncSetAttribute(k_qlt_decode<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess &&
                   cudaFuncSetAttribute(k_qlt_decode<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->spread_smem[1]) == cudaSuccess;
         if (!ok) { cudaGetLastError(); ctx->spread_smem[0] = ctx->spread_smem[1] = ctx->spread_smem[2] = 0; }
+        // SFQ_GEN_CARVEOUT=<percent>: preferred shared-memory carve-out of the base decoder.  With a carve-out that holds ONE of its
+        // CTAs (75 KB reserved + 8 KB static) but not two, the block scheduler cannot pack two onto an SM, and L1 keeps the rest
+        // (unlike a 112 KB reservation).  Needs at most one CTA per SM to exist: SFQ_DEC_FIT=1.
+        if (const char *e = getenv("SFQ_GEN_CARVEOUT")) {
+            const int pct = atoi(e);
+            if (pct >= 0 && pct <= 100 && cudaFuncSetAttribute(k_decode<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) cudaGetLastError();
+        }
     }
     *out = ctx;
     return 0;
