@@ -90,24 +90,42 @@ template <int LPC> struct SfqQdGeo {
 };
 template <int LPC> struct SfqQdModelT {
     typedef SfqQdGeo<LPC> G;
-    uint32_t f[G::SPL];
+    uint32_t pw[G::FW];                 // the frequencies as stored (u16 pairs): the state carried from step to step
+    uint32_t f[G::SPL];                 // ... and taken apart: rebuilt from pw at the top of every step (derive), so the common
+                                        // update is one add into a packed word instead of a 16-way select + repacking
     uint32_t sy[G::SW];
     uint32_t hdr, excl;
     __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int k = 0; k < G::FW; k++) pw[k] = 0;
 #pragma unroll
         for (int k = 0; k < G::SPL; k++) f[k] = 0;
 #pragma unroll
         for (int k = 0; k < G::SW; k++) sy[k] = 0;
         hdr = 0; excl = 0;
     }
+    __device__ __forceinline__ void derive() {
+#pragma unroll
+        for (int k = 0; k < G::FW; k++) { f[2 * k] = pw[k] & 0xffffu; f[2 * k + 1] = pw[k] >> 16; }
+    }
+    __device__ __forceinline__ void pack() {
+#pragma unroll
+        for (int k = 0; k < G::FW; k++) pw[k] = f[2 * k] | (f[2 * k + 1] << 16);
+    }
+    // freq[k] += inc in the packed words (the caller knows the sum stays below 2^16)
+    __device__ __forceinline__ void add_packed(uint32_t k, uint32_t inc) {
+        const uint32_t v = inc << (16u * (k & 1u));
+#pragma unroll
+        for (int q = 0; q < G::FW; q++) pw[q] += (k >> 1) == (uint32_t)q ? v : 0u;
+    }
     // word j (a compile-time index after unrolling) of the lane's vectors: stays in registers
     static __device__ __forceinline__ uint32_t word(const uint4 (&v)[G::NV], int j) {
         const uint4 &q = v[j >> 2];
         return (j & 3) == 0 ? q.x : (j & 3) == 1 ? q.y : (j & 3) == 2 ? q.z : q.w;
     }
-    __device__ __forceinline__ void unpack(const uint4 (&v)[G::NV]) {
+    __device__ __forceinline__ void unpack(const uint4 (&v)[G::NV]) {      // (pw only: derive() follows before f is used)
 #pragma unroll
-        for (int k = 0; k < G::FW; k++) { const uint32_t w = word(v, k); f[2 * k] = w & 0xffffu; f[2 * k + 1] = w >> 16; }
+        for (int k = 0; k < G::FW; k++) pw[k] = word(v, k);
 #pragma unroll
         for (int k = 0; k < G::SW; k++) sy[k] = word(v, G::FW + k);
         hdr = word(v, G::HW); excl = word(v, G::HW + 1);
@@ -115,8 +133,7 @@ template <int LPC> struct SfqQdModelT {
     __device__ __forceinline__ void store_freqs(uint32_t *e) const {
 #pragma unroll
         for (int q = 0; q < G::FW / 4; q++)
-            *reinterpret_cast<uint4 *>(e + 4 * q) = make_uint4(f[8 * q] | (f[8 * q + 1] << 16), f[8 * q + 2] | (f[8 * q + 3] << 16),
-                                                               f[8 * q + 4] | (f[8 * q + 5] << 16), f[8 * q + 6] | (f[8 * q + 7] << 16));
+            *reinterpret_cast<uint4 *>(e + 4 * q) = make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
     }
     __device__ __forceinline__ void store_syms(uint32_t *e) const {
         if (G::SW == 2) *reinterpret_cast<uint2 *>(e + G::FW) = make_uint2(sy[0], sy[1]);
@@ -254,7 +271,7 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
         if (CH) {                                                                                          \
             const uint32_t fw_[8] = {nv[1].x, nv[1].y, nv[1].z, nv[1].w, nv[2].x, nv[2].y, nv[2].z, nv[2].w}; \
             _Pragma("unroll")                                                                              \
-            for (int k_ = 0; k_ < 8; k_++) { m.f[(2 * k_) % SPL] = fw_[k_] & 0xffffu; m.f[(2 * k_ + 1) % SPL] = fw_[k_] >> 16; } \
+            for (int k_ = 0; k_ < 8; k_++) m.pw[k_ % G::FW] = fw_[k_];                                    \
             m.sy[0] = nv[3].x; m.sy[G::SW > 1 ? 1 : 0] = nv[3].y; m.sy[G::SW > 2 ? 2 : 0] = nv[3].z; m.sy[G::SW > 3 ? 3 : 0] = nv[3].w; \
             m.hdr = nv[0].x; ex1 = nv[0].y; ex2 = nv[0].z; ex3 = nv[0].w; key = nkey;                      \
             m.excl = l8 == 1u ? ex1 : l8 == 2u ? ex2 : l8 == 3u ? ex3 : 0u;                                \
@@ -295,6 +312,7 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
                 if (!vb) break;
             }
         }
+        m.derive();
         const bool act = live;
         if (SPEC) {
             // The next context is only known once this symbol is: its model is requested below, after the search, and its
@@ -418,7 +436,7 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
 
         // ---------------------------------------------------------------- update_freq (log64_ranger.hpp:69-87)
         const uint32_t slot = SPL * hl + hk;
-        bool skip = false, wide = false;
+        bool skip = false, wide = false, halved = false, repack = false;
         uint32_t fn = f, tot2 = tot;
         if (__any_sync(FULL, act && f > 65472u - 6u)) {
             const bool hv = act && f > 65472u - 6u;
@@ -439,7 +457,7 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
                 if (l8) m.excl = inc - ls;
                 tot2 = total;
                 fn = f >> 1;
-                wide = true;
+                wide = true; halved = true; repack = true;
             }
         }
         const bool upd = act && !skip;
@@ -450,7 +468,7 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
             if (l8 > hl) m.excl += 6u;
             if (CH) { ex1 += hl < 1u ? 6u : 0u; ex2 += hl < 2u ? 6u : 0u; ex3 += hl < 3u ? 6u : 0u; }
         }
-        if (mine) m.set_freq(hk, fn);
+        if (mine) { if (halved) m.set_freq(hk, fn); else m.add_packed(hk, 6u); }      // (f[] of this lane is stale for slot hk from here on, unless halved)
         uint32_t cnt2 = count;
         const bool cand = upd && slot != 0u;                                 // `++count` is not evaluated for slot 0
         if (cand) cnt2 = (count + 1u) & 0xffu;
@@ -483,24 +501,24 @@ k_qlt_decode(const uint8_t *__restrict__ in, const SfqDecChunk *__restrict__ dc,
                         m.set_freq(hk - 1u, fn); m.set_freq(hk, fprev);
                         m.set_sym_byte(hk - 1u, byte_lo); m.set_sym_byte(hk, byte_hi);
                     }
-                    syms_dirty = true;
+                    syms_dirty = true; repack = true;
                 }
                 if (hk == 0u && l8 + 1u == hl) {
                     m.f[SPL - 1] = fn;
                     m.set_sym_byte(SPL - 1u, byte_lo);
-                    syms_dirty = true; wide = true;
+                    syms_dirty = true; wide = true; repack = true;
                 }
             }
         }
+        if (repack) m.pack();                // rare: a halving or a swap rewrote f[] (every slot of it is current in those lanes)
         if (act) {
             m.hdr = tot2 | (cnt2 << 24);
             uint32_t *e = tab + (size_t)h * 64u;
             if (CH) {
                 if (wide || mine) {
                     uint32_t *fe = e + 8 + 8 * l8;
-                    *reinterpret_cast<uint4 *>(fe) = make_uint4(m.f[0] | (m.f[1] << 16), m.f[2] | (m.f[3] << 16), m.f[4] | (m.f[5] << 16), m.f[6] | (m.f[7] << 16));
-                    *reinterpret_cast<uint4 *>(fe + 4) = make_uint4(m.f[8 % SPL] | (m.f[9 % SPL] << 16), m.f[10 % SPL] | (m.f[11 % SPL] << 16),
-                                                                    m.f[12 % SPL] | (m.f[13 % SPL] << 16), m.f[14 % SPL] | (m.f[15 % SPL] << 16));
+                    *reinterpret_cast<uint4 *>(fe) = make_uint4(m.pw[0], m.pw[1 % G::FW], m.pw[2 % G::FW], m.pw[3 % G::FW]);
+                    *reinterpret_cast<uint4 *>(fe + 4) = make_uint4(m.pw[4 % G::FW], m.pw[5 % G::FW], m.pw[6 % G::FW], m.pw[7 % G::FW]);
                 }
                 if (syms_dirty) *reinterpret_cast<uint4 *>(e + 40 + 4 * l8) = make_uint4(m.sy[0], m.sy[G::SW > 1 ? 1 : 0], m.sy[G::SW > 2 ? 2 : 0], m.sy[G::SW > 3 ? 3 : 0]);
                 if (l8 == 0) {
