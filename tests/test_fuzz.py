@@ -92,3 +92,27 @@ def test_reference_oracle_and_kernel_routines_agree(oracle, seed):
         chunks = emul.compress(data, level, 4096, two_phase=not bool(seed & 2))
         check_container_against_oracle(oracle, data, chunks, level)
         assert emul.decompress(chunks) == oracle.decode(mine)
+
+
+@pytest.mark.parametrize("seed", SEEDS[::3])
+def test_interchange_with_the_reference_file_format(oracle, seed):
+    """What the kernels' routines write, exported to the reference's page file, the unmodified binary must decode; what the
+    binary writes, imported, the kernels' decoder routines must decode (format conversions are host code: no GPU needed)."""
+    import tempfile
+
+    import slimfastq_b200 as S
+    from test_reference_format import ref_compress, ref_decompress
+
+    if not O.have_ref():
+        pytest.skip("oracle/_ref/slimfastq is not built")
+    data = random_fastq(seed)
+    level = 1 + seed % 4
+    try:
+        want = oracle.decode(oracle.encode(data, level))          # the reference's own round trip of this file (lossy cases included)
+    except Exception:
+        pytest.skip("rejected input (covered above)")
+    with tempfile.TemporaryDirectory() as d:
+        ours = emul.compress(data, level, 1 << 40, two_phase=bool(seed & 1))
+        assert ref_decompress(S.export_reference(ours, "in.fq"), d) == want
+        theirs = ref_compress(data, level, d)
+        assert emul.decompress(S.import_reference(theirs)) == want
