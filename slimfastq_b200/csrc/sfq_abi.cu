@@ -632,9 +632,8 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
     for (uint32_t c = 0; c < nchunks; c++) {
         const SfqBlobHeader &b = blobs[c];
         const uint64_t off = index[c];
-        if (b.magic != SFQ_BLOB_MAGIC || off + sfq_blob_size(&b) > n || b.level < 1 || b.level > 4 ||
-            b.nrec == 0 || b.rec_first_len > 399)       // (rec_first_len 0: every record of the chunk is oversized)
-            return fail(ctx, SFQ_ERR_FORMAT, "chunk %u: bad blob header", c);
+        const int bad = sfq_blob_check(&b, off, n);
+        if (bad == 2) return fail(ctx, SFQ_ERR_FORMAT, "chunk %u: bad blob header", c);
         SfqChunkMeta &m = metas[c];
         memset(&m, 0, sizeof m);
         m.text_len = b.text_len; m.out_len = b.out_len; m.nrec = b.nrec; m.nbases = b.nbases; m.nquals = b.nquals;
@@ -651,10 +650,7 @@ int decompress_on_device(sfq_ctx *ctx, const uint8_t *d_in, size_t n, const SfqF
         nrec += b.nrec; nb += d.base_cap; nq += d.qual_cap; nh += d.hdr_cap; no += b.out_len;
         max_bases = std::max<uint64_t>(max_bases, b.nbases);
         max_level = std::max(max_level, (int)b.level);
-        // a record prints at least "@h\nb\n+\nq\n": reject headers whose counts cannot match their out_len
-        if (!(b.pad & SFQ_BLOB_IMPORTED) && (b.out_len < 6ull * b.nrec || b.nbig > b.nrec ||
-                                             (uint64_t)b.nbases + b.nquals + b.hdr_bytes + b.big_bases + b.big_quals + b.big_hdr > b.out_len))
-            return fail(ctx, SFQ_ERR_FORMAT, "chunk %u: inconsistent blob header", c);
+        if (bad) return fail(ctx, SFQ_ERR_FORMAT, "chunk %u: inconsistent blob header", c);
     }
     if (no > out_cap) return fail(ctx, SFQ_ERR_SPACE, "output buffer too small (need %llu bytes)", (unsigned long long)no);
     CK(ctx->blob_off.ensure(nchunks * 8ull));          // reused as per-chunk output sizes / offsets

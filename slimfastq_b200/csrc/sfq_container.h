@@ -73,3 +73,19 @@ static inline uint64_t sfq_blob_size(const SfqBlobHeader *b) {
     for (int k = 0; k < SFQ_NSTREAMS; k++) s += b->ssize[k];
     return s;
 }
+
+// Framing checks of an untrusted container, shared by the library (csrc/sfq_abi.cu) and the test emulation so that both
+// refuse the same files.  0 = fine; 1 = corrupt index; 2 = bad blob header; 3 = blob header whose counts cannot match.
+static inline int sfq_index_check(const SfqFileHeader *fh, size_t n) {
+    return (fh->nchunks == 0 || fh->nchunks > 0x7fffffffull || fh->index_off > n || n - fh->index_off < fh->nchunks * 8) ? 1 : 0;
+}
+static inline int sfq_blob_check(const SfqBlobHeader *b, uint64_t off, size_t n) {
+    if (b->magic != SFQ_BLOB_MAGIC || off > n || sfq_blob_size(b) > n - off || b->level < 1 || b->level > 4 ||
+        b->nrec == 0 || b->rec_first_len > 399)             // (rec_first_len 0: every record of the chunk is oversized)
+        return 2;
+    // a record prints at least "@h\nb\n+\nq\n": reject headers whose counts cannot match their out_len
+    if (!(b->pad & SFQ_BLOB_IMPORTED) && (b->out_len < 6ull * b->nrec || b->nbig > b->nrec ||
+                                          (uint64_t)b->nbases + b->nquals + b->hdr_bytes + b->big_bases + b->big_quals + b->big_hdr > b->out_len))
+        return 3;
+    return 0;
+}

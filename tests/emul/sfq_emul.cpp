@@ -168,11 +168,16 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **ou
     *status_out = 0;
     if (!sfq_is_chunked_container(sfq, n)) { *status_out = SFQ_E_CORRUPT; return 1; }
     SfqFileHeader h; memcpy(&h, sfq, sizeof h);
+    if (sfq_index_check(&h, n)) { *status_out = SFQ_E_CORRUPT; return 1; }          // the library's own framing checks (sfq_container.h)
     std::vector<uint8_t> text;
     for (uint64_t c = 0; c < h.nchunks; c++) {
         uint64_t off; memcpy(&off, sfq + h.index_off + 8 * c, 8);
+        if (off > n || n - off < sizeof(SfqBlobHeader)) { *status_out = SFQ_E_CORRUPT; return 1; }
         SfqBlobHeader b; memcpy(&b, sfq + off, sizeof b);
-        if (b.magic != SFQ_BLOB_MAGIC) { *status_out = SFQ_E_CORRUPT; return 1; }
+        if (sfq_blob_check(&b, off, n)) { *status_out = SFQ_E_CORRUPT; return 1; }
+        // (the library is bounded by the caller's output buffer and by device memory; this harness by a fixed limit)
+        if (b.out_len > (1ull << 28) || b.nrec > (1u << 24) || b.nbases > (1u << 28) || b.nquals > (1u << 28) || b.hdr_bytes > (1u << 28) ||
+            b.big_bases > (1u << 28) || b.big_quals > (1u << 28) || b.big_hdr > (1u << 28)) { *status_out = SFQ_E_CORRUPT; return 1; }
         SfqChunkMeta m; memset(&m, 0, sizeof m);
         m.nrec = b.nrec; m.nbases = b.nbases; m.nquals = b.nquals; m.hdr_bytes = b.hdr_bytes; m.llen = b.llen;
         m.solid = b.solid; m.two_id = b.two_id; m.n_byte = b.n_byte; m.text_len = b.text_len; m.out_len = b.out_len;
@@ -185,6 +190,7 @@ extern "C" int sfq_emul_decompress(const uint8_t *sfq_in, size_t n, uint8_t **ou
         void *gt = calloc(1, sfq_gbuckets_bytes(level, hbits));
         uint32_t *qt = (uint32_t *)calloc(1, sfq_qtable_bytes(level));
         uint32_t *pw = (uint32_t *)calloc(1, sfq_pwpool_bytes());
+        if (!gt || !qt || !pw) { free(gt); free(qt); free(pw); *status_out = SFQ_E_CORRUPT; return 1; }   // (a wild table hint: the library's cudaMalloc fails the same way)
         static uint32_t lut[SFQ_B2_LUT];
         sfq_b2_lut_fill(lut, 0, 1);
         std::vector<uint32_t> llen(m.nrec), qlen(m.nrec), hlen(m.nrec);

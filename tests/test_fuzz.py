@@ -116,3 +116,59 @@ def test_interchange_with_the_reference_file_format(oracle, seed):
         assert ref_decompress(S.export_reference(ours, "in.fq"), d) == want
         theirs = ref_compress(data, level, d)
         assert emul.decompress(S.import_reference(theirs)) == want
+
+
+CORRUPT = r"""
+import random, resource, sys
+resource.setrlimit(resource.RLIMIT_AS, (16 << 30, 16 << 30))      # a wild size field must fail an allocation, not take the machine
+sys.path.insert(0, sys.argv[2]); sys.path.insert(0, sys.argv[3])
+import slimfastq_b200 as S
+import emul, test_fuzz
+from slimfastq_b200 import container as K
+rnd = random.Random(int(sys.argv[1]))
+data = test_fuzz.random_fastq(int(sys.argv[1]))
+blob = emul.compress(data, 3, 1 << 40)
+ref = S.export_reference(blob, "in.fq")
+ok = err = 0
+for trial in range(120):
+    for name, buf, fn in (("import", ref, S.import_reference), ("export", blob, lambda b: S.export_reference(b, "x.fq")),
+                          ("size", blob, S.decompressed_size), ("parse", blob, K.parse), ("decode", blob, emul.decompress)):
+        b = bytearray(buf)
+        mode = rnd.randrange(5)
+        if mode == 0:
+            for _ in range(rnd.randrange(1, 6)):
+                b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        elif mode == 1:
+            b = b[: rnd.randrange(0, len(b))]
+        elif mode == 2:
+            p = rnd.randrange(len(b)); b[p:p + 8] = rnd.randbytes(8)
+        elif mode == 3:
+            p = rnd.randrange(min(len(b), 300)); b[p:p + 4] = (0xFFFFFFFF).to_bytes(4, "little")
+        else:
+            p = 80 + rnd.randrange(132); b[p] = rnd.randrange(256)        # a field of the first blob header / of the info page
+        try:
+            r = fn(bytes(b)); ok += 1
+            if name == "import":
+                try:
+                    emul.decompress(r)
+                except Exception:
+                    pass
+        except Exception:
+            err += 1
+print("survived", ok, err)
+"""
+
+
+@pytest.mark.parametrize("seed", [0, 7])
+def test_corrupt_containers_never_crash_the_host_code(seed):
+    """Bit flips, truncations and wild counts in a container / a reference-format file: the host-side format code (import,
+    export, size query, parser) and the decoder routines behind the library's own framing checks (sfq_index_check /
+    sfq_blob_check, shared with the test emulation) must answer with an error or an answer, never with a crash - run in a
+    child process so that a crash is a test failure instead of the end of the test run."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-c", CORRUPT, str(seed), os.path.dirname(here), here], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "survived" in r.stdout, (r.returncode, r.stderr[-1500:])
